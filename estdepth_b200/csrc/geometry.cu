@@ -1,0 +1,115 @@
+// Device-side camera algebra: one tiny kernel per (target, source) pair replaces the reference's chains of
+// torch.inverse / matmul (each a cuSOLVER/cuBLAS launch plus a host-syncing error check; 60 per window,
+// SURVEY.md section 2.4).  Inputs are fp32 device tensors; the algebra runs in fp64 and is rounded once.
+#include "common.cuh"
+
+namespace estd {
+
+template <int N>
+__device__ void invert(const double* a, double* inv) {
+    double m[N][2 * N];
+    for (int r = 0; r < N; ++r)
+        for (int c = 0; c < N; ++c) { m[r][c] = a[r * N + c]; m[r][N + c] = (r == c) ? 1.0 : 0.0; }
+    for (int col = 0; col < N; ++col) {
+        int piv = col;
+        double best = fabs(m[col][col]);
+        for (int r = col + 1; r < N; ++r) if (fabs(m[r][col]) > best) { best = fabs(m[r][col]); piv = r; }
+        if (piv != col) for (int c = 0; c < 2 * N; ++c) { double t = m[col][c]; m[col][c] = m[piv][c]; m[piv][c] = t; }
+        double d = 1.0 / m[col][col];
+        for (int c = 0; c < 2 * N; ++c) m[col][c] *= d;
+        for (int r = 0; r < N; ++r) {
+            if (r == col) continue;
+            double f = m[r][col];
+            for (int c = 0; c < 2 * N; ++c) m[r][c] -= f * m[col][c];
+        }
+    }
+    for (int r = 0; r < N; ++r) for (int c = 0; c < N; ++c) inv[r * N + c] = m[r][N + c];
+}
+
+__device__ void matmul4(const double* a, const double* b, double* c) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+            c[i * 4 + j] = s;
+        }
+}
+
+// proj = [K * E[:3,:4] ; E[3,:]]   (model_hybrid.py:83-88)
+__device__ void projection(const double* K, const double* E, double* P) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 3; ++k) s += K[i * 3 + k] * E[k * 4 + j];
+            P[i * 4 + j] = s;
+        }
+    for (int j = 0; j < 4; ++j) P[12 + j] = E[12 + j];
+}
+
+__global__ void homography_setup_kernel(const float* __restrict__ ref_pose, const float* __restrict__ src_pose,
+                                        const float* __restrict__ cam_intr, float* __restrict__ out12) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double Pr[16], Ps[16], K[9], Er[16], Es[16], R[16], S[16], Rinv[16], M[16];
+    for (int i = 0; i < 16; ++i) { Pr[i] = ref_pose[i]; Ps[i] = src_pose[i]; }
+    for (int i = 0; i < 9; ++i) K[i] = cam_intr[i];
+    invert<4>(Pr, Er);
+    invert<4>(Ps, Es);
+    projection(K, Er, R);
+    projection(K, Es, S);
+    invert<4>(R, Rinv);
+    matmul4(S, Rinv, M);                                     // homo_utils.py:469
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) out12[i * 3 + j] = (float)M[i * 4 + j];
+        out12[9 + i] = (float)M[i * 4 + 3];
+    }
+}
+
+__global__ void homography_from_proj_kernel(const float* __restrict__ src_proj, const float* __restrict__ ref_proj,
+                                            float* __restrict__ out12) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double S[16], R[16], Rinv[16], M[16];
+    for (int i = 0; i < 16; ++i) { S[i] = src_proj[i]; R[i] = ref_proj[i]; }
+    invert<4>(R, Rinv);
+    matmul4(S, Rinv, M);
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) out12[i * 3 + j] = (float)M[i * 4 + j];
+        out12[9 + i] = (float)M[i * 4 + 3];
+    }
+}
+
+__global__ void volume_warp_setup_kernel(const float* __restrict__ pose_i, const float* __restrict__ pose_j,
+                                         const float* __restrict__ cam_intr, float* __restrict__ out30) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double Pi[16], Pj[16], K[9], Kinv[9], Piinv[16], rel[16], Minv[16];
+    for (int i = 0; i < 16; ++i) { Pi[i] = pose_i[i]; Pj[i] = pose_j[i]; }
+    for (int i = 0; i < 9; ++i) K[i] = cam_intr[i];
+    invert<3>(K, Kinv);                                      // homo_utils.py:51
+    invert<4>(Pi, Piinv);
+    matmul4(Pj, Piinv, rel);                                 // hybrid_depth_decoder.py:235 (quirk Q7)
+    invert<4>(rel, Minv);                                    // homo_utils.py:258
+    for (int i = 0; i < 9; ++i) out30[i] = (float)Kinv[i];
+    for (int i = 0; i < 12; ++i) out30[9 + i] = (float)Minv[i];
+    for (int i = 0; i < 9; ++i) out30[21 + i] = (float)K[i];
+}
+
+}  // namespace estd
+
+extern "C" int estd_homography_setup(const float* ref_pose, const float* src_pose, const float* cam_intr,
+                                     float* out12, void* stream) {
+    ESTD_REQUIRE(ref_pose && src_pose && cam_intr && out12, "estd_homography_setup: null pointer");
+    estd::homography_setup_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ref_pose, src_pose, cam_intr, out12);
+    return estd::check_launch("estd_homography_setup");
+}
+
+extern "C" int estd_homography_from_proj(const float* src_proj, const float* ref_proj, float* out12, void* stream) {
+    ESTD_REQUIRE(src_proj && ref_proj && out12, "estd_homography_from_proj: null pointer");
+    estd::homography_from_proj_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(src_proj, ref_proj, out12);
+    return estd::check_launch("estd_homography_from_proj");
+}
+
+extern "C" int estd_volume_warp_setup(const float* pose_i, const float* pose_j, const float* cam_intr,
+                                      float* out30, void* stream) {
+    ESTD_REQUIRE(pose_i && pose_j && cam_intr && out30, "estd_volume_warp_setup: null pointer");
+    estd::volume_warp_setup_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pose_i, pose_j, cam_intr, out30);
+    return estd::check_launch("estd_volume_warp_setup");
+}

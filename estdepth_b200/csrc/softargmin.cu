@@ -1,0 +1,143 @@
+// K4: 1x1x1 logit head + softmax over depth + expectation (soft-argmin) at quarter resolution, written
+// `up` x `up` replicated, plus the small layout conversions at the boundary.
+//
+// Reference seam: nn.Conv3d(16,1,1,bias=True) of stereo_head{0,1} (hybrid_depth_decoder.py:106,111),
+// F.interpolate(scale_factor=4) (:202,259,359,379) and depthlayer (:33-38).  The reference up-samples the logits 16x
+// and then runs softmax / sum / max over a [T,64,480,640] tensor (~0.5 GB of traffic per target); nearest up-sampling
+// commutes with a per-pixel softmax (quirk Q11), so this kernel reads the 16-channel hidden volume once, writes the
+// quarter-resolution logits (needed by the 2-D refinement, :268) and replicates depth / prob / argmax.
+#include "common.cuh"
+
+namespace estd {
+
+__global__ void __launch_bounds__(128) head_softargmin_kernel(const float* __restrict__ hidden, const float* __restrict__ head_w,
+                                                              const float* __restrict__ head_b, const float* __restrict__ logits_in,
+                                                              const float* __restrict__ depth_values, float* __restrict__ logits_out,
+                                                              float* __restrict__ depth_out, float* __restrict__ prob_out,
+                                                              int* __restrict__ argmax_out, int D, int H, int W, int up) {
+    const int HW = H * W;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int h = p / W, w = p - h * W;
+    const size_t vox = (size_t)D * HW;
+    float4 hw4[4];
+    float bias = 0.0f;
+    if (hidden) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hw4[j] = ldg4(head_w + j * 4);
+        bias = __ldg(head_b);
+    }
+    float m = -INFINITY, s = 0.0f, ws = 0.0f;
+    int best = 0;
+    for (int d = 0; d < D; ++d) {
+        float l;
+        if (hidden) {
+            l = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 x = ldg4(hidden + (j * vox + (size_t)d * HW + p) * 4);
+                l = fmaf(x.x, hw4[j].x, l); l = fmaf(x.y, hw4[j].y, l);
+                l = fmaf(x.z, hw4[j].z, l); l = fmaf(x.w, hw4[j].w, l);
+            }
+            l += bias;
+        } else {
+            l = __ldg(logits_in + (size_t)d * HW + p);
+        }
+        if (logits_out) logits_out[(size_t)d * HW + p] = l;
+        const float dv = __ldg(depth_values + d);
+        if (l > m) {                                   // strict: first maximum wins, like torch.max
+            const float scale = expf(m - l);           // exp(-inf) = 0 on the first plane
+            s = fmaf(s, scale, 1.0f);
+            ws = fmaf(ws, scale, dv);
+            m = l;
+            best = d;
+        } else {
+            const float e = expf(l - m);
+            s += e;
+            ws = fmaf(e, dv, ws);
+        }
+    }
+    const float depth = __fdiv_rn(ws, s);
+    const float prob = __fdiv_rn(1.0f, s);
+    const int WU = W * up;
+    for (int r = 0; r < up; ++r) {
+        const size_t row = ((size_t)(h * up + r)) * WU + (size_t)w * up;
+        if (up == 4) {
+            if (depth_out) st4(depth_out + row, make_float4(depth, depth, depth, depth));
+            if (prob_out) st4(prob_out + row, make_float4(prob, prob, prob, prob));
+            if (argmax_out) *reinterpret_cast<int4*>(argmax_out + row) = make_int4(best, best, best, best);
+        } else {
+            for (int c = 0; c < up; ++c) {
+                if (depth_out) depth_out[row + c] = depth;
+                if (prob_out) prob_out[row + c] = prob;
+                if (argmax_out) argmax_out[row + c] = best;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) vol4_to_ncdhw_kernel(const float* __restrict__ vol4, float* __restrict__ ncdhw,
+                                                            size_t vox, size_t total) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t j = i / vox, v = i - j * vox;
+        const float4 x = ldg4(vol4 + i * 4);
+        float* o = ncdhw + (j * 4) * vox + v;
+        o[0] = x.x; o[vox] = x.y; o[2 * vox] = x.z; o[3 * vox] = x.w;
+    }
+}
+
+__global__ void __launch_bounds__(256) ncdhw_to_vol4_kernel(const float* __restrict__ ncdhw, float* __restrict__ vol4,
+                                                            size_t vox, size_t total) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t j = i / vox, v = i - j * vox;
+        const float* s = ncdhw + (j * 4) * vox + v;
+        st4(vol4 + i * 4, make_float4(__ldg(s), __ldg(s + vox), __ldg(s + 2 * vox), __ldg(s + 3 * vox)));
+    }
+}
+
+__global__ void __launch_bounds__(256) scalar_to_vol4_kernel(const float* __restrict__ in, float* __restrict__ out, size_t vox) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vox; i += (size_t)gridDim.x * blockDim.x)
+        st4(out + i * 4, make_float4(__ldg(in + i), 0.0f, 0.0f, 0.0f));
+}
+
+static int ew_blocks(size_t total) {
+    size_t b = (total + 255) / 256;
+    return (int)(b < 148 * 16 ? b : 148 * 16);
+}
+
+}  // namespace estd
+
+extern "C" int estd_head_softargmin(const float* hidden_vol4, const float* head_w, const float* head_b, const float* logits_in,
+                                    const float* depth_values, float* logits_out, float* depth_out, float* prob_out,
+                                    int* argmax_out, int D, int H, int W, int up, void* stream) {
+    using namespace estd;
+    ESTD_REQUIRE(depth_values && D > 0 && H > 0 && W > 0 && up >= 1 && up <= 8, "estd_head_softargmin: bad arguments");
+    ESTD_REQUIRE((hidden_vol4 && head_w && head_b) || logits_in, "estd_head_softargmin: need hidden+head or logits_in");
+    if (up == 4) ESTD_REQUIRE((!depth_out || aligned16(depth_out)) && (!prob_out || aligned16(prob_out)) &&
+                              (!argmax_out || aligned16(argmax_out)), "estd_head_softargmin: outputs must be 16-byte aligned");
+    head_softargmin_kernel<<<(H * W + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        hidden_vol4, head_w, head_b, hidden_vol4 ? nullptr : logits_in, depth_values, logits_out, depth_out, prob_out,
+        argmax_out, D, H, W, up);
+    return check_launch("estd_head_softargmin");
+}
+
+extern "C" int estd_vol4_to_ncdhw(const float* vol4, float* ncdhw, int C, int D, int H, int W, void* stream) {
+    ESTD_REQUIRE(vol4 && ncdhw && C > 0 && (C % 4) == 0 && D > 0 && H > 0 && W > 0, "estd_vol4_to_ncdhw: bad arguments");
+    const size_t vox = (size_t)D * H * W, total = vox * (C / 4);
+    estd::vol4_to_ncdhw_kernel<<<estd::ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(vol4, ncdhw, vox, total);
+    return estd::check_launch("estd_vol4_to_ncdhw");
+}
+
+extern "C" int estd_ncdhw_to_vol4(const float* ncdhw, float* vol4, int C, int D, int H, int W, void* stream) {
+    ESTD_REQUIRE(vol4 && ncdhw && C > 0 && (C % 4) == 0 && D > 0 && H > 0 && W > 0, "estd_ncdhw_to_vol4: bad arguments");
+    const size_t vox = (size_t)D * H * W, total = vox * (C / 4);
+    estd::ncdhw_to_vol4_kernel<<<estd::ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(ncdhw, vol4, vox, total);
+    return estd::check_launch("estd_ncdhw_to_vol4");
+}
+
+extern "C" int estd_scalar_to_vol4(const float* dhw, float* vol4_1chunk, int D, int H, int W, void* stream) {
+    ESTD_REQUIRE(dhw && vol4_1chunk && D > 0 && H > 0 && W > 0, "estd_scalar_to_vol4: bad arguments");
+    const size_t vox = (size_t)D * H * W;
+    estd::scalar_to_vol4_kernel<<<estd::ew_blocks(vox), 256, 0, (cudaStream_t)stream>>>(dhw, vol4_1chunk, vox);
+    return estd::check_launch("estd_scalar_to_vol4");
+}

@@ -1,0 +1,173 @@
+"""2-D feeder networks of the ESTDepth hot path.
+
+These stay on cuDNN (they are marked "kept" in the scope table): the B200-native work of this
+package is the 3-D plane-sweep / matching / EST path that consumes their outputs.  The modules
+below only exist so that
+
+  * ``state_dict`` key names and shapes are identical to the reference's
+    (``matchingFeature.*``   <- networks/psm_submodule.py:40-116,
+     ``semanticFeature.encoder.*`` <- hybrid_models/resnet_encoder.py:17-51,
+     ``CostRegNet.upconv_*`` / ``dispconv_*`` <- hybrid_models/hybrid_depth_decoder.py:56-75),
+    so a checkpoint written by the reference's ``train_hybrid.py`` loads with ``strict=True``;
+  * the 2-D arithmetic is the same sequence of conv / BN(eval) / ReLU / pool / resize ops.
+
+Parameter containers are registered under the reference's attribute names; the forward code is
+written against small functional helpers rather than mirroring the reference's module nesting.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import torchvision.models as tvm
+
+
+def _conv_bn(cin, cout, k, stride, pad, dilation):
+    """conv(bias=False)+BN pair; padding rule of networks/layers_op.py:10-14 (pad = dilation if dilation>1)."""
+    return nn.Sequential(
+        nn.Conv2d(cin, cout, k, stride=stride, padding=dilation if dilation > 1 else pad,
+                  dilation=dilation, bias=False),
+        nn.BatchNorm2d(cout))
+
+
+class _ResidualUnit(nn.Module):
+    """Two conv+BN with ReLU after the first only; NO ReLU after the add (psm_submodule.py:14-37, quirk Q12)."""
+
+    def __init__(self, cin, cout, stride, pad, dilation, project):
+        super().__init__()
+        self.conv1 = nn.Sequential(_conv_bn(cin, cout, 3, stride, pad, dilation), nn.ReLU(inplace=True))
+        self.conv2 = _conv_bn(cout, cout, 3, 1, pad, dilation)
+        self.downsample = project
+
+    def forward(self, x):
+        y = self.conv2(self.conv1(x))
+        return y + (x if self.downsample is None else self.downsample(x))
+
+
+def _stage(cin, cout, n, stride, pad, dilation):
+    project = None
+    if stride != 1 or cin != cout:
+        project = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride, bias=False), nn.BatchNorm2d(cout))
+    units = [_ResidualUnit(cin, cout, stride, pad, dilation, project)]
+    units += [_ResidualUnit(cout, cout, 1, pad, dilation, None) for _ in range(n - 1)]
+    return nn.Sequential(*units)
+
+
+class MatchingFeatureNet(nn.Module):
+    """PSMNet-style 1/4-resolution, 32-channel matching features; output is a raw conv (no BN/ReLU).
+
+    Reference: networks/psm_submodule.py:40-116.  Stage table (channels, units, stride, dilation):
+    (32,3,1,1) (64,16,2,1) (128,3,1,1) (128,3,1,2); SPP pools 32/16/8/4; fuse 320->128->32.
+    """
+
+    def __init__(self):
+        super().__init__()
+        stem = []
+        for cin, stride in ((3, 2), (32, 1), (32, 1)):
+            stem += [_conv_bn(cin, 32, 3, stride, 1, 1), nn.ReLU(inplace=True)]
+        self.firstconv = nn.Sequential(*stem)
+        self.layer1 = _stage(32, 32, 3, 1, 1, 1)
+        self.layer2 = _stage(32, 64, 16, 2, 1, 1)
+        self.layer3 = _stage(64, 128, 3, 1, 1, 1)
+        self.layer4 = _stage(128, 128, 3, 1, 1, 2)
+        for idx, win in ((1, 32), (2, 16), (3, 8), (4, 4)):
+            setattr(self, "branch%d" % idx, nn.Sequential(
+                nn.AvgPool2d((win, win), stride=(win, win)), _conv_bn(128, 32, 1, 1, 0, 1), nn.ReLU(inplace=True)))
+        self.lastconv = nn.Sequential(_conv_bn(320, 128, 3, 1, 1, 1), nn.ReLU(inplace=True),
+                                      nn.Conv2d(128, 32, 1, bias=False))
+        self.out_channels = [32]
+
+    def forward(self, x):
+        x = self.layer1(self.firstconv(x))
+        quarter = self.layer2(x)
+        deep = self.layer4(self.layer3(quarter))
+        size = deep.shape[-2:]
+        # F.upsample(mode='bilinear') of the reference == interpolate(align_corners=False)
+        pyramid = [F.interpolate(getattr(self, "branch%d" % i)(deep), size=size, mode="bilinear", align_corners=False)
+                   for i in (4, 3, 2, 1)]
+        return self.lastconv(torch.cat([quarter, deep] + pyramid, dim=1))
+
+
+class ContextEncoder(nn.Module):
+    """torchvision ResNet trunk returning the 5 feature maps at /2 ... /32 (resnet_encoder.py:17-51).
+
+    The reference asks torchvision for ImageNet weights; there is no network here and eval always loads
+    a checkpoint afterwards (eval_hybrid.py:328-333), so the trunk is created un-initialised
+    (``weights=None``).  The unused ``fc`` layer is kept because it is part of the checkpoint.
+    """
+
+    def __init__(self, num_layers):
+        super().__init__()
+        ctor = {18: tvm.resnet18, 34: tvm.resnet34, 50: tvm.resnet50, 101: tvm.resnet101, 152: tvm.resnet152}
+        if num_layers not in ctor:
+            raise ValueError("{} is not a valid number of resnet layers".format(num_layers))
+        self.num_ch_enc = np.array([64, 64, 128, 256, 512])
+        if num_layers > 34:
+            self.num_ch_enc[1:] *= 4
+        self.encoder = ctor[num_layers](weights=None)
+
+    def forward(self, x):
+        e = self.encoder
+        maps = [e.relu(e.bn1(e.conv1(x)))]
+        maps.append(e.layer1(e.maxpool(maps[-1])))
+        for stage in (e.layer2, e.layer3, e.layer4):
+            maps.append(stage(maps[-1]))
+        return maps
+
+
+class _UpBlock(nn.Module):
+    """3x3 conv + BN + ReLU (hybrid_depth_decoder.py:17-30); parameter names ``conv.0`` / ``conv.1``."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = _conv_bn(int(cin), int(cout), 3, 1, 1, 1)
+
+    def forward(self, x):
+        return F.relu(self.conv(x), inplace=True)
+
+
+def _up2(x):
+    return F.interpolate(x, scale_factor=2, mode="nearest")
+
+
+class ContextDecoder2D(nn.Module):
+    """The 2-D halves of the hybrid decoder (hybrid_depth_decoder.py:56-75, 163-184, 264-290).
+
+    ``context(maps)``      -> ``semantic_vs`` [B*T, D, H/4, W/4]   (row a7)
+    ``refine(...)``        -> depth at 1/2 (nearest x2) and full resolution        (row a13)
+    Registered under ``CostRegNet`` by the owning module so the keys read ``CostRegNet.upconv_4_0...``.
+    """
+
+    def __init__(self, num_ch_enc, ndepths, depth_max):
+        super().__init__()
+        enc = [int(c) for c in num_ch_enc]
+        dec = [16, 32, int(ndepths), 128, 256]
+        self.depth_max = float(depth_max)
+        self.upconv_4_0 = _UpBlock(enc[4], dec[4])
+        self.upconv_4_1 = _UpBlock(dec[4] + enc[3], dec[4])
+        self.upconv_3_0 = _UpBlock(dec[4], dec[3])
+        self.upconv_3_1 = _UpBlock(dec[3] + enc[2], dec[3])
+        self.upconv_2_0 = _UpBlock(dec[3], dec[2])
+        self.upconv_2_1 = _UpBlock(dec[2] + enc[1], ndepths)
+        self.upconv_1_0 = _UpBlock(dec[2] + ndepths, dec[1])
+        self.upconv_1_1 = _UpBlock(dec[1] + enc[0], dec[1])
+        self.dispconv_1 = nn.Conv2d(dec[1], 1, 3, 1, 1, 1, bias=True)
+        self.upconv_0_0 = _UpBlock(dec[1], dec[0])
+        self.upconv_0_1 = _UpBlock(dec[0], dec[0])
+        self.dispconv_0 = nn.Conv2d(dec[0], 1, 3, 1, 1, 1, bias=True)
+
+    def context(self, maps):
+        x = self.upconv_4_0(maps[4])
+        x = self.upconv_4_1(torch.cat([_up2(x), maps[3]], 1))
+        x = self.upconv_3_0(x)
+        x = self.upconv_3_1(torch.cat([_up2(x), maps[2]], 1))
+        x = self.upconv_2_0(x)
+        return self.upconv_2_1(torch.cat([_up2(x), maps[1]], 1))
+
+    def refine(self, semantic_vs, fused_logits, skip_half):
+        """fused_logits: [B*T, D, H/4, W/4] raw logits of stereo_head1 (ReLU applied here, :268)."""
+        x = self.upconv_1_0(torch.cat([semantic_vs, F.relu(fused_logits)], dim=1))
+        x = self.upconv_1_1(torch.cat([_up2(x), skip_half], 1))
+        depth_half = _up2(self.depth_max * torch.sigmoid(self.dispconv_1(x)))
+        x = self.upconv_0_1(_up2(self.upconv_0_0(x)))
+        depth_full = self.depth_max * torch.sigmoid(self.dispconv_0(x))
+        return depth_half, depth_full

@@ -1,0 +1,319 @@
+"""``DepthNetHybrid`` -- the drop-in boundary.
+
+Same constructor, ``forward`` signature, return values and ``state_dict`` keys as the reference's
+``hybrid_models.model_hybrid.DepthNetHybrid`` (hybrid_models/model_hybrid.py:15-184) for inference
+(``mode='val'``, the mode both eval drivers use: eval_hybrid.py:113-121, eval_hybrid_seq.py:180-183).
+
+What runs where:
+  * 2-D feature nets and the 2-D context decoder / refinement: PyTorch + cuDNN (``encoders.py``; "kept" rows);
+  * everything 3-D -- plane-sweep warp + folded pre0 (K1), every 3x3x3 convolution with its BN/activation/residual
+    (K2), the EST warp+attention (K3), soft-argmin (K4), GroupNorm/GRU glue (K5), the camera algebra -- runs in the
+    hand-written CUDA library through ``ops.py``.  The 3-D ``nn.Conv3d``/``BatchNorm3d``/``GroupNorm`` modules below
+    are parameter containers only (they give the reference's state-dict names); their ``forward`` is never called.
+    There is no PyTorch fallback for the 3-D path: without the CUDA library ``forward`` raises.
+
+Protocol quirks reproduced on purpose: Q3 first window of a scene has no EST fusion,
+Q4 the returned hidden-state pose is the LAST MEMORY pose once a memory exists, Q5 targets are fused in order and
+later targets attend to already-fused values, Q6 mean-not-sum attention, Q7 rel_pose = P_j P_i^-1.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops, packing
+from .encoders import ContextDecoder2D, ContextEncoder, MatchingFeatureNet
+
+
+def _conv_bn3(cin, cout, k):
+    return nn.Sequential(nn.Conv3d(cin, cout, k, padding=(k - 1) // 2, bias=False), nn.BatchNorm3d(cout))
+
+
+def _conv_bn_act3(cin, cout, act):
+    return nn.Sequential(nn.Conv3d(cin, cout, 3, padding=1, bias=False), nn.BatchNorm3d(cout), act)
+
+
+class _ESTParams(nn.Module):
+    """Parameter container with the names of transformer/epipolar_transformer.py:12-29."""
+
+    def __init__(self, channels=16):
+        super().__init__()
+        self.gate_conv = nn.Conv3d(2 * channels, 2 * channels, 3, padding=1)
+        self.reset_gate_norm = nn.GroupNorm(1, channels, 1e-5, True)
+        self.update_gate_norm = nn.GroupNorm(1, channels, 1e-5, True)
+        self.output_conv = nn.Conv3d(2 * channels, channels, 3, padding=1)
+        self.output_norm = nn.GroupNorm(1, channels, 1e-5, True)
+
+
+class HybridDecoder(ContextDecoder2D):
+    """``CostRegNet``: 2-D context decoder (cuDNN) + parameter containers of the 3-D matching net."""
+
+    def __init__(self, num_ch_enc, ndepths, depth_max, est):
+        super().__init__(num_ch_enc, ndepths, depth_max)
+        if est:
+            self.epipolar_transformer = _ESTParams(16)
+        relu = lambda: nn.ReLU(inplace=True)  # noqa: E731
+        self.dres0 = nn.Sequential(_conv_bn_act3(32, 32, relu()), _conv_bn_act3(32, 32, relu()))
+        self.dres1 = nn.Sequential(_conv_bn_act3(32, 32, relu()), _conv_bn_act3(32, 32, relu()))
+        self.dres2 = nn.Sequential(_conv_bn_act3(33, 33, relu()))
+        self.key_layer = nn.Sequential(_conv_bn_act3(33, 16, relu()))
+        self.value_layer = nn.Sequential(_conv_bn_act3(33, 16, nn.Tanh()))
+        self.stereo_head0 = nn.Sequential(_conv_bn_act3(16, 16, relu()), nn.Conv3d(16, 1, 1, bias=True))
+        self.stereo_head1 = nn.Sequential(_conv_bn_act3(16, 16, relu()), nn.Conv3d(16, 1, 1, bias=True))
+
+
+class _Workspace(object):
+    """Scratch volumes reused across calls (never returned to the caller)."""
+
+    def __init__(self, device, D, H, W, gn_rows):
+        def vol(chunks):
+            return torch.empty(chunks, D, H, W, 4, device=device, dtype=torch.float32)
+        self.key = (str(device), D, H, W)
+        self.x0, self.y, self.cost, self.a, self.b = vol(8), vol(8), vol(8), vol(8), vol(8)
+        self.sem, self.z = vol(1), vol(9)
+        self.hid = vol(4)
+        self.h, self.rh, self.o = vol(4), vol(4), vol(4)
+        self.f = vol(8)
+        self.part_f = torch.zeros(gn_rows, 2, 2, device=device, dtype=torch.float64)
+        self.part_o = torch.zeros(gn_rows, 2, 2, device=device, dtype=torch.float64)
+        self.stats_f = torch.empty(4, device=device, dtype=torch.float32)
+        self.stats_o = torch.empty(4, device=device, dtype=torch.float32)
+        self.homo = torch.empty(12, device=device, dtype=torch.float32)
+        self.warp30 = torch.empty(ops.MAX_SOURCES, 30, device=device, dtype=torch.float32)
+
+
+class DepthNetHybrid(nn.Module):
+    def __init__(self, ndepths=64, depth_min=0.01, depth_max=10.0, resnet=50, IF_EST_transformer=True,
+                 align_corners=False, fix_stale_pose=False):
+        """First five arguments: hybrid_models/model_hybrid.py:15-16.  Extra, keyword-only in practice:
+
+        align_corners   grid_sample semantics of the warps: False = torch >= 1.3 (what the reference computes when run
+                        today, and what the oracle pins); True = the torch 1.2 it was written for (quirk Q1).
+        fix_stale_pose  opt-in fix of quirk Q4 (return the current target's pose with the hidden state).
+        """
+        super().__init__()
+        self.ndepths = int(ndepths)
+        self.depth_min = depth_min
+        self.depth_max = depth_max
+        self.depth_interval = (depth_max - depth_min) / (ndepths - 1)
+        # model_hybrid.py:32-33 (fp32 arange * interval + min, evaluated by torch on the CPU)
+        self.depth_cands = torch.arange(0, ndepths, requires_grad=False).reshape(1, -1).to(
+            torch.float32) * self.depth_interval + self.depth_min
+        self.IF_EST_transformer = bool(IF_EST_transformer)
+        self.align_corners = bool(align_corners)
+        self.fix_stale_pose = bool(fix_stale_pose)
+
+        self.matchingFeature = MatchingFeatureNet()
+        self.semanticFeature = ContextEncoder(resnet)
+        self.CostRegNet = HybridDecoder(self.semanticFeature.num_ch_enc, self.ndepths, self.depth_max,
+                                        self.IF_EST_transformer)
+        self.pre0 = _conv_bn3(64, 32, 1)
+        self.pre1 = _conv_bn_act3(32, 32, nn.ReLU(inplace=True))
+        self.pre2 = _conv_bn3(32, 32, 3)
+
+        self._packed = None          # folded / packed 3-D parameters (rebuilt when the state dict changes)
+        self._packed_key = None
+        self._ws = None
+        self._depth_dev = None
+
+    # ------------------------------------------------------------------ parameter packing
+    def _param_fingerprint(self, device):
+        p = self.pre0[0].weight
+        return (str(device), p.data_ptr(), p._version, self.pre1[0].weight._version,
+                self.CostRegNet.dres0[0][0].weight._version)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._packed = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._packed = None
+        self._depth_dev = None
+        self._ws = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def repack(self):
+        """Re-fold BN and re-pack the 3-D weights (call after mutating parameters in place)."""
+        self._packed = None
+
+    def _layers(self, device):
+        key = self._param_fingerprint(device)
+        if self._packed is None or self._packed_key != key:
+            sd = {k: v.detach() for k, v in self.state_dict().items()
+                  if k.startswith(("pre", "CostRegNet.dres", "CostRegNet.key_layer", "CostRegNet.value_layer",
+                                   "CostRegNet.stereo_head", "CostRegNet.epipolar_transformer"))}
+            self._packed = packing.pack_layers(sd, device)
+            self._packed_key = key
+        return self._packed
+
+    def _workspace(self, device, D, H, W, L):
+        key = (str(device), D, H, W)
+        if self._ws is None or self._ws.key != key:
+            rows = max(ops.conv3d_num_ctas(L["head0"], D, H, W), ops.conv3d_num_ctas(L["pre1"], D, H, W)) + 8
+            self._ws = _Workspace(device, D, H, W, rows)
+        return self._ws
+
+    def scale_cam_intr(self, cam_intr, scale):
+        out = cam_intr.clone()
+        out[:, :2, :] *= scale
+        return out
+
+    # ------------------------------------------------------------------ the 3-D path for one batch element
+    def _cost_volume(self, L, ws, ref_mix, src_mix, poses, K4, t, depth_values, out):
+        """get_costvolume (model_hybrid.py:62-102) for target view t+1 with sources t and t+2."""
+        for n, s in enumerate((t, t + 2)):
+            ops.homography_setup(poses[t + 1], poses[s], K4, ws.homo)
+            ops.warp_cost(ref_mix[t + 1], src_mix[s], ws.homo, depth_values, ws.x0, self.align_corners)
+            ops.conv3d(L["pre1"], ws.x0, ws.y)
+            if n == 0:      # cost = x0 + pre2(pre1(x0))
+                ops.conv3d(L["pre2"], ws.y, ws.cost, res0=ws.x0)
+            else:           # cost = (cost + x0 + pre2(pre1(x0))) / 2
+                ops.conv3d(L["pre2"], ws.y, out, res0=ws.x0, res1=ws.cost, post_scale=0.5)
+        return out
+
+    def _matching(self, L, ws, cost, semantic_vs_t, depth_values, logits_out, depth_out, prob_out):
+        """dres0..2, value/key heads, stereo_head0 + soft-argmin (hybrid_depth_decoder.py:187-209)."""
+        dev = cost.device
+        _, D, H, W, _ = cost.shape
+        ops.conv3d(L["dres0.0"], cost, ws.a)
+        ops.conv3d(L["dres0.1"], ws.a, ws.b)
+        ops.conv3d(L["dres1.0"], ws.b, ws.a)
+        ops.conv3d(L["dres1.1"], ws.a, ws.b)
+        ops.scalar_to_vol4(semantic_vs_t, ws.sem)
+        ops.conv3d(L["dres2"], ws.b, ws.z, in1=ws.sem)
+        value = torch.empty(4, D, H, W, 4, device=dev, dtype=torch.float32)
+        key = torch.empty(4, D, H, W, 4, device=dev, dtype=torch.float32)
+        ops.conv3d(L["value_key"], ws.z, value, out1=key)
+        ops.conv3d(L["head0"], value, ws.hid)
+        ops.head_softargmin(depth_values, hidden=ws.hid, head_w=L["head0_w"], head_b=L["head0_b"],
+                            logits_out=logits_out, depth_out=depth_out, prob_out=prob_out, up=4)
+        return value, key
+
+    def _fuse(self, L, ws, key_i, value_i, src_keys, src_values, pose_i, src_poses, K4, depth_values):
+        """EpipolarTransformer.forward (transformer/epipolar_transformer.py:56-83) for one target."""
+        _, D, H, W, _ = value_i.shape
+        n = len(src_keys)
+        for k in range(n):
+            ops.volume_warp_setup(pose_i, src_poses[k], K4, ws.warp30[k])
+        ops.est_attend(key_i, src_keys, src_values, ws.warp30, depth_values, self.depth_min, self.depth_interval,
+                       out=ws.h, align_corners=self.align_corners)
+        count = 16.0 * D * H * W
+        rows_f = ops.conv3d_num_ctas(L["gate"], D, H, W)
+        ops.conv3d(L["gate"], value_i, ws.f, in1=ws.h, gn_partials=ws.part_f)
+        ops.gn_finalize(ws.part_f[:rows_f], 2, count, out=ws.stats_f)
+        ops.gru_reset(ws.f, ws.h, ws.stats_f, L["gn_r_w"], L["gn_r_b"], out=ws.rh)
+        rows_o = ops.conv3d_num_ctas(L["output"], D, H, W)
+        ops.conv3d(L["output"], value_i, ws.o, in1=ws.rh, gn_partials=ws.part_o)
+        ops.gn_finalize(ws.part_o[:rows_o], 1, count, out=ws.stats_o)
+        fused = torch.empty_like(value_i)
+        ops.gru_blend(ws.f, ws.h, ws.o, ws.stats_f, ws.stats_o, L["gn_u_w"], L["gn_u_b"], L["gn_o_w"], L["gn_o_b"],
+                      out=fused)
+        return fused
+
+    @staticmethod
+    def _state_to_vol4(t, b):
+        """Hidden-state tensor [B,16,D,H,W] handed back by a driver -> this batch element's vol4."""
+        cached = getattr(t, "_estd_vol4", None)
+        if cached is not None and cached[b].device == t.device:
+            return cached[b]
+        return ops.ncdhw_to_vol4(t[b].detach().to(torch.float32).contiguous())
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, imgs, cam_poses, cam_intr, sample=None, pre_costs=None, pre_cam_poses=None, mode='train'):
+        """imgs [B,V,3,H,W] (0..255), cam_poses [B,V,4,4] cam->world, cam_intr [B,3,3]; V-2 target views.
+
+        mode='val' -> (outputs, {"keys": [k], "values": [v]}, [pose]) exactly as the reference
+        (hybrid_models/model_hybrid.py:183-184).  'train' / 'test' (loss / metric heads) are outside the inference
+        hot path and raise.
+        """
+        if mode != 'val':
+            raise NotImplementedError("estdepth_b200 implements the inference path (mode='val'); got mode=%r" % (mode,))
+        if not imgs.is_cuda:
+            raise RuntimeError("estdepth_b200.DepthNetHybrid runs on CUDA only (no CPU fallback); imgs is on %s" % imgs.device)
+        with torch.no_grad():
+            return self._forward_val(imgs, cam_poses, cam_intr, pre_costs, pre_cam_poses)
+
+    def _forward_val(self, imgs, cam_poses, cam_intr, pre_costs, pre_cam_poses):
+        dev = imgs.device
+        imgs = 2 * (imgs / 255.) - 1.
+        B, V, _, Hi, Wi = imgs.shape
+        H, W = Hi // 4, Wi // 4
+        assert V > 2  # the views_num should be larger than 2 (model_hybrid.py:123)
+        T = V - 2
+        D = self.ndepths
+        L = self._layers(dev)
+        ws = self._workspace(dev, D, H, W, L)
+        if self._depth_dev is None or self._depth_dev.device != dev:
+            self._depth_dev = self.depth_cands.reshape(-1).to(dev).contiguous()
+        depth_values = self._depth_dev
+
+        # ---- 2-D feeders (cuDNN) ----
+        feats = self.matchingFeature(imgs.reshape(B * V, 3, Hi, Wi)).reshape(B, V, 32, H, W)
+        maps = self.semanticFeature(imgs[:, 1:1 + T].reshape(B * T, 3, Hi, Wi))
+        semantic_vs = self.CostRegNet.context(maps).contiguous()                 # [B*T, D, H, W]
+        K4 = self.scale_cam_intr(cam_intr.to(torch.float32), 0.25).contiguous()
+        poses = cam_poses.to(torch.float32).contiguous()
+
+        init_logits = torch.empty(B * T, D, H, W, device=dev, dtype=torch.float32)
+        fused_logits = torch.empty(B * T, D, H, W, device=dev, dtype=torch.float32)
+        out = {name: torch.empty(B, T, 1, Hi, Wi, device=dev, dtype=torch.float32)
+               for name in ("depth3", "init_prob", "depth2", "fused_prob")}
+        use_est = self.IF_EST_transformer and pre_costs is not None              # quirk Q3 (hybrid_depth_decoder.py:423)
+        pre_num = len(pre_cam_poses) if use_est else 0
+        state_key = torch.empty(B, 16, D, H, W, device=dev, dtype=torch.float32)
+        state_value = torch.empty(B, 16, D, H, W, device=dev, dtype=torch.float32)
+        state_key._estd_vol4, state_value._estd_vol4 = [None] * B, [None] * B
+
+        for b in range(B):
+            ref_mix = [ops.premix(feats[b, v], L["pre0_ref"], L["pre0_bias"]) for v in range(V)]
+            src_mix = [ops.premix(feats[b, v], L["pre0_src"], None) for v in range(V)]
+            values, keys = [], []
+            for t in range(T):
+                self._cost_volume(L, ws, ref_mix, src_mix, poses[b], K4[b], t, depth_values, ws.cost)
+                value, key = self._matching(L, ws, ws.cost, semantic_vs[b * T + t], depth_values,
+                                            init_logits[b * T + t], out["depth3"][b, t, 0], out["init_prob"][b, t, 0])
+                values.append(value)
+                keys.append(key)
+            all_poses = [poses[b, t + 1] for t in range(T)]
+            if use_est:
+                # memory volumes are appended after the current ones (hybrid_depth_decoder.py:220-224)
+                all_poses += [p[b].to(device=dev, dtype=torch.float32).contiguous() for p in pre_cam_poses]
+                values += [self._state_to_vol4(v, b) for v in pre_costs["values"]]
+                keys += [self._state_to_vol4(k, b) for k in pre_costs["keys"]]
+            for i in range(T):
+                if use_est:
+                    others = [j for j in range(T + pre_num) if j != i]
+                    fused = self._fuse(L, ws, keys[i], values[i], [keys[j] for j in others], [values[j] for j in others],
+                                       all_poses[i], [all_poses[j] for j in others], K4[b], depth_values)
+                    values[i] = fused                                             # quirk Q5 (:253)
+                ops.conv3d(L["head1"], values[i], ws.hid)
+                ops.head_softargmin(depth_values, hidden=ws.hid, head_w=L["head1_w"], head_b=L["head1_b"],
+                                    logits_out=fused_logits[b * T + i], depth_out=out["depth2"][b, i, 0],
+                                    prob_out=out["fused_prob"][b, i, 0], up=4)
+            ops.vol4_to_ncdhw(keys[T - 1], state_key[b])
+            ops.vol4_to_ncdhw(values[T - 1], state_value[b])
+            state_key._estd_vol4[b], state_value._estd_vol4[b] = keys[T - 1], values[T - 1]
+            if b == 0:
+                last_pose_src = (T + pre_num - 1) if (use_est and not self.fix_stale_pose) else (T - 1)
+
+        # ---- 2-D refinement (cuDNN) ----
+        depth_half, depth_full = self.CostRegNet.refine(semantic_vs, fused_logits, maps[0])
+        depth_half = depth_half.reshape(B, T, 1, Hi, Wi)
+        depth_full = depth_full.reshape(B, T, 1, Hi, Wi)
+
+        outputs = {}
+        for t in range(T):
+            outputs[("depth", t, 3)] = out["depth3"][:, t]
+            outputs[("init_prob", t)] = out["init_prob"][:, t]
+        for t in range(T):
+            outputs[("depth", t, 2)] = out["depth2"][:, t]
+            outputs[("fused_prob", t)] = out["fused_prob"][:, t]
+        for t in range(T):
+            outputs[("depth", t, 1)] = depth_half[:, t]
+        for t in range(T):
+            outputs[("depth", t, 0)] = depth_full[:, t]
+
+        # hidden state: last target's key and (fused) value; pose = last element of the (extended) pose list -- Q4
+        if last_pose_src >= T:
+            state_pose = pre_cam_poses[last_pose_src - T]
+        else:
+            state_pose = cam_poses[:, last_pose_src + 1, :, :]
+        return outputs, {"keys": [state_key], "values": [state_value]}, [state_pose]

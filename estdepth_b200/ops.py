@@ -1,0 +1,267 @@
+"""Host-side operators over the C ABI (include/estdepth_b200.h).
+
+Two levels:
+
+* thin wrappers (``premix``, ``warp_cost``, ``conv3d``, ``est_attend`` ...) that take torch CUDA tensors in the
+  library's native layouts (vol4 = [C/4,D,H,W,4], map4 = [C/4,H,W,4]) and enqueue one kernel on the current
+  stream -- PyTorch is only the owner of the device memory here;
+* reference-named operators with the reference's argument meaning and NCDHW tensors, for drop-in use and so the
+  parity tests read like tests of the reference: ``homo_warping`` (utils/homo_utils.py:458), ``warp_volume``
+  (utils/homo_utils.py:240), ``depthlayer`` (hybrid_models/hybrid_depth_decoder.py:33).
+
+Nothing here falls back to PyTorch arithmetic: without the CUDA library every call raises.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check
+
+ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2}
+MAX_SOURCES = 8
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=torch.float32):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("estdepth_b200 ops need CUDA tensors (there is no CPU fallback)")
+    if t.dtype != dtype or not t.is_contiguous():
+        raise RuntimeError("estdepth_b200 ops need contiguous %s tensors, got %s contiguous=%s" %
+                           (dtype, t.dtype, t.is_contiguous()))
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------ thin wrappers
+
+def homography_setup(ref_pose, src_pose, cam_intr, out=None):
+    """[4,4], [4,4], [3,3] device tensors -> [12] = rot(9) | trans(3)."""
+    out = torch.empty(12, device=ref_pose.device, dtype=torch.float32) if out is None else out
+    check(_lib.get().estd_homography_setup(_ptr(ref_pose), _ptr(src_pose), _ptr(cam_intr), _ptr(out), _stream()),
+          "estd_homography_setup")
+    return out
+
+
+def homography_from_proj(src_proj, ref_proj, out=None):
+    out = torch.empty(12, device=src_proj.device, dtype=torch.float32) if out is None else out
+    check(_lib.get().estd_homography_from_proj(_ptr(src_proj), _ptr(ref_proj), _ptr(out), _stream()),
+          "estd_homography_from_proj")
+    return out
+
+
+def volume_warp_setup(pose_i, pose_j, cam_intr, out=None):
+    """-> [30] = Kinv(9) | Minv 3x4 (12) | K(9), Minv = (P_j P_i^-1)^-1."""
+    out = torch.empty(30, device=pose_i.device, dtype=torch.float32) if out is None else out
+    check(_lib.get().estd_volume_warp_setup(_ptr(pose_i), _ptr(pose_j), _ptr(cam_intr), _ptr(out), _stream()),
+          "estd_volume_warp_setup")
+    return out
+
+
+def premix(fea_chw, weight, bias=None, out=None):
+    """fea [Cin,H,W], weight [Cout,Cin], bias [Cout]|None -> map4 [Cout/4,H,W,4]."""
+    cin, H, W = fea_chw.shape
+    cout = weight.shape[0]
+    out = torch.empty(cout // 4, H, W, 4, device=fea_chw.device, dtype=torch.float32) if out is None else out
+    check(_lib.get().estd_premix(_ptr(fea_chw), _ptr(weight), _ptr(bias), _ptr(out), cin, cout, H, W, _stream()),
+          "estd_premix")
+    return out
+
+
+def warp_cost(ref_mix, src_mix, homo12, depth_values, out=None, align_corners=False):
+    """map4 [C/4,H,W,4] x2, [12], [D] -> vol4 [C/4,D,H,W,4]."""
+    chunks, H, W, _ = ref_mix.shape
+    D = depth_values.numel()
+    out = torch.empty(chunks, D, H, W, 4, device=ref_mix.device, dtype=torch.float32) if out is None else out
+    check(_lib.get().estd_warp_cost(_ptr(ref_mix), _ptr(src_mix), _ptr(homo12), _ptr(depth_values), _ptr(out),
+                                    chunks * 4, D, H, W, int(bool(align_corners)), _stream()), "estd_warp_cost")
+    return out
+
+
+class PackedConv(object):
+    """Folded, packed parameters of one 3x3x3 layer (see packing.pack_conv3d)."""
+    __slots__ = ("weight", "scale", "shift", "cin_chunks", "cout_pad", "out_chunks", "act_split", "act_lo", "act_hi")
+
+    def __init__(self, weight, scale, shift, cin_chunks, cout_pad, out_chunks, act_split, act_lo, act_hi):
+        self.weight, self.scale, self.shift = weight, scale, shift
+        self.cin_chunks, self.cout_pad, self.out_chunks = cin_chunks, cout_pad, out_chunks
+        self.act_split, self.act_lo, self.act_hi = act_split, ACT[act_lo], ACT[act_hi]
+
+
+def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials):
+    chunks0, D, H, W, _ = in0.shape
+    d = ConvDesc()
+    d.in0, d.in0_chunks = _ptr(in0), chunks0
+    d.in1, d.in1_chunks = (_ptr(in1), in1.shape[0]) if in1 is not None else (None, 0)
+    if d.in0_chunks + d.in1_chunks != pc.cin_chunks:
+        raise RuntimeError("conv3d: layer packed for %d input chunks, got %d" % (pc.cin_chunks, d.in0_chunks + d.in1_chunks))
+    d.weight, d.scale, d.shift = _ptr(pc.weight), _ptr(pc.scale), _ptr(pc.shift)
+    d.cout_pad, d.act_split, d.act_lo, d.act_hi = pc.cout_pad, pc.act_split, pc.act_lo, pc.act_hi
+    d.res0, d.res1 = _ptr(res0), _ptr(res1)
+    d.post_scale = float(post_scale)
+    d.out0, d.out0_chunks = _ptr(out0), out0.shape[0]
+    d.out1, d.out1_chunks = (_ptr(out1), out1.shape[0]) if out1 is not None else (None, 0)
+    if d.out0_chunks + d.out1_chunks != pc.out_chunks:
+        raise RuntimeError("conv3d: layer produces %d chunks, outputs hold %d" % (pc.out_chunks, d.out0_chunks + d.out1_chunks))
+    d.gn_partials = _ptr(gn_partials, torch.float64)
+    d.D, d.H, d.W = D, H, W
+    return d
+
+
+def conv3d_num_ctas(pc, D, H, W):
+    d = ConvDesc()
+    d.in0_chunks, d.in1_chunks, d.cout_pad = pc.cin_chunks, 0, pc.cout_pad
+    d.D, d.H, d.W = D, H, W
+    n = _lib.get().estd_conv3d_num_ctas(ctypes.byref(d))
+    if n < 0:
+        check(n, "estd_conv3d_num_ctas")
+    return n
+
+
+def conv3d(pc, in0, out0, in1=None, out1=None, res0=None, res1=None, post_scale=1.0, gn_partials=None):
+    """3x3x3 conv + folded affine + activation (+ residuals, x post_scale) over vol4 tensors; returns out0."""
+    d = _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials)
+    check(_lib.get().estd_conv3d(ctypes.byref(d), _stream()), "estd_conv3d")
+    return out0
+
+
+def est_attend(key_t, src_keys, src_values, warp30, depth_values, depth_min, depth_interval, out=None,
+               align_corners=False):
+    """key_t vol4 [4,D,H,W,4]; lists of N source key/value vol4; warp30 [N,30] -> h vol4 [4,D,H,W,4]."""
+    n = len(src_keys)
+    if n < 1 or n > MAX_SOURCES or len(src_values) != n:
+        raise RuntimeError("est_attend: need 1..%d sources, got %d" % (MAX_SOURCES, n))
+    _, D, H, W, _ = key_t.shape
+    out = torch.empty_like(key_t) if out is None else out
+    karr = (ctypes.c_void_p * n)(*[_ptr(k).value for k in src_keys])
+    varr = (ctypes.c_void_p * n)(*[_ptr(v).value for v in src_values])
+    check(_lib.get().estd_est_attend(_ptr(key_t), n, karr, varr, _ptr(warp30), _ptr(depth_values), float(depth_min),
+                                     float(depth_interval), _ptr(out), D, H, W, int(bool(align_corners)), _stream()),
+          "estd_est_attend")
+    return out
+
+
+def gn_finalize(partials, n_groups, count_per_group, eps=1e-5, out=None):
+    out = torch.empty(4, device=partials.device, dtype=torch.float32) if out is None else out
+    check(_lib.get().estd_gn_finalize(_ptr(partials, torch.float64), partials.shape[0], n_groups, float(count_per_group),
+                                      float(eps), _ptr(out), _stream()), "estd_gn_finalize")
+    return out
+
+
+def gru_reset(f, h, stats, gamma, beta, out=None):
+    _, D, H, W, _ = h.shape
+    out = torch.empty_like(h) if out is None else out
+    check(_lib.get().estd_gru_reset(_ptr(f), _ptr(h), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(out), D, H, W, _stream()),
+          "estd_gru_reset")
+    return out
+
+
+def gru_blend(f, h, o, stats_f, stats_o, gamma_u, beta_u, gamma_o, beta_o, out=None):
+    _, D, H, W, _ = h.shape
+    out = torch.empty_like(h) if out is None else out
+    check(_lib.get().estd_gru_blend(_ptr(f), _ptr(h), _ptr(o), _ptr(stats_f), _ptr(stats_o), _ptr(gamma_u), _ptr(beta_u),
+                                    _ptr(gamma_o), _ptr(beta_o), _ptr(out), D, H, W, _stream()), "estd_gru_blend")
+    return out
+
+
+def head_softargmin(depth_values, hidden=None, head_w=None, head_b=None, logits_in=None, logits_out=None,
+                    depth_out=None, prob_out=None, argmax_out=None, up=4, shape=None):
+    """Logit head (optional) + softmax over D + expectation; outputs are written `up` x replicated."""
+    if hidden is not None:
+        _, D, H, W, _ = hidden.shape
+    else:
+        D, H, W = logits_in.shape
+    check(_lib.get().estd_head_softargmin(_ptr(hidden), _ptr(head_w), _ptr(head_b), _ptr(logits_in), _ptr(depth_values),
+                                          _ptr(logits_out), _ptr(depth_out), _ptr(prob_out),
+                                          _ptr(argmax_out, torch.int32), D, H, W, up, _stream()), "estd_head_softargmin")
+
+
+def vol4_to_ncdhw(vol4, out=None):
+    chunks, D, H, W, _ = vol4.shape
+    out = torch.empty(chunks * 4, D, H, W, device=vol4.device, dtype=torch.float32) if out is None else out
+    check(_lib.get().estd_vol4_to_ncdhw(_ptr(vol4), _ptr(out), chunks * 4, D, H, W, _stream()), "estd_vol4_to_ncdhw")
+    return out
+
+
+def ncdhw_to_vol4(x, out=None):
+    C, D, H, W = x.shape
+    out = torch.empty(C // 4, D, H, W, 4, device=x.device, dtype=torch.float32) if out is None else out
+    check(_lib.get().estd_ncdhw_to_vol4(_ptr(x), _ptr(out), C, D, H, W, _stream()), "estd_ncdhw_to_vol4")
+    return out
+
+
+def scalar_to_vol4(x, out=None):
+    D, H, W = x.shape
+    out = torch.empty(1, D, H, W, 4, device=x.device, dtype=torch.float32) if out is None else out
+    check(_lib.get().estd_scalar_to_vol4(_ptr(x), _ptr(out), D, H, W, _stream()), "estd_scalar_to_vol4")
+    return out
+
+
+# ------------------------------------------------------------------------------------ reference-named operators
+
+def homo_warping(src_fea, src_proj, ref_proj, depth_values, align_corners=False):
+    """Same contract as the reference's ``homo_warping`` (utils/homo_utils.py:458-504).
+
+    src_fea [B,C,H,W], src_proj/ref_proj [B,4,4], depth_values [B,D] or [B,D,1,1] -> [B,C,D,H,W].
+    (The product path never calls this un-fused form; it exists as the operator-level drop-in.)
+    """
+    B, C, H, W = src_fea.shape
+    dv = _f32c(depth_values).reshape(B, -1)
+    D = dv.shape[1]
+    Cp = (C + 3) // 4 * 4
+    eye = torch.eye(Cp, C, device=src_fea.device, dtype=torch.float32)
+    out = torch.empty(B, Cp, D, H, W, device=src_fea.device, dtype=torch.float32)
+    zeros = torch.zeros(Cp // 4, H, W, 4, device=src_fea.device, dtype=torch.float32)
+    for b in range(B):
+        src_mix = premix(_f32c(src_fea[b]), eye)
+        h12 = homography_from_proj(_f32c(src_proj[b]), _f32c(ref_proj[b]))
+        vol = warp_cost(zeros, src_mix, h12, dv[b].contiguous(), align_corners=align_corners)
+        vol4_to_ncdhw(vol, out[b])
+    return out[:, :C]
+
+
+def warp_volume(feat_volume, depth, pose, cam_intr, pixel_coords=None, depth_min=None, depth_interval=None,
+                align_corners=False):
+    """Same contract as the reference's ``warp_volume`` (utils/homo_utils.py:240-279), zeros padding.
+
+    feat_volume [N,C,D,H,W] (C <= 16), depth [N,1,D,H*W] (the plane depths, constant over H*W as in the decoder,
+    hybrid_depth_decoder.py:237), pose [N,4,4] = P_j P_i^-1, cam_intr [N,3,3].  ``pixel_coords`` is accepted and
+    ignored (the kernel generates the pixel grid).  Implemented as the fused EST gather with a single source,
+    whose softmax weight is exactly 1.
+    """
+    N, C, D, H, W = feat_volume.shape
+    if C > 16:
+        raise RuntimeError("warp_volume: at most 16 channels (the EST key/value width)")
+    dev = feat_volume.device
+    out = torch.empty(N, 16, D, H, W, device=dev, dtype=torch.float32)
+    eye = torch.eye(4, device=dev, dtype=torch.float32)
+    for n in range(N):
+        padded = torch.zeros(16, D, H, W, device=dev, dtype=torch.float32)
+        padded[:C] = feat_volume[n]
+        vol = ncdhw_to_vol4(padded)
+        dv = _f32c(depth[n, 0, :, 0])
+        w30 = volume_warp_setup(eye, _f32c(pose[n]), _f32c(cam_intr[n])).reshape(1, 30)
+        key_t = torch.ones_like(vol)
+        h = est_attend(key_t, [vol], [vol], w30, dv, depth_min, depth_interval, align_corners=align_corners)
+        vol4_to_ncdhw(h, out[n])
+    return out[:, :C]
+
+
+def depthlayer(logits, depth_values):
+    """Same contract as ``depthlayer`` (hybrid_depth_decoder.py:33-38): logits [B,D,H,W], depth_values [B,D,H,W]
+    (constant over H,W) -> (depth [B,1,H,W], prob [B,1,H,W])."""
+    B, D, H, W = logits.shape
+    depth = torch.empty(B, 1, H, W, device=logits.device, dtype=torch.float32)
+    prob = torch.empty_like(depth)
+    for b in range(B):
+        dv = _f32c(depth_values[min(b, depth_values.shape[0] - 1), :, 0, 0])
+        head_softargmin(dv, logits_in=_f32c(logits[b]), depth_out=depth[b, 0], prob_out=prob[b, 0], up=1)
+    return depth, prob

@@ -1,0 +1,115 @@
+"""Parameter folding and packing for the CUDA kernels (pure tensor reshuffling; testable on CPU).
+
+* eval-mode BatchNorm3d -> per-channel (scale, shift):  s = gamma / sqrt(var + eps),  b = beta - mean * s
+  (networks/layers_op.py:16-39 put a BatchNorm3d after every bias-free Conv3d; eps = 1e-5).
+* pre0 (1x1x1, 64->32, hybrid_models/model_hybrid.py:58) splits into the two 32x32 matrices applied to the target
+  and source feature maps at 2-D resolution: ``cat([ref_volume, warped])`` puts the target
+  features in input channels 0..31 and the warped source in 32..63 (model_hybrid.py:93).
+* 3x3x3 weights [Cout,Cin,3,3,3] -> [27][cin_pad][cout_pad] with tap = (kd*3+kh)*3+kw, with the channel
+  permutations that the vol4 segment layout of each layer implies (see ``LAYER_PLAN``).
+
+The 33-channel tensors of the reference (context map concatenated as channel 0, hybrid_depth_decoder.py:195) live
+in a 36-channel "canonical" order here: [ref channels 1..32 | ref channel 0 | 3 zero pads] so that the 32 matching
+channels stay chunk aligned and the context channel is a separate 1-chunk tensor.
+"""
+import torch
+
+from .ops import PackedConv
+
+BN_EPS = 1e-5
+
+
+def fold_bn(sd, prefix, eps=BN_EPS):
+    """-> (scale, shift) of the eval-mode BatchNorm at ``prefix``."""
+    var = sd[prefix + ".running_var"].to(torch.float64)
+    mean = sd[prefix + ".running_mean"].to(torch.float64)
+    gamma = sd[prefix + ".weight"].to(torch.float64)
+    beta = sd[prefix + ".bias"].to(torch.float64)
+    scale = gamma / torch.sqrt(var + eps)
+    shift = beta - mean * scale
+    return scale.to(torch.float32), shift.to(torch.float32)
+
+
+def split_pre0(sd):
+    """-> (W_ref [32,32], W_src [32,32], bias [32]) with the BN scale folded into the matrices."""
+    w = sd["pre0.0.weight"].reshape(sd["pre0.0.weight"].shape[0], -1).to(torch.float64)       # [32, 64]
+    scale, shift = fold_bn(sd, "pre0.1")
+    w = w * scale.to(torch.float64).unsqueeze(1)
+    half = w.shape[1] // 2
+    return (w[:, :half].to(torch.float32).contiguous(), w[:, half:].to(torch.float32).contiguous(),
+            shift.contiguous())
+
+
+def pack_weight(weight, cin_order, cout_order):
+    """[Cout,Cin,3,3,3] -> [27, len(cin_order), len(cout_order)]; order entries are reference channel indices, -1 = zero pad."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    w = weight.reshape(cout, cin, 27).permute(2, 1, 0)                     # [27, Cin, Cout]
+    out = torch.zeros(27, len(cin_order), len(cout_order), dtype=torch.float32, device=weight.device)
+    ci_dst = [i for i, c in enumerate(cin_order) if c >= 0]
+    ci_src = [c for c in cin_order if c >= 0]
+    co_dst = [i for i, c in enumerate(cout_order) if c >= 0]
+    co_src = [c for c in cout_order if c >= 0]
+    sub = w[:, ci_src][:, :, co_src]
+    out[:, torch.tensor(ci_dst).unsqueeze(1), torch.tensor(co_dst).unsqueeze(0)] = sub.to(torch.float32)
+    return out.contiguous()
+
+
+def _affine(scale, shift, cout_order, device):
+    s = torch.zeros(len(cout_order), dtype=torch.float32, device=device)
+    b = torch.zeros(len(cout_order), dtype=torch.float32, device=device)
+    for i, c in enumerate(cout_order):
+        if c >= 0:
+            s[i] = scale[c]
+            b[i] = shift[c]
+    return s, b
+
+
+CANON36 = list(range(1, 33)) + [0, -1, -1, -1]            # canonical order of the 33-channel tensors
+
+
+def pack_layers(sd, device):
+    """All 3-D layers of the hot path -> dict name -> PackedConv (tensors on ``device``)."""
+    def conv_bn(prefix, cin_order, cout_order, cout_pad, act_split, act_lo, act_hi, out_chunks):
+        w = sd[prefix + ".0.weight"].to(device)
+        scale, shift = fold_bn(sd, prefix + ".1")
+        order = list(cout_order) + [-1] * (cout_pad - len(cout_order))
+        s, b = _affine(scale, shift, order, device)
+        return PackedConv(pack_weight(w, cin_order, order), s, b, len(cin_order) // 4, cout_pad, out_chunks,
+                          act_split, act_lo, act_hi)
+
+    def conv_bias(prefix, cout_pad, act_split, out_chunks):
+        w = sd[prefix + ".weight"].to(device)
+        order = list(range(w.shape[0]))
+        s = torch.ones(cout_pad, dtype=torch.float32, device=device)
+        b = sd[prefix + ".bias"].to(device=device, dtype=torch.float32).contiguous()
+        return PackedConv(pack_weight(w, list(range(w.shape[1])), order), s, b, w.shape[1] // 4, cout_pad, out_chunks,
+                          act_split, "none", "none")
+
+    r32, r16 = list(range(32)), list(range(16))
+    layers = {}
+    layers["pre1"] = conv_bn("pre1", r32, r32, 32, 32, "relu", "relu", 8)
+    layers["pre2"] = conv_bn("pre2", r32, r32, 32, 32, "none", "none", 8)
+    for name in ("dres0.0", "dres0.1", "dres1.0", "dres1.1"):
+        layers[name] = conv_bn("CostRegNet." + name, r32, r32, 32, 32, "relu", "relu", 8)
+    layers["dres2"] = conv_bn("CostRegNet.dres2.0", CANON36, CANON36[:33], 40, 40, "relu", "relu", 9)
+    # value (tanh) and key (ReLU) share their input: one 33->32 layer, outputs split into two tensors
+    wv, wk = sd["CostRegNet.value_layer.0.0.weight"].to(device), sd["CostRegNet.key_layer.0.0.weight"].to(device)
+    sv, bv = fold_bn(sd, "CostRegNet.value_layer.0.1")
+    sk, bk = fold_bn(sd, "CostRegNet.key_layer.0.1")
+    layers["value_key"] = PackedConv(pack_weight(torch.cat([wv, wk], 0), CANON36, r32),
+                                     torch.cat([sv, sk]).to(device).contiguous(), torch.cat([bv, bk]).to(device).contiguous(),
+                                     9, 32, 8, 16, "tanh", "relu")
+    for i in (0, 1):
+        layers["head%d" % i] = conv_bn("CostRegNet.stereo_head%d.0" % i, r16, r16, 16, 16, "relu", "relu", 4)
+        layers["head%d_w" % i] = sd["CostRegNet.stereo_head%d.1.weight" % i].to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+        layers["head%d_b" % i] = sd["CostRegNet.stereo_head%d.1.bias" % i].to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+    est = "CostRegNet.epipolar_transformer"
+    if (est + ".gate_conv.weight") in sd:
+        layers["gate"] = conv_bias(est + ".gate_conv", 32, 16, 8)
+        layers["output"] = conv_bias(est + ".output_conv", 16, 16, 4)
+        for gate, key in (("r", "reset_gate_norm"), ("u", "update_gate_norm"), ("o", "output_norm")):
+            layers["gn_%s_w" % gate] = sd["%s.%s.weight" % (est, key)].to(device=device, dtype=torch.float32).contiguous()
+            layers["gn_%s_b" % gate] = sd["%s.%s.bias" % (est, key)].to(device=device, dtype=torch.float32).contiguous()
+    w_ref, w_src, bias = split_pre0(sd)
+    layers["pre0_ref"], layers["pre0_src"], layers["pre0_bias"] = w_ref.to(device), w_src.to(device), bias.to(device)
+    return layers

@@ -1,0 +1,150 @@
+/*
+ * estdepth_b200 -- C ABI of the B200 (sm_100a) kernels behind ESTDepth's inference hot path.
+ *
+ * This is the drop-in boundary of SURVEY.md section 8(b).  The reference (xxlong0/ESTDepth) is pure
+ * PyTorch and has no FFI of its own; the seams this library replaces are the Python call sites listed
+ * next to each entry point below (paths relative to the reference tree).  A maintainer binds these
+ * symbols with ctypes (INTEGRATION.md shows the stub); `estdepth_b200/ops.py` is that binding.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, ints, floats; no torch / C++ types cross the boundary.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises the
+ *     host, the library never allocates, frees or retains device memory (caller owns every buffer).
+ *   - return value: 0 on success, negative ESTD_E* code on failure (never throws); the message is in
+ *     estd_last_error() (thread-local).  Unsupported shapes are errors -- there is no CPU fallback.
+ *   - all tensors are fp32.  Layouts:
+ *       vol4  : a C-channel volume stored as [C/4][D][H][W][4]   ("chunk" = 4 consecutive channels)
+ *       map4  : a C-channel 2-D map stored as [C/4][H][W][4]
+ *       NCDHW / NCHW / [D][H][W] : plain contiguous torch layouts where stated.
+ *     H, W are the quarter-resolution sizes (H' , W' in SURVEY.md), D the number of depth planes.
+ */
+#ifndef ESTDEPTH_B200_H_
+#define ESTDEPTH_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ESTD_API __attribute__((visibility("default")))
+#else
+#define ESTD_API
+#endif
+
+#define ESTD_VERSION 100            /* 0.1.0 */
+
+#define ESTD_OK            0
+#define ESTD_EINVAL       -1        /* bad argument / unsupported shape */
+#define ESTD_ECUDA        -2        /* CUDA runtime / driver error at launch */
+#define ESTD_EUNSUPPORTED -3        /* no kernel specialisation for this channel configuration */
+
+#define ESTD_ACT_NONE 0
+#define ESTD_ACT_RELU 1
+#define ESTD_ACT_TANH 2
+
+#define ESTD_MAX_SOURCES 8          /* max N of the EST attention */
+
+ESTD_API int estd_version(void);
+ESTD_API const char* estd_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+ESTD_API unsigned long long estd_launch_count(void);
+
+/* ---- geometry set-up (device-side 3x3 / 4x4 algebra; replaces the ~60 torch.inverse/matmul calls per
+ *      window: model_hybrid.py:74-88, homo_utils.py:469-471, :51, :258, hybrid_depth_decoder.py:235) ---- */
+
+/* out12 = {rot[9] row-major, trans[3]} of M = (K E_src)(K E_ref)^-1 with E = pose^-1
+ * (model_hybrid.py:83-88 + homo_utils.py:469-471).  ref_pose, src_pose: [4,4] cam->world; cam_intr: [3,3]
+ * already scaled to quarter resolution.  All pointers are device pointers. */
+ESTD_API int estd_homography_setup(const float* ref_pose, const float* src_pose, const float* cam_intr,
+                          float* out12, void* stream);
+
+/* Same, from the two 4x4 projection matrices the reference's homo_warping receives
+ * (utils/homo_utils.py:458,469): M = src_proj * ref_proj^-1. */
+ESTD_API int estd_homography_from_proj(const float* src_proj, const float* ref_proj, float* out12, void* stream);
+
+/* out30 = {Kinv[9], Minv[12] (3x4 row-major), K[9]} with Minv = (P_j P_i^-1)^-1
+ * (hybrid_depth_decoder.py:235 + homo_utils.py:51,258; quirk Q7).  pose_i = target, pose_j = source. */
+ESTD_API int estd_volume_warp_setup(const float* pose_i, const float* pose_j, const float* cam_intr,
+                           float* out30, void* stream);
+
+/* ---- K1: fused plane-sweep warp -> cost-volume input  (replaces homo_warping, utils/homo_utils.py:458-504,
+ *      + ref_volume repeat / cat / pre0 conv+BN, hybrid_models/model_hybrid.py:76,90-94) ---- */
+
+/* out map4 [C/4][H][W][4] = W[C x Cin] * fea[Cin,H,W] (+ bias): the folded halves of pre0 at 2-D resolution.
+ * fea is NCHW ([Cin,H,W] contiguous), weight row-major [C][Cin], bias [C] or NULL.  C, Cin multiples of 4, <= 64. */
+ESTD_API int estd_premix(const float* fea_chw, const float* weight, const float* bias, float* out_map4,
+                int cin, int cout, int H, int W, void* stream);
+
+/* x0 vol4 [C/4][D][H][W][4] = ref_mix[c,h,w] + bilinear_zeros(src_mix[c], homography(d,h,w)).
+ * homo12: device pointer from estd_homography_setup.  depth_values: device [D].
+ * align_corners: 0 = grid_sample semantics of torch >= 1.3 (what the oracle runs), 1 = torch 1.2 (quirk Q1). */
+ESTD_API int estd_warp_cost(const float* ref_mix_map4, const float* src_mix_map4, const float* homo12,
+                   const float* depth_values, float* x0_vol4, int C, int D, int H, int W,
+                   int align_corners, void* stream);
+
+/* ---- K2: 3x3x3 convolution, stride 1, pad 1, folded BN/bias + activation + residuals
+ *      (replaces every convbn*_3d / nn.Conv3d(k=3): networks/layers_op.py:16-39, model_hybrid.py:59-60,94-95,
+ *       hybrid_depth_decoder.py:84-112,190-200,256,377, transformer/epipolar_transformer.py:21,26) ---- */
+typedef struct estd_conv3d_desc {
+    const float* in0;  int in0_chunks;    /* vol4 input, first channel segment                          */
+    const float* in1;  int in1_chunks;    /* optional second segment (torch.cat on channels), or NULL/0  */
+    const float* weight;                  /* packed [27][cin_pad][cout_pad], cin_pad = 4*(in0+in1 chunks) */
+    const float* scale;                   /* [cout_pad] per-channel multiplier (folded BN gamma/sqrt(var+eps)) */
+    const float* shift;                   /* [cout_pad] per-channel offset (folded BN beta - mean*scale, or conv bias) */
+    int cout_pad;                         /* 16, 32 or 40 */
+    int act_split;                        /* channels [0,act_split) use act_lo, [act_split,cout_pad) act_hi; multiple of 8 */
+    int act_lo, act_hi;                   /* ESTD_ACT_* */
+    const float* res0; const float* res1; /* optional vol4 tensors (cout_pad/4 chunks) added after the activation */
+    float post_scale;                     /* result multiplied by this last (1.0f for none) */
+    float* out0; int out0_chunks;         /* vol4 output, first channel segment                         */
+    float* out1; int out1_chunks;         /* optional second output tensor for the remaining chunks      */
+    double* gn_partials;                  /* optional [n_ctas][2][2] (sum,sumsq) per channel group {[0,act_split),[act_split,..)} */
+    int D, H, W;
+} estd_conv3d_desc;
+
+/* number of CTAs estd_conv3d will launch for this shape == rows of gn_partials the caller must provide */
+ESTD_API int estd_conv3d_num_ctas(const estd_conv3d_desc* desc);
+ESTD_API int estd_conv3d(const estd_conv3d_desc* desc, void* stream);
+
+/* ---- K3: EST attention: fused frustum warp of N (key,value) volumes + per-voxel softmax over N + mean
+ *      (replaces warp_volume x 2N, utils/homo_utils.py:240-279, and EpipolarTransformer.forward's attention,
+ *       transformer/epipolar_transformer.py:62-73; quirk Q6 mean-not-sum) ---- */
+/* key_t: vol4 (16 ch).  src_keys/src_values: HOST arrays of n_src device pointers (vol4, 16 ch each).
+ * warp30: device [n_src][30] from estd_volume_warp_setup.  h_out: vol4 (16 ch). */
+ESTD_API int estd_est_attend(const float* key_t, int n_src, const float* const* src_keys, const float* const* src_values,
+                    const float* warp30, const float* depth_values, float depth_min, float depth_interval,
+                    float* h_out, int D, int H, int W, int align_corners, void* stream);
+
+/* ---- K5: ConvGRU glue around the two EST convolutions (transformer/epipolar_transformer.py:31-54,80-83) ---- */
+/* stats[g] = {mean, rstd} (float2) of group g from n_rows x n_groups x {sum,sumsq} double partials; eps as GroupNorm. */
+ESTD_API int estd_gn_finalize(const double* partials, int n_rows, int n_groups, double count_per_group, float eps,
+                     float* stats, void* stream);
+/* rh = sigmoid(GN(f[0:16])) * h          (f: vol4 32ch = gate_conv output; stats: group 0 = reset gate) */
+ESTD_API int estd_gru_reset(const float* f_vol4, const float* h_vol4, const float* stats, const float* gamma, const float* beta,
+                   float* rh_vol4, int D, int H, int W, void* stream);
+/* out = u*h + (1-u)*tanh(GN(o)),  u = sigmoid(GN(f[16:32]))   (stats_f group 1 = update gate; stats_o group 0) */
+ESTD_API int estd_gru_blend(const float* f_vol4, const float* h_vol4, const float* o_vol4, const float* stats_f,
+                   const float* stats_o, const float* gamma_u, const float* beta_u, const float* gamma_o,
+                   const float* beta_o, float* out_vol4, int D, int H, int W, void* stream);
+
+/* ---- K4: logit head + soft-argmin at quarter resolution, written `up` x replicated
+ *      (replaces the 1x1x1 head conv, F.interpolate(scale_factor=4) and depthlayer:
+ *       hybrid_depth_decoder.py:104-112,202-209,259-260,33-38; quirk Q11) ---- */
+/* hidden: vol4 (16 ch) output of the head's 3x3x3 conv, or NULL to use logits_in [D][H][W].
+ * head_w [16], head_b [1] device.  logits_out [D][H][W] (may be NULL).
+ * depth_out/prob_out [up*H][up*W], argmax_out int32 [up*H][up*W] (each may be NULL). */
+ESTD_API int estd_head_softargmin(const float* hidden_vol4, const float* head_w, const float* head_b, const float* logits_in,
+                         const float* depth_values, float* logits_out, float* depth_out, float* prob_out,
+                         int* argmax_out, int D, int H, int W, int up, void* stream);
+
+/* ---- layout helpers at the boundary (hidden state / context channel) ---- */
+ESTD_API int estd_vol4_to_ncdhw(const float* vol4, float* ncdhw, int C, int D, int H, int W, void* stream);
+ESTD_API int estd_ncdhw_to_vol4(const float* ncdhw, float* vol4, int C, int D, int H, int W, void* stream);
+/* out vol4 (1 chunk) = (in[d,h,w], 0, 0, 0): the 2-D context map entering dres2 as one 3-D channel
+ * (hybrid_depth_decoder.py:195, quirk Q13) */
+ESTD_API int estd_scalar_to_vol4(const float* dhw, float* vol4_1chunk, int D, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* ESTDEPTH_B200_H_ */

@@ -1,0 +1,333 @@
+"""GPU parity of every kernel behind the C ABI against the CPU oracle / the reference's golden outputs.
+
+All calls go through ``estdepth_b200.ops`` -> ctypes -> libestdepth_b200.so (the C ABI).  Tolerances are written
+next to each check; they are fp32 round-off scale, far inside the 1e-3 depth gate of BASELINE.json.
+"""
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from estdepth_b200 import ops, packing, synth
+from oracle import estdepth_oracle as orc
+from oracle.make_golden import ops_inputs
+from tests.helpers import from_vol4, to_map4, to_vol4
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda"
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def maxdiff(a, b):
+    return (a.detach().cpu().double() - torch.as_tensor(b).double()).abs().max().item()
+
+
+def test_library_loads_and_counts_launches():
+    from estdepth_b200 import _lib
+    lib = _lib.get()
+    assert lib.estd_version() >= 100
+    before = _lib.launch_count()
+    ops.scalar_to_vol4(torch.zeros(2, 3, 4, device=DEV))
+    assert _lib.launch_count() == before + 1
+
+
+def test_errors_are_reported_not_swallowed():
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        ops.scalar_to_vol4(torch.zeros(2, 3, 4))
+    pc = ops.PackedConv(torch.zeros(27, 12, 24, device=DEV), torch.zeros(24, device=DEV), torch.zeros(24, device=DEV),
+                        3, 24, 6, 24, "none", "none")
+    x = torch.zeros(3, 4, 8, 8, 4, device=DEV)
+    y = torch.zeros(6, 4, 8, 8, 4, device=DEV)
+    with pytest.raises(RuntimeError, match="no kernel"):
+        ops.conv3d(pc, x, y)
+
+
+def test_layout_roundtrip():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(16, 5, 7, 9, generator=g)
+    v = ops.ncdhw_to_vol4(x.to(DEV))
+    assert maxdiff(v, to_vol4(x)) == 0.0
+    assert maxdiff(ops.vol4_to_ncdhw(v), x) == 0.0
+    s = torch.randn(5, 7, 9, generator=g)
+    sv = ops.scalar_to_vol4(s.to(DEV)).cpu()
+    assert torch.equal(sv[0, ..., 0], s) and sv[0, ..., 1:].abs().max() == 0
+
+
+def test_premix_matches_matmul():
+    g = torch.Generator().manual_seed(2)
+    fea = torch.randn(32, 30, 40, generator=g)
+    w = torch.randn(32, 32, generator=g) / 5
+    b = torch.randn(32, generator=g)
+    out = ops.premix(fea.to(DEV), w.to(DEV), b.to(DEV))
+    want = to_map4(torch.einsum("oc,chw->ohw", w.double(), fea.double()).float() + b.view(-1, 1, 1))
+    assert maxdiff(out, want) < 2e-5            # 32-term fp32 dot products of O(1) values
+
+
+@pytest.mark.parametrize("src", [0, 2])
+def test_homo_warping_vs_reference_golden(src):
+    """ops.homo_warping == the reference's homo_warping on the same inputs (golden from oracle/make_golden.py)."""
+    x = ops_inputs()
+    D = x["depth_values"].numel()
+    ext = torch.inverse(x["poses"]).unsqueeze(0)
+    sp, rp = ext[:, src].clone(), ext[:, 1].clone()
+    sp[:, :3, :4] = x["K4"] @ ext[:, src, :3, :4]
+    rp[:, :3, :4] = x["K4"] @ ext[:, 1, :3, :4]
+    got = ops.homo_warping(x["fea"].to(DEV), sp.to(DEV), rp.to(DEV), x["depth_values"].view(1, D, 1, 1).to(DEV))
+    want = golden("ops_small.npz")["homo_warp_%d" % src]
+    # white-noise features: a 1e-5 px coordinate difference moves a sample by ~1e-5 * |gradient| ~ 5e-5
+    assert maxdiff(got, want) < 2e-4
+    oracle = orc.homo_warp(x["fea"], sp, rp, x["depth_values"], sampler="explicit")
+    assert maxdiff(got, oracle) < 2e-4
+
+
+def test_warp_cost_fused_equals_pre0_of_cat():
+    """K1 == pre0(cat[ref_volume, homo_warping(src)]) (model_hybrid.py:76,90-94), incl. out-of-range planes."""
+    g = torch.Generator().manual_seed(3)
+    C, D, H, W = 32, 12, 36, 44
+    feats = [torch.randn(1, C, H, W, generator=g) for _ in range(3)]
+    sd = {"pre0.0.weight": torch.randn(32, 64, 1, 1, 1, generator=g) / 8,
+          "pre0.1.weight": torch.rand(32, generator=g) + 0.5, "pre0.1.bias": torch.randn(32, generator=g) / 5,
+          "pre0.1.running_mean": torch.randn(32, generator=g) / 5, "pre0.1.running_var": torch.rand(32, generator=g) + 0.5}
+    poses = synth.camera_track(3).unsqueeze(0)
+    K4 = synth.intrinsics(4 * H, 4 * W).unsqueeze(0).clone()
+    K4[:, :2] *= 0.25
+    dv = torch.linspace(0.1, 10.0, D)
+    w_ref, w_src, bias = packing.split_pre0(sd)
+    for s in (0, 2):
+        ext = torch.inverse(poses)
+        sp, rp = ext[:, s].clone(), ext[:, 1].clone()
+        sp[:, :3, :4] = K4 @ ext[:, s, :3, :4]
+        rp[:, :3, :4] = K4 @ ext[:, 1, :3, :4]
+        warped = orc.homo_warp(feats[s], sp, rp, dv)
+        want = orc._cb3(torch.cat([feats[1].unsqueeze(2).repeat(1, 1, D, 1, 1), warped], 1), sd, "pre0")[0]
+        ref_mix = ops.premix(feats[1][0].to(DEV), w_ref.to(DEV), bias.to(DEV))
+        src_mix = ops.premix(feats[s][0].to(DEV), w_src.to(DEV))
+        h12 = ops.homography_setup(poses[0, 1].to(DEV), poses[0, s].to(DEV), K4[0].to(DEV))
+        got = from_vol4(ops.warp_cost(ref_mix, src_mix, h12, dv.to(DEV)).cpu())
+        assert maxdiff(got, want) < 3e-4
+        frac_zero = (warped.abs().sum(1) == 0).float().mean().item()
+        assert 0.01 < frac_zero < 0.99, "test must cover both in-range and out-of-range samples"
+
+
+CONV_CASES = [
+    # name, cin segments (chunks), cout real, cout_pad, out segments (chunks), act_split, act_lo, act_hi
+    ("32to32", (8,), 32, 32, (8,), 32, "relu", "relu"),
+    ("16+16to32", (4, 4), 32, 32, (8,), 16, "none", "none"),
+    ("36to40", (8, 1), 33, 40, (9,), 40, "relu", "relu"),
+    ("36to16+16", (9,), 32, 32, (4, 4), 16, "tanh", "relu"),
+    ("16to16", (4,), 16, 16, (4,), 16, "relu", "relu"),
+    ("16+16to16", (4, 4), 16, 16, (4,), 16, "none", "none"),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("shape", [(5, 21, 40), (8, 32, 64)], ids=["ragged", "aligned"])
+def test_conv3d_vs_torch_cpu(case, shape):
+    """K2 against F.conv3d (CPU fp32) + affine + activation + residuals, all channel configurations, ragged edges."""
+    name, cin_seg, cout, cout_pad, out_seg, act_split, act_lo, act_hi = case
+    D, H, W = shape
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)
+    cin = 4 * sum(cin_seg)
+    x = torch.randn(cin, D, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) / (cin * 27) ** 0.5
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) / 3
+    res0 = torch.randn(4 * sum(out_seg), D, H, W, generator=g)
+    res1 = torch.randn(4 * sum(out_seg), D, H, W, generator=g)
+    order = list(range(cout)) + [-1] * (cout_pad - cout)
+    pw = packing.pack_weight(w, list(range(cin)), order)
+    s_pad = torch.zeros(cout_pad)
+    b_pad = torch.zeros(cout_pad)
+    s_pad[:cout], b_pad[:cout] = scale, shift
+    pc = ops.PackedConv(pw.to(DEV), s_pad.to(DEV), b_pad.to(DEV), sum(cin_seg), cout_pad, sum(out_seg), act_split, act_lo, act_hi)
+
+    y = F.conv3d(x.unsqueeze(0), w, None, 1, 1)[0] * scale.view(-1, 1, 1, 1) + shift.view(-1, 1, 1, 1)
+    acts = {"none": lambda t: t, "relu": torch.relu, "tanh": torch.tanh}
+    y = torch.cat([acts[act_lo](y[:act_split]), acts[act_hi](y[act_split:])], 0)
+    cpad = 4 * sum(out_seg)
+    ypad = torch.zeros(cpad, D, H, W)
+    ypad[:cout] = y
+    want = (ypad + res0 + res1) * 0.5
+
+    xin = to_vol4(x).to(DEV)
+    ins = [xin[:cin_seg[0]].contiguous()] + ([xin[cin_seg[0]:].contiguous()] if len(cin_seg) > 1 else [])
+    outs = [torch.full((c, D, H, W, 4), float("nan"), device=DEV) for c in out_seg]
+    n_ctas = ops.conv3d_num_ctas(pc, D, H, W)
+    partials = torch.zeros(n_ctas, 2, 2, device=DEV, dtype=torch.float64)
+    ops.conv3d(pc, ins[0], outs[0], in1=ins[1] if len(ins) > 1 else None, out1=outs[1] if len(outs) > 1 else None,
+               res0=to_vol4(res0).to(DEV), res1=to_vol4(res1).to(DEV), post_scale=0.5, gn_partials=partials)
+    got = from_vol4(torch.cat(outs, 0).cpu())
+    assert torch.isfinite(got).all()
+    # K = 27*cin <= 972 fp32 products of O(1)/sqrt(K) terms: round-off ~ 1e-6; 3e-5 leaves margin for tanh
+    assert maxdiff(got, want) < 3e-5
+    # deterministic GroupNorm partial sums (over the real, written channels of each group)
+    tot = partials.sum(0).cpu()
+    real = want.clone()
+    g0 = real[:min(act_split, cpad)].double()
+    assert abs(tot[0, 0].item() - g0.sum().item()) < 1e-3 * max(1.0, g0.abs().sum().item() ** 0.5)
+    assert abs(tot[0, 1].item() - (g0 ** 2).sum().item()) < 1e-4 * (g0 ** 2).sum().item()
+    if act_split < cpad:
+        g1 = real[act_split:].double()
+        assert abs(tot[1, 1].item() - (g1 ** 2).sum().item()) < 1e-4 * (g1 ** 2).sum().item()
+
+
+def test_conv3d_is_bitwise_deterministic():
+    g = torch.Generator().manual_seed(5)
+    D, H, W = 6, 24, 64
+    x = to_vol4(torch.randn(32, D, H, W, generator=g)).to(DEV)
+    w = torch.randn(32, 32, 3, 3, 3, generator=g) / 30
+    pc = ops.PackedConv(packing.pack_weight(w, list(range(32)), list(range(32))).to(DEV), torch.ones(32, device=DEV),
+                        torch.zeros(32, device=DEV), 8, 32, 8, 16, "none", "none")
+    outs, parts = [], []
+    for _ in range(2):
+        y = torch.empty_like(x)
+        p = torch.zeros(ops.conv3d_num_ctas(pc, D, H, W), 2, 2, device=DEV, dtype=torch.float64)
+        ops.conv3d(pc, x, y, gn_partials=p)
+        outs.append(y.cpu())
+        parts.append(p.cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(parts[0], parts[1])
+
+
+@pytest.mark.parametrize("j", [0, 2])
+def test_warp_volume_vs_reference_golden(j):
+    """ops.warp_volume (the fused EST gather with N=1) == the reference's warp_volume (utils/homo_utils.py:240)."""
+    x = ops_inputs()
+    D = x["depth_values"].numel()
+    _, C, _, H, W = x["vol"].shape
+    rel = torch.matmul(x["poses"][j:j + 1], torch.inverse(x["poses"][1:2]))
+    dv = x["depth_values"].view(1, 1, D, 1).repeat(1, 1, 1, H * W)
+    got = ops.warp_volume(x["vol"].to(DEV), dv.to(DEV), rel.to(DEV), x["K4"].to(DEV), None, x["depth_min"], x["interval"])
+    want = golden("ops_small.npz")["warp_volume_%d" % j]
+    assert maxdiff(got, want) < 3e-4        # white-noise volume; see SURVEY.md 8c (4e-5 restatement noise)
+    oracle = orc.warp_volume(x["vol"], rel, x["K4"], x["depth_values"], x["depth_min"], x["interval"], sampler="explicit")
+    assert maxdiff(got, oracle) < 3e-4
+    frac_zero = (torch.as_tensor(want).abs().sum(1) == 0).float().mean().item()
+    assert 0.01 < frac_zero < 0.99
+
+
+@pytest.mark.parametrize("n_src", [1, 2, 3])
+def test_est_attend_vs_oracle(n_src):
+    """K3 == warp_volume x 2N + attention (epipolar_transformer.py:62-73) on smooth volumes."""
+    g = torch.Generator().manual_seed(10 + n_src)
+    D, H, W = 8, 24, 40
+    dmin, dmax = 0.5, 6.0
+    interval = (dmax - dmin) / (D - 1)
+    dv = torch.arange(D, dtype=torch.float32) * interval + dmin
+
+    def smooth(c):
+        return F.interpolate(torch.randn(1, c, D // 2, H // 4, W // 4, generator=g), size=(D, H, W), mode="trilinear")
+
+    key_t = torch.relu(smooth(16))
+    keys = [torch.relu(smooth(16)) for _ in range(n_src)]
+    vals = [torch.tanh(smooth(16)) for _ in range(n_src)]
+    poses = synth.camera_track(n_src + 1)
+    K4 = synth.intrinsics(4 * H, 4 * W).unsqueeze(0).clone()
+    K4[:, :2] *= 0.25
+    wk, wv, w30 = [], [], []
+    for n in range(n_src):
+        rel = torch.matmul(poses[n + 1:n + 2], torch.inverse(poses[0:1]))
+        wk.append(orc.warp_volume(keys[n], rel, K4, dv, dmin, interval))
+        wv.append(orc.warp_volume(vals[n], rel, K4, dv, dmin, interval))
+        w30.append(ops.volume_warp_setup(poses[0].to(DEV), poses[n + 1].to(DEV), K4[0].to(DEV)))
+    want = orc.est_attention(key_t, wk, wv)[0]
+    got = ops.est_attend(to_vol4(key_t[0]).to(DEV), [to_vol4(k[0]).to(DEV) for k in keys],
+                         [to_vol4(v[0]).to(DEV) for v in vals], torch.stack(w30), dv.to(DEV), dmin, interval)
+    assert maxdiff(from_vol4(got.cpu()), want) < 1e-4
+
+
+@pytest.mark.parametrize("n_src", [1, 2, 3])
+def test_gru_chain_vs_reference_golden(n_src):
+    """gate conv -> GroupNorm -> reset -> output conv -> GroupNorm -> blend == reference EpipolarTransformer output."""
+    from oracle.ref_loader import reference_available  # noqa: F401  (golden was produced by the reference)
+    x = ops_inputs()
+    tmpl = {"gate_conv.weight": torch.empty(32, 32, 3, 3, 3), "gate_conv.bias": torch.empty(32),
+            "reset_gate_norm.weight": torch.empty(16), "reset_gate_norm.bias": torch.empty(16),
+            "update_gate_norm.weight": torch.empty(16), "update_gate_norm.bias": torch.empty(16),
+            "output_conv.weight": torch.empty(16, 32, 3, 3, 3), "output_conv.bias": torch.empty(16),
+            "output_norm.weight": torch.empty(16), "output_norm.bias": torch.empty(16)}
+    sd = {"CostRegNet.epipolar_transformer." + k: v for k, v in synth.synth_state_dict(tmpl, seed=3).items()}
+    want = golden("ops_small.npz")["est_n%d" % n_src][0]
+    assert maxdiff(orc.est_fuse(sd, x["key_t"], x["wkeys"][:n_src], x["val_t"], x["wvals"][:n_src])[0], want) < 1e-5
+    h = orc.est_attention(x["key_t"], x["wkeys"][:n_src], x["wvals"][:n_src])
+    _, _, D, H, W = h.shape
+    r32 = list(range(32))
+    gate = ops.PackedConv(packing.pack_weight(sd["CostRegNet.epipolar_transformer.gate_conv.weight"], r32, r32).to(DEV),
+                          torch.ones(32, device=DEV), sd["CostRegNet.epipolar_transformer.gate_conv.bias"].to(DEV),
+                          8, 32, 8, 16, "none", "none")
+    outc = ops.PackedConv(packing.pack_weight(sd["CostRegNet.epipolar_transformer.output_conv.weight"], r32, list(range(16))).to(DEV),
+                          torch.ones(16, device=DEV), sd["CostRegNet.epipolar_transformer.output_conv.bias"].to(DEV),
+                          8, 16, 4, 16, "none", "none")
+    p = {k.rsplit("transformer.", 1)[1]: v.to(DEV) for k, v in sd.items()}
+    v4, h4 = to_vol4(x["val_t"][0]).to(DEV), to_vol4(h[0]).to(DEV)
+    f = torch.empty(8, D, H, W, 4, device=DEV)
+    pf = torch.zeros(ops.conv3d_num_ctas(gate, D, H, W), 2, 2, device=DEV, dtype=torch.float64)
+    ops.conv3d(gate, v4, f, in1=h4, gn_partials=pf)
+    sf = ops.gn_finalize(pf, 2, 16.0 * D * H * W)
+    rh = ops.gru_reset(f, h4, sf, p["reset_gate_norm.weight"], p["reset_gate_norm.bias"])
+    o = torch.empty(4, D, H, W, 4, device=DEV)
+    po = torch.zeros(ops.conv3d_num_ctas(outc, D, H, W), 2, 2, device=DEV, dtype=torch.float64)
+    ops.conv3d(outc, v4, o, in1=rh, gn_partials=po)
+    so = ops.gn_finalize(po, 1, 16.0 * D * H * W)
+    fused = ops.gru_blend(f, h4, o, sf, so, p["update_gate_norm.weight"], p["update_gate_norm.bias"],
+                          p["output_norm.weight"], p["output_norm.bias"])
+    assert maxdiff(from_vol4(fused.cpu()), want) < 2e-5
+
+
+def test_depthlayer_vs_reference_golden():
+    x = ops_inputs()
+    D = x["depth_values"].numel()
+    dv = x["depth_values"].view(1, D, 1, 1).repeat(1, 1, 9, 11)
+    depth, prob = ops.depthlayer(x["logits"].to(DEV), dv.to(DEV))
+    gold = golden("ops_small.npz")
+    assert maxdiff(depth, gold["depthlayer_depth"]) < 2e-6 * 4.0      # depths up to 4.0, fp32 softmax round-off
+    assert maxdiff(prob, gold["depthlayer_prob"]) < 2e-6
+
+
+def test_head_softargmin_fused_head_upsample_and_argmax():
+    """1x1x1 head + x4 replicated soft-argmin; argmax index bit-exact wherever the top-2 logit gap exceeds round-off."""
+    g = torch.Generator().manual_seed(7)
+    D, H, W = 32, 12, 20
+    hid = torch.relu(torch.randn(16, D, H, W, generator=g))
+    w = torch.randn(16, generator=g)
+    b = torch.randn(1, generator=g)
+    dv = torch.linspace(0.1, 10.0, D)
+    logits = (hid * w.view(16, 1, 1, 1)).sum(0) + b
+    want_d, want_p, want_i = orc.soft_argmin(logits.unsqueeze(0), dv)
+    lo = torch.empty(D, H, W, device=DEV)
+    d = torch.empty(4 * H, 4 * W, device=DEV)
+    p = torch.empty(4 * H, 4 * W, device=DEV)
+    i = torch.empty(4 * H, 4 * W, device=DEV, dtype=torch.int32)
+    ops.head_softargmin(dv.to(DEV), hidden=to_vol4(hid).to(DEV), head_w=w.to(DEV), head_b=b.to(DEV), logits_out=lo,
+                        depth_out=d, prob_out=p, argmax_out=i, up=4)
+    assert maxdiff(lo, logits) < 1e-5
+    assert maxdiff(d, want_d[0, 0]) < 1e-4
+    assert maxdiff(p, want_p[0, 0]) < 1e-5
+    top2 = torch.topk(logits, 2, dim=0).values
+    safe = F.interpolate(((top2[0] - top2[1]) > 1e-4).float()[None, None], scale_factor=4)[0, 0].bool()
+    assert safe.float().mean() > 0.95
+    assert torch.equal(i.cpu()[safe].long(), want_i[0, 0][safe])
+
+
+def test_align_corners_flag_changes_sampling():
+    """Quirk Q1: both grid_sample conventions are implemented; True matches F.grid_sample(align_corners=True)."""
+    x = ops_inputs()
+    D = x["depth_values"].numel()
+    ext = torch.inverse(x["poses"]).unsqueeze(0)
+    sp, rp = ext[:, 0].clone(), ext[:, 1].clone()
+    sp[:, :3, :4] = x["K4"] @ ext[:, 0, :3, :4]
+    rp[:, :3, :4] = x["K4"] @ ext[:, 1, :3, :4]
+    _, C, H, W = x["fea"].shape
+    xn, yn = orc.plane_sweep_grid(sp[0], rp[0], x["depth_values"], H, W)
+    grid = torch.stack((xn, yn), 2).view(1, D * H, W, 2)
+    want = F.grid_sample(x["fea"], grid, mode="bilinear", padding_mode="zeros", align_corners=True).view(1, C, D, H, W)
+    got = ops.homo_warping(x["fea"].to(DEV), sp.to(DEV), rp.to(DEV), x["depth_values"].view(1, D).to(DEV), align_corners=True)
+    assert maxdiff(got, want) < 2e-4
+    got_false = ops.homo_warping(x["fea"].to(DEV), sp.to(DEV), rp.to(DEV), x["depth_values"].view(1, D).to(DEV))
+    assert maxdiff(got_false, want) > 1e-2
