@@ -246,9 +246,11 @@ class DepthNetHybrid(nn.Module):
         depth_values = self._depth_dev
 
         # ---- 2-D feeders (cuDNN) ----
+        t_prof = ops._pb()
         feats = self.matchingFeature(imgs.reshape(B * V, 3, Hi, Wi)).reshape(B, V, 32, H, W)
         maps = self.semanticFeature(imgs[:, 1:1 + T].reshape(B * T, 3, Hi, Wi))
         semantic_vs = self.CostRegNet.context(maps).contiguous()                 # [B*T, D, H, W]
+        ops._pe(t_prof, "cudnn_2d_feeders")
         K4 = self.scale_cam_intr(cam_intr.to(torch.float32), 0.25).contiguous()
         poses = cam_poses.to(torch.float32).contiguous()
 
@@ -295,7 +297,9 @@ class DepthNetHybrid(nn.Module):
                 last_pose_src = (T + pre_num - 1) if (use_est and not self.fix_stale_pose) else (T - 1)
 
         # ---- 2-D refinement (cuDNN) ----
+        t_prof = ops._pb()
         depth_half, depth_full = self.CostRegNet.refine(semantic_vs, fused_logits, maps[0])
+        ops._pe(t_prof, "cudnn_2d_refine")
         depth_half = depth_half.reshape(B, T, 1, Hi, Wi)
         depth_full = depth_full.reshape(B, T, 1, Hi, Wi)
 

@@ -22,6 +22,45 @@ ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2}
 MAX_SOURCES = 8
 
 
+class KernelProfile(object):
+    """Optional per-kernel-family CUDA-event timing (bench.py's roofline pass).  Events are recorded on the stream the
+    kernels are launched on; algorithmic flops / bytes per launch follow SURVEY.md section 8(d)."""
+
+    def __init__(self):
+        self.records = {}          # family -> list of (start_event, end_event, flops, bytes)
+
+    def begin(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        return e
+
+    def end(self, family, start, flops=0.0, nbytes=0.0):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        self.records.setdefault(family, []).append((start, e, float(flops), float(nbytes)))
+
+    def summary(self, steps):
+        """-> family -> (ms per step, calls per step, flops per step, bytes per step)"""
+        torch.cuda.synchronize()
+        out = {}
+        for fam, recs in self.records.items():
+            ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
+            out[fam] = (ms / steps, len(recs) / float(steps), sum(r[2] for r in recs) / steps, sum(r[3] for r in recs) / steps)
+        return out
+
+
+PROFILE = None      # set to a KernelProfile() to time every launch (bench.py)
+
+
+def _pb():
+    return PROFILE.begin() if PROFILE is not None else None
+
+
+def _pe(start, family, flops=0.0, nbytes=0.0):
+    if start is not None:
+        PROFILE.end(family, start, flops, nbytes)
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -46,8 +85,10 @@ def _f32c(t):
 def homography_setup(ref_pose, src_pose, cam_intr, out=None):
     """[4,4], [4,4], [3,3] device tensors -> [12] = rot(9) | trans(3)."""
     out = torch.empty(12, device=ref_pose.device, dtype=torch.float32) if out is None else out
+    t = _pb()
     check(_lib.get().estd_homography_setup(_ptr(ref_pose), _ptr(src_pose), _ptr(cam_intr), _ptr(out), _stream()),
           "estd_homography_setup")
+    _pe(t, "geometry_setup")
     return out
 
 
@@ -61,8 +102,10 @@ def homography_from_proj(src_proj, ref_proj, out=None):
 def volume_warp_setup(pose_i, pose_j, cam_intr, out=None):
     """-> [30] = Kinv(9) | Minv 3x4 (12) | K(9), Minv = (P_j P_i^-1)^-1."""
     out = torch.empty(30, device=pose_i.device, dtype=torch.float32) if out is None else out
+    t = _pb()
     check(_lib.get().estd_volume_warp_setup(_ptr(pose_i), _ptr(pose_j), _ptr(cam_intr), _ptr(out), _stream()),
           "estd_volume_warp_setup")
+    _pe(t, "geometry_setup")
     return out
 
 
@@ -71,8 +114,10 @@ def premix(fea_chw, weight, bias=None, out=None):
     cin, H, W = fea_chw.shape
     cout = weight.shape[0]
     out = torch.empty(cout // 4, H, W, 4, device=fea_chw.device, dtype=torch.float32) if out is None else out
+    t = _pb()
     check(_lib.get().estd_premix(_ptr(fea_chw), _ptr(weight), _ptr(bias), _ptr(out), cin, cout, H, W, _stream()),
           "estd_premix")
+    _pe(t, "premix", 2.0 * cin * cout * H * W, 4.0 * (cin + cout) * H * W)
     return out
 
 
@@ -81,17 +126,23 @@ def warp_cost(ref_mix, src_mix, homo12, depth_values, out=None, align_corners=Fa
     chunks, H, W, _ = ref_mix.shape
     D = depth_values.numel()
     out = torch.empty(chunks, D, H, W, 4, device=ref_mix.device, dtype=torch.float32) if out is None else out
+    t = _pb()
     check(_lib.get().estd_warp_cost(_ptr(ref_mix), _ptr(src_mix), _ptr(homo12), _ptr(depth_values), _ptr(out),
                                     chunks * 4, D, H, W, int(bool(align_corners)), _stream()), "estd_warp_cost")
+    _pe(t, "warp_cost", 0.0, 4.0 * chunks * 4 * H * W * (D + 2))       # 4*C*P*(D+2)
     return out
 
 
 class PackedConv(object):
     """Folded, packed parameters of one 3x3x3 layer (see packing.pack_conv3d)."""
-    __slots__ = ("weight", "scale", "shift", "cin_chunks", "cout_pad", "out_chunks", "act_split", "act_lo", "act_hi")
+    __slots__ = ("weight", "scale", "shift", "cin_chunks", "cout_pad", "out_chunks", "act_split", "act_lo", "act_hi",
+                 "cin", "cout")
 
-    def __init__(self, weight, scale, shift, cin_chunks, cout_pad, out_chunks, act_split, act_lo, act_hi):
+    def __init__(self, weight, scale, shift, cin_chunks, cout_pad, out_chunks, act_split, act_lo, act_hi,
+                 cin=None, cout=None):
         self.weight, self.scale, self.shift = weight, scale, shift
+        self.cin = cin if cin is not None else 4 * cin_chunks          # real (un-padded) channel counts, for flop accounting
+        self.cout = cout if cout is not None else min(cout_pad, 4 * out_chunks)
         self.cin_chunks, self.cout_pad, self.out_chunks = cin_chunks, cout_pad, out_chunks
         self.act_split, self.act_lo, self.act_hi = act_split, ACT[act_lo], ACT[act_hi]
 
@@ -129,7 +180,10 @@ def conv3d_num_ctas(pc, D, H, W):
 def conv3d(pc, in0, out0, in1=None, out1=None, res0=None, res1=None, post_scale=1.0, gn_partials=None):
     """3x3x3 conv + folded affine + activation (+ residuals, x post_scale) over vol4 tensors; returns out0."""
     d = _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials)
+    t = _pb()
     check(_lib.get().estd_conv3d(ctypes.byref(d), _stream()), "estd_conv3d")
+    vox = float(d.D) * d.H * d.W
+    _pe(t, "conv3d", 54.0 * pc.cin * pc.cout * vox, 4.0 * vox * (pc.cin + pc.cout))     # SURVEY 8d (K2)
     return out0
 
 
@@ -143,32 +197,40 @@ def est_attend(key_t, src_keys, src_values, warp30, depth_values, depth_min, dep
     out = torch.empty_like(key_t) if out is None else out
     karr = (ctypes.c_void_p * n)(*[_ptr(k).value for k in src_keys])
     varr = (ctypes.c_void_p * n)(*[_ptr(v).value for v in src_values])
+    t = _pb()
     check(_lib.get().estd_est_attend(_ptr(key_t), n, karr, varr, _ptr(warp30), _ptr(depth_values), float(depth_min),
                                      float(depth_interval), _ptr(out), D, H, W, int(bool(align_corners)), _stream()),
           "estd_est_attend")
+    _pe(t, "est_attend", 0.0, 4.0 * 16 * D * H * W * (2 + 2 * n))
     return out
 
 
 def gn_finalize(partials, n_groups, count_per_group, eps=1e-5, out=None):
     out = torch.empty(4, device=partials.device, dtype=torch.float32) if out is None else out
+    t = _pb()
     check(_lib.get().estd_gn_finalize(_ptr(partials, torch.float64), partials.shape[0], n_groups, float(count_per_group),
                                       float(eps), _ptr(out), _stream()), "estd_gn_finalize")
+    _pe(t, "gn_finalize")
     return out
 
 
 def gru_reset(f, h, stats, gamma, beta, out=None):
     _, D, H, W, _ = h.shape
     out = torch.empty_like(h) if out is None else out
+    t = _pb()
     check(_lib.get().estd_gru_reset(_ptr(f), _ptr(h), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(out), D, H, W, _stream()),
           "estd_gru_reset")
+    _pe(t, "gru_reset", 0.0, 4.0 * 16 * D * H * W * 3)
     return out
 
 
 def gru_blend(f, h, o, stats_f, stats_o, gamma_u, beta_u, gamma_o, beta_o, out=None):
     _, D, H, W, _ = h.shape
     out = torch.empty_like(h) if out is None else out
+    t = _pb()
     check(_lib.get().estd_gru_blend(_ptr(f), _ptr(h), _ptr(o), _ptr(stats_f), _ptr(stats_o), _ptr(gamma_u), _ptr(beta_u),
                                     _ptr(gamma_o), _ptr(beta_o), _ptr(out), D, H, W, _stream()), "estd_gru_blend")
+    _pe(t, "gru_blend", 0.0, 4.0 * 16 * D * H * W * 4)
     return out
 
 
@@ -179,29 +241,39 @@ def head_softargmin(depth_values, hidden=None, head_w=None, head_b=None, logits_
         _, D, H, W, _ = hidden.shape
     else:
         D, H, W = logits_in.shape
+    t = _pb()
     check(_lib.get().estd_head_softargmin(_ptr(hidden), _ptr(head_w), _ptr(head_b), _ptr(logits_in), _ptr(depth_values),
                                           _ptr(logits_out), _ptr(depth_out), _ptr(prob_out),
                                           _ptr(argmax_out, torch.int32), D, H, W, up, _stream()), "estd_head_softargmin")
+    n_out = sum(x is not None for x in (depth_out, prob_out, argmax_out))
+    _pe(t, "head_softargmin", 0.0, 4.0 * ((16 if hidden is not None else 1) * D * H * W
+                                          + (D * H * W if logits_out is not None else 0) + n_out * up * up * H * W))
 
 
 def vol4_to_ncdhw(vol4, out=None):
     chunks, D, H, W, _ = vol4.shape
     out = torch.empty(chunks * 4, D, H, W, device=vol4.device, dtype=torch.float32) if out is None else out
+    t = _pb()
     check(_lib.get().estd_vol4_to_ncdhw(_ptr(vol4), _ptr(out), chunks * 4, D, H, W, _stream()), "estd_vol4_to_ncdhw")
+    _pe(t, "layout", 0.0, 8.0 * chunks * 4 * D * H * W)
     return out
 
 
 def ncdhw_to_vol4(x, out=None):
     C, D, H, W = x.shape
     out = torch.empty(C // 4, D, H, W, 4, device=x.device, dtype=torch.float32) if out is None else out
+    t = _pb()
     check(_lib.get().estd_ncdhw_to_vol4(_ptr(x), _ptr(out), C, D, H, W, _stream()), "estd_ncdhw_to_vol4")
+    _pe(t, "layout", 0.0, 8.0 * C * D * H * W)
     return out
 
 
 def scalar_to_vol4(x, out=None):
     D, H, W = x.shape
     out = torch.empty(1, D, H, W, 4, device=x.device, dtype=torch.float32) if out is None else out
+    t = _pb()
     check(_lib.get().estd_scalar_to_vol4(_ptr(x), _ptr(out), D, H, W, _stream()), "estd_scalar_to_vol4")
+    _pe(t, "layout", 0.0, 20.0 * D * H * W)
     return out
 
 

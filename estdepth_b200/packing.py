@@ -75,7 +75,7 @@ def pack_layers(sd, device):
         order = list(cout_order) + [-1] * (cout_pad - len(cout_order))
         s, b = _affine(scale, shift, order, device)
         return PackedConv(pack_weight(w, cin_order, order), s, b, len(cin_order) // 4, cout_pad, out_chunks,
-                          act_split, act_lo, act_hi)
+                          act_split, act_lo, act_hi, cin=w.shape[1], cout=w.shape[0])
 
     def conv_bias(prefix, cout_pad, act_split, out_chunks):
         w = sd[prefix + ".weight"].to(device)
@@ -98,7 +98,7 @@ def pack_layers(sd, device):
     sk, bk = fold_bn(sd, "CostRegNet.key_layer.0.1")
     layers["value_key"] = PackedConv(pack_weight(torch.cat([wv, wk], 0), CANON36, r32),
                                      torch.cat([sv, sk]).to(device).contiguous(), torch.cat([bv, bk]).to(device).contiguous(),
-                                     9, 32, 8, 16, "tanh", "relu")
+                                     9, 32, 8, 16, "tanh", "relu", cin=33, cout=32)
     for i in (0, 1):
         layers["head%d" % i] = conv_bn("CostRegNet.stereo_head%d.0" % i, r16, r16, 16, 16, "relu", "relu", 4)
         layers["head%d_w" % i] = sd["CostRegNet.stereo_head%d.1.weight" % i].to(device=device, dtype=torch.float32).reshape(-1).contiguous()
