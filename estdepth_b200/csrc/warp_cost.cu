@@ -7,9 +7,9 @@
 // so ref_volume, the warped volume and their concat (157+157+315 MB at 480x640/D=64) never exist; the kernel
 // reads two L2-resident 2.5 MB maps and streams x0 (157 MB) out once: it is HBM-store bound.
 //
-// Data layout: maps are map4 [C/4][H][W][4], x0 is vol4 [C/4][D][H][W][4].  One thread owns one voxel (d,h,w)
-// for all channel chunks: the homography is evaluated once, every global access is a 16-byte vector, and for a
-// fixed chunk the 32 lanes of a warp (32 consecutive w) store 512 contiguous bytes.
+// Data layout: maps are map4 [C/4][H][W][4], x0 is vol4 [C/4][D][H][W][4].  One thread owns one target pixel for a
+// few consecutive planes and all channel chunks: the homography is evaluated once per (pixel, plane), every global
+// access is a 16-byte vector, and for a fixed chunk the 32 lanes of a warp (32 consecutive w) store 512 contiguous bytes.
 #include "common.cuh"
 
 namespace estd {
@@ -45,31 +45,22 @@ __global__ void __launch_bounds__(256) premix_kernel(const float* __restrict__ f
     }
 }
 
-template <int ALIGN>
-__global__ void __launch_bounds__(256) warp_cost_kernel(const float* __restrict__ ref_mix, const float* __restrict__ src_mix,
-                                                        const float* __restrict__ homo12,
-                                                        const float* __restrict__ depth_values,
-                                                        float* __restrict__ x0, int chunks, int D, int H, int W) {
-    const int HW = H * W;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int d = blockIdx.y;
-    if (p >= HW) return;
-    const int h = p / W;
-    const int w = p - h * W;
+// Tap set of one (pixel, plane) sample: clamped float4 offsets into a source chunk + bilinear weights (0 when the tap
+// is out of bounds, so zero padding costs nothing).
+struct Taps2 {
+    int o_nw, o_ne, o_sw, o_se;
+    float w_nw, w_ne, w_sw, w_se;
+};
 
-    // --- homography (utils/homo_utils.py:469-485), fp32, same operation order as the reference ---
-    const float r00 = __ldg(homo12 + 0), r01 = __ldg(homo12 + 1), r02 = __ldg(homo12 + 2);
-    const float r10 = __ldg(homo12 + 3), r11 = __ldg(homo12 + 4), r12 = __ldg(homo12 + 5);
-    const float r20 = __ldg(homo12 + 6), r21 = __ldg(homo12 + 7), r22 = __ldg(homo12 + 8);
-    const float t0 = __ldg(homo12 + 9), t1 = __ldg(homo12 + 10), t2 = __ldg(homo12 + 11);
-    const float depth = __ldg(depth_values + d);
-    const float fx = (float)w, fy = (float)h;
-    const float qx = fmaf(r02, 1.0f, fmaf(r01, fy, r00 * fx));
-    const float qy = fmaf(r12, 1.0f, fmaf(r11, fy, r10 * fx));
-    const float qz = fmaf(r22, 1.0f, fmaf(r21, fy, r20 * fx));
-    const float px3 = __fadd_rn(__fmul_rn(qx, depth), t0);
-    const float py3 = __fadd_rn(__fmul_rn(qy, depth), t1);
-    const float pz3 = __fadd_rn(__fmul_rn(qz, depth), t2);
+// --- homography (utils/homo_utils.py:469-491) + ATen GridSampler tap arithmetic, fp32, reference operation order ---
+template <int ALIGN>
+__device__ __forceinline__ Taps2 plane_sweep_taps(const float (&hm)[12], float fx, float fy, float depth, int H, int W) {
+    const float qx = fmaf(hm[2], 1.0f, fmaf(hm[1], fy, hm[0] * fx));
+    const float qy = fmaf(hm[5], 1.0f, fmaf(hm[4], fy, hm[3] * fx));
+    const float qz = fmaf(hm[8], 1.0f, fmaf(hm[7], fy, hm[6] * fx));
+    const float px3 = __fadd_rn(__fmul_rn(qx, depth), hm[9]);
+    const float py3 = __fadd_rn(__fmul_rn(qy, depth), hm[10]);
+    const float pz3 = __fadd_rn(__fmul_rn(qz, depth), hm[11]);
     const float zden = __fadd_rn(pz3, 1e-8f);
     const float px = __fdiv_rn(px3, zden);
     const float py = __fdiv_rn(py3, zden);
@@ -85,39 +76,72 @@ __global__ void __launch_bounds__(256) warp_cost_kernel(const float* __restrict_
     const float wy1 = iy - y0f, wy0 = (y0f + 1.0f) - iy;
     // NaN / huge coordinates: the float->int conversion saturates and the bounds test rejects the tap
     const int xi = (int)x0f, yi = (int)y0f;
-    const bool vx0 = (xi >= 0) && (xi < W), vx1 = (xi + 1 >= 0) && (xi + 1 < W);
+    const bool fin = (ix == ix) && (iy == iy);
+    const bool vx0 = fin && (xi >= 0) && (xi < W), vx1 = fin && (xi + 1 >= 0) && (xi + 1 < W);
     const bool vy0 = (yi >= 0) && (yi < H), vy1 = (yi + 1 >= 0) && (yi + 1 < H);
-    const float w_nw = (vx0 && vy0) ? wx0 * wy0 : 0.0f;
-    const float w_ne = (vx1 && vy0) ? wx1 * wy0 : 0.0f;
-    const float w_sw = (vx0 && vy1) ? wx0 * wy1 : 0.0f;
-    const float w_se = (vx1 && vy1) ? wx1 * wy1 : 0.0f;
-    const bool any = (vx0 || vx1) && (vy0 || vy1) && (ix == ix) && (iy == iy);
-    // clamped tap addresses (weight is already 0 for out-of-bounds taps)
+    Taps2 t;
+    t.w_nw = (vx0 && vy0) ? wx0 * wy0 : 0.0f;
+    t.w_ne = (vx1 && vy0) ? wx1 * wy0 : 0.0f;
+    t.w_sw = (vx0 && vy1) ? wx0 * wy1 : 0.0f;
+    t.w_se = (vx1 && vy1) ? wx1 * wy1 : 0.0f;
     const int cx0 = min(max(xi, 0), W - 1), cx1 = min(max(xi + 1, 0), W - 1);
     const int cy0 = min(max(yi, 0), H - 1), cy1 = min(max(yi + 1, 0), H - 1);
-    const int o_nw = (cy0 * W + cx0) * 4, o_ne = (cy0 * W + cx1) * 4;
-    const int o_sw = (cy1 * W + cx0) * 4, o_se = (cy1 * W + cx1) * 4;
+    t.o_nw = (cy0 * W + cx0) * 4; t.o_ne = (cy0 * W + cx1) * 4;
+    t.o_sw = (cy1 * W + cx0) * 4; t.o_se = (cy1 * W + cx1) * 4;
+    return t;
+}
 
-    const size_t plane = (size_t)HW * 4;
-    const float* refp = ref_mix + (size_t)p * 4;
-    float* outp = x0 + ((size_t)d * HW + p) * 4;
-    const size_t out_chunk = (size_t)D * HW * 4;
-    if (!any) {                                         // whole sample out of range: x0 = ref part (exact zeros added)
-#pragma unroll 4
-        for (int j = 0; j < chunks; ++j) st4(outp + j * out_chunk, ldg4(refp + j * plane));
-        return;
+// Block = 8 rows x 32 columns of target pixels, kPlanes consecutive depth planes per thread.  The target-side value is
+// loaded once per chunk and reused for all planes, vertically adjacent warps share source rows in L1, and each thread
+// keeps 4*kPlanes+1 independent 16-byte loads in flight per chunk.  (The first version, one voxel per thread and one
+// plane per block, re-fetched both maps from L2 for every plane and was L2-bandwidth bound: profiles/README.md.)
+constexpr int kPlanes = 4;
+
+template <int ALIGN>
+__global__ void __launch_bounds__(256) warp_cost_kernel(const float* __restrict__ ref_mix, const float* __restrict__ src_mix,
+                                                        const float* __restrict__ homo12,
+                                                        const float* __restrict__ depth_values,
+                                                        float* __restrict__ x0, int chunks, int D, int H, int W) {
+    const int w = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int h = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int d0 = blockIdx.z * kPlanes;
+    if (w >= W || h >= H) return;
+    const int HW = H * W;
+    const int p = h * W + w;
+    float hm[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) hm[i] = __ldg(homo12 + i);
+    Taps2 taps[kPlanes];
+#pragma unroll
+    for (int k = 0; k < kPlanes; ++k) {
+        const int d = min(d0 + k, D - 1);
+        taps[k] = plane_sweep_taps<ALIGN>(hm, (float)w, (float)h, __ldg(depth_values + d), H, W);
     }
-#pragma unroll 2
+    const size_t plane = (size_t)HW * 4;
+    const size_t out_chunk = (size_t)D * HW * 4;
+    const float* refp = ref_mix + (size_t)p * 4;
+    float* outp = x0 + ((size_t)d0 * HW + p) * 4;
+#pragma unroll 1
     for (int j = 0; j < chunks; ++j) {
         const float* s = src_mix + j * plane;
-        const float4 a = ldg4(s + o_nw), b = ldg4(s + o_ne), c = ldg4(s + o_sw), e = ldg4(s + o_se);
         const float4 r = ldg4(refp + j * plane);
-        float4 o;
-        o.x = r.x + fmaf(e.x, w_se, fmaf(c.x, w_sw, fmaf(b.x, w_ne, a.x * w_nw)));
-        o.y = r.y + fmaf(e.y, w_se, fmaf(c.y, w_sw, fmaf(b.y, w_ne, a.y * w_nw)));
-        o.z = r.z + fmaf(e.z, w_se, fmaf(c.z, w_sw, fmaf(b.z, w_ne, a.z * w_nw)));
-        o.w = r.w + fmaf(e.w, w_se, fmaf(c.w, w_sw, fmaf(b.w, w_ne, a.w * w_nw)));
-        st4(outp + j * out_chunk, o);
+        float4 a[kPlanes], b[kPlanes], c[kPlanes], e[kPlanes];
+#pragma unroll
+        for (int k = 0; k < kPlanes; ++k) {
+            a[k] = ldg4(s + taps[k].o_nw); b[k] = ldg4(s + taps[k].o_ne);
+            c[k] = ldg4(s + taps[k].o_sw); e[k] = ldg4(s + taps[k].o_se);
+        }
+#pragma unroll
+        for (int k = 0; k < kPlanes; ++k) {
+            if (d0 + k >= D) break;
+            const Taps2& t = taps[k];
+            float4 o;
+            o.x = r.x + fmaf(e[k].x, t.w_se, fmaf(c[k].x, t.w_sw, fmaf(b[k].x, t.w_ne, a[k].x * t.w_nw)));
+            o.y = r.y + fmaf(e[k].y, t.w_se, fmaf(c[k].y, t.w_sw, fmaf(b[k].y, t.w_ne, a[k].y * t.w_nw)));
+            o.z = r.z + fmaf(e[k].z, t.w_se, fmaf(c[k].z, t.w_sw, fmaf(b[k].z, t.w_ne, a[k].z * t.w_nw)));
+            o.w = r.w + fmaf(e[k].w, t.w_se, fmaf(c[k].w, t.w_sw, fmaf(b[k].w, t.w_ne, a[k].w * t.w_nw)));
+            st4(outp + j * out_chunk + (size_t)k * plane, o);
+        }
     }
 }
 
@@ -140,12 +164,11 @@ extern "C" int estd_warp_cost(const float* ref_mix_map4, const float* src_mix_ma
                               const float* depth_values, float* x0_vol4, int C, int D, int H, int W,
                               int align_corners, void* stream) {
     ESTD_REQUIRE(ref_mix_map4 && src_mix_map4 && homo12 && depth_values && x0_vol4, "estd_warp_cost: null pointer");
-    ESTD_REQUIRE(C > 0 && (C % 4) == 0 && D > 0 && D <= 65535 && H > 1 && W > 1,
+    ESTD_REQUIRE(C > 0 && (C % 4) == 0 && D > 0 && D <= 65535 * 4 && H > 1 && W > 1 && H <= 65535 * 8,
                  "estd_warp_cost: unsupported shape C=%d D=%d H=%d W=%d", C, D, H, W);
     ESTD_REQUIRE(estd::aligned16(ref_mix_map4) && estd::aligned16(src_mix_map4) && estd::aligned16(x0_vol4),
                  "estd_warp_cost: tensors must be 16-byte aligned");
-    const int HW = H * W;
-    dim3 grid((HW + 255) / 256, D);
+    dim3 grid((W + 31) / 32, (H + 7) / 8, (D + estd::kPlanes - 1) / estd::kPlanes);
     if (align_corners)
         estd::warp_cost_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(ref_mix_map4, src_mix_map4, homo12,
                                                                           depth_values, x0_vol4, C / 4, D, H, W);

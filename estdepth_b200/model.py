@@ -232,6 +232,13 @@ class DepthNetHybrid(nn.Module):
             return self._forward_val(imgs, cam_poses, cam_intr, pre_costs, pre_cam_poses)
 
     def _forward_val(self, imgs, cam_poses, cam_intr, pre_costs, pre_cam_poses):
+        return self.fuse(self.prepare(imgs, cam_poses, cam_intr), pre_costs, pre_cam_poses)
+
+    def prepare(self, imgs, cam_poses, cam_intr):
+        """Everything that does not depend on the hidden state (about 89 % of the FLOPs of a step):
+        2-D feeders, cost volumes, matching net, key/value volumes, initial depth.  ``forward`` is
+        ``fuse(prepare(...), pre_costs, pre_cam_poses)``; the split lets a rank of the ESTM clip pipeline
+        (``sharding.py``) run ahead while it waits for its predecessor's memory."""
         dev = imgs.device
         imgs = 2 * (imgs / 255.) - 1.
         B, V, _, Hi, Wi = imgs.shape
@@ -255,9 +262,35 @@ class DepthNetHybrid(nn.Module):
         poses = cam_poses.to(torch.float32).contiguous()
 
         init_logits = torch.empty(B * T, D, H, W, device=dev, dtype=torch.float32)
+        depth3 = torch.empty(B, T, 1, Hi, Wi, device=dev, dtype=torch.float32)
+        init_prob = torch.empty(B, T, 1, Hi, Wi, device=dev, dtype=torch.float32)
+        keys, values = [], []
+        for b in range(B):
+            ref_mix = [ops.premix(feats[b, v], L["pre0_ref"], L["pre0_bias"]) for v in range(V)]
+            src_mix = [ops.premix(feats[b, v], L["pre0_src"], None) for v in range(V)]
+            kb, vb = [], []
+            for t in range(T):
+                self._cost_volume(L, ws, ref_mix, src_mix, poses[b], K4[b], t, depth_values, ws.cost)
+                value, key = self._matching(L, ws, ws.cost, semantic_vs[b * T + t], depth_values,
+                                            init_logits[b * T + t], depth3[b, t, 0], init_prob[b, t, 0])
+                vb.append(value)
+                kb.append(key)
+            keys.append(kb)
+            values.append(vb)
+        return dict(B=B, V=V, T=T, D=D, H=H, W=W, Hi=Hi, Wi=Wi, dev=dev, keys=keys, values=values, poses=poses,
+                    cam_poses=cam_poses, K4=K4, semantic_vs=semantic_vs, skip_half=maps[0], depth3=depth3,
+                    init_prob=init_prob, depth_values=depth_values)
+
+    def fuse(self, prep, pre_costs=None, pre_cam_poses=None):
+        """EST fusion against the memory (or the no-EST path, quirk Q3), stereo_head1 + soft-argmin, 2-D refinement,
+        outputs and the hidden state to hand to the next call (hybrid_depth_decoder.py:211-292 / :373-417)."""
+        B, T, D, H, W, Hi, Wi, dev = (prep[k] for k in ("B", "T", "D", "H", "W", "Hi", "Wi", "dev"))
+        L = self._layers(dev)
+        ws = self._workspace(dev, D, H, W, L)
+        depth_values, poses, K4, cam_poses = prep["depth_values"], prep["poses"], prep["K4"], prep["cam_poses"]
         fused_logits = torch.empty(B * T, D, H, W, device=dev, dtype=torch.float32)
-        out = {name: torch.empty(B, T, 1, Hi, Wi, device=dev, dtype=torch.float32)
-               for name in ("depth3", "init_prob", "depth2", "fused_prob")}
+        depth2 = torch.empty(B, T, 1, Hi, Wi, device=dev, dtype=torch.float32)
+        fused_prob = torch.empty(B, T, 1, Hi, Wi, device=dev, dtype=torch.float32)
         use_est = self.IF_EST_transformer and pre_costs is not None              # quirk Q3 (hybrid_depth_decoder.py:423)
         pre_num = len(pre_cam_poses) if use_est else 0
         state_key = torch.empty(B, 16, D, H, W, device=dev, dtype=torch.float32)
@@ -265,15 +298,7 @@ class DepthNetHybrid(nn.Module):
         state_key._estd_vol4, state_value._estd_vol4 = [None] * B, [None] * B
 
         for b in range(B):
-            ref_mix = [ops.premix(feats[b, v], L["pre0_ref"], L["pre0_bias"]) for v in range(V)]
-            src_mix = [ops.premix(feats[b, v], L["pre0_src"], None) for v in range(V)]
-            values, keys = [], []
-            for t in range(T):
-                self._cost_volume(L, ws, ref_mix, src_mix, poses[b], K4[b], t, depth_values, ws.cost)
-                value, key = self._matching(L, ws, ws.cost, semantic_vs[b * T + t], depth_values,
-                                            init_logits[b * T + t], out["depth3"][b, t, 0], out["init_prob"][b, t, 0])
-                values.append(value)
-                keys.append(key)
+            values, keys = list(prep["values"][b]), list(prep["keys"][b])
             all_poses = [poses[b, t + 1] for t in range(T)]
             if use_est:
                 # memory volumes are appended after the current ones (hybrid_depth_decoder.py:220-224)
@@ -288,28 +313,27 @@ class DepthNetHybrid(nn.Module):
                     values[i] = fused                                             # quirk Q5 (:253)
                 ops.conv3d(L["head1"], values[i], ws.hid)
                 ops.head_softargmin(depth_values, hidden=ws.hid, head_w=L["head1_w"], head_b=L["head1_b"],
-                                    logits_out=fused_logits[b * T + i], depth_out=out["depth2"][b, i, 0],
-                                    prob_out=out["fused_prob"][b, i, 0], up=4)
+                                    logits_out=fused_logits[b * T + i], depth_out=depth2[b, i, 0],
+                                    prob_out=fused_prob[b, i, 0], up=4)
             ops.vol4_to_ncdhw(keys[T - 1], state_key[b])
             ops.vol4_to_ncdhw(values[T - 1], state_value[b])
             state_key._estd_vol4[b], state_value._estd_vol4[b] = keys[T - 1], values[T - 1]
-            if b == 0:
-                last_pose_src = (T + pre_num - 1) if (use_est and not self.fix_stale_pose) else (T - 1)
+        last_pose_src = (T + pre_num - 1) if (use_est and not self.fix_stale_pose) else (T - 1)
 
         # ---- 2-D refinement (cuDNN) ----
         t_prof = ops._pb()
-        depth_half, depth_full = self.CostRegNet.refine(semantic_vs, fused_logits, maps[0])
+        depth_half, depth_full = self.CostRegNet.refine(prep["semantic_vs"], fused_logits, prep["skip_half"])
         ops._pe(t_prof, "cudnn_2d_refine")
         depth_half = depth_half.reshape(B, T, 1, Hi, Wi)
         depth_full = depth_full.reshape(B, T, 1, Hi, Wi)
 
         outputs = {}
         for t in range(T):
-            outputs[("depth", t, 3)] = out["depth3"][:, t]
-            outputs[("init_prob", t)] = out["init_prob"][:, t]
+            outputs[("depth", t, 3)] = prep["depth3"][:, t]
+            outputs[("init_prob", t)] = prep["init_prob"][:, t]
         for t in range(T):
-            outputs[("depth", t, 2)] = out["depth2"][:, t]
-            outputs[("fused_prob", t)] = out["fused_prob"][:, t]
+            outputs[("depth", t, 2)] = depth2[:, t]
+            outputs[("fused_prob", t)] = fused_prob[:, t]
         for t in range(T):
             outputs[("depth", t, 1)] = depth_half[:, t]
         for t in range(T):

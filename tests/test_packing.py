@@ -1,0 +1,65 @@
+"""Host-side folding/packing against the oracle's un-fused arithmetic (CPU only)."""
+import torch
+import torch.nn.functional as F
+
+from estdepth_b200 import packing, synth
+from oracle import estdepth_oracle as orc
+from tests.helpers import from_vol4, state_template, to_vol4
+
+
+def _sd():
+    _, tmpl = state_template(18, 32)
+    return synth.synth_state_dict(tmpl, seed=4)
+
+
+def test_pre0_split_equals_conv_bn_of_concat():
+    sd = _sd()
+    g = torch.Generator().manual_seed(0)
+    ref = torch.randn(1, 32, 5, 6, 7, generator=g)
+    warped = torch.randn(1, 32, 5, 6, 7, generator=g)
+    want = orc._cb3(torch.cat([ref, warped], 1), sd, "pre0")
+    w_ref, w_src, bias = packing.split_pre0(sd)
+    got = torch.einsum("oc,bcdhw->bodhw", w_ref, ref) + torch.einsum("oc,bcdhw->bodhw", w_src, warped) + bias.view(1, -1, 1, 1, 1)
+    assert (got - want).abs().max() < 2e-5
+
+
+def _emulate(pc, x):
+    """conv with the packed [27][cin][cout] weights + affine, the way the kernel consumes them."""
+    cin = pc.weight.shape[1]
+    w = pc.weight.permute(2, 1, 0).reshape(pc.cout_pad, cin, 3, 3, 3)
+    y = F.conv3d(x.unsqueeze(0), w, None, 1, 1)[0]
+    return y * pc.scale.view(-1, 1, 1, 1) + pc.shift.view(-1, 1, 1, 1)
+
+
+def test_packed_layers_reproduce_the_oracle_chain():
+    sd = _sd()
+    L = packing.pack_layers(sd, torch.device("cpu"))
+    g = torch.Generator().manual_seed(1)
+    D, H, W = 4, 6, 8
+    m = torch.randn(32, D, H, W, generator=g)
+    sem = torch.randn(D, H, W, generator=g)
+    # dres2 on cat[sem, m] (reference order) vs packed layer on canonical order [m | sem,0,0,0]
+    want_z = orc._cb3(torch.cat([sem.unsqueeze(0), m], 0).unsqueeze(0), sd, "CostRegNet.dres2.0", "relu")[0]      # 33 ch
+    canon_in = torch.cat([m, sem.unsqueeze(0), torch.zeros(3, D, H, W)], 0)
+    z = torch.relu(_emulate(L["dres2"], canon_in))[:36]
+    assert (z[:32] - want_z[1:]).abs().max() < 1e-5 and (z[32] - want_z[0]).abs().max() < 1e-5
+    assert z[33:].abs().max() == 0
+    # fused value/key layer
+    want_v = orc._cb3(want_z.unsqueeze(0), sd, "CostRegNet.value_layer.0", "tanh")[0]
+    want_k = orc._cb3(want_z.unsqueeze(0), sd, "CostRegNet.key_layer.0", "relu")[0]
+    vk = _emulate(L["value_key"], z)
+    assert (torch.tanh(vk[:16]) - want_v).abs().max() < 1e-5 and (torch.relu(vk[16:]) - want_k).abs().max() < 1e-5
+    assert L["value_key"].act_split == 16 and L["dres2"].out_chunks == 9 and L["dres2"].cin == 33
+    # plain 32->32 and the biased EST convs
+    x = torch.randn(32, D, H, W, generator=g)
+    assert (torch.relu(_emulate(L["pre1"], x)) - orc._cb3(x.unsqueeze(0), sd, "pre1", "relu")[0]).abs().max() < 1e-5
+    p = "CostRegNet.epipolar_transformer"
+    want = F.conv3d(x.unsqueeze(0), sd[p + ".gate_conv.weight"], sd[p + ".gate_conv.bias"], 1, 1)[0]
+    assert (_emulate(L["gate"], x) - want).abs().max() < 1e-5
+
+
+def test_vol4_helpers_roundtrip():
+    x = torch.arange(16 * 2 * 3 * 5, dtype=torch.float32).reshape(16, 2, 3, 5)
+    v = to_vol4(x)
+    assert v.shape == (4, 2, 3, 5, 4) and v[1, 0, 0, 0, 2] == x[6, 0, 0, 0]
+    assert torch.equal(from_vol4(v), x)

@@ -1,0 +1,89 @@
+"""Host logic of the multi-GPU path on CPU: partitioning, and a world_size-2 gloo run of the ESTM clip pipeline with
+a stand-in model whose prepare/fuse mimic the hidden-state protocol (memory FIFO, stale pose)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from estdepth_b200 import sharding
+
+
+def test_partition_is_contiguous_balanced_and_complete():
+    for n in (0, 1, 7, 32, 33):
+        for world in (1, 2, 4, 8):
+            ranges = [sharding.partition(n, world, r) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            sizes = [b - a for a, b in ranges]
+            assert max(sizes) - min(sizes) <= 1
+    assert sharding.clip_steps(20, 3, 1, 0) == (0, 18)           # 20-frame ESTM clip -> 18 forwards (BASELINE cfg3)
+    assert sharding.partition(32, 8, 3) == (12, 16)              # cfg4: 32 sequences, 4 per rank
+    with pytest.raises(ValueError):
+        sharding.partition(4, 2, 2)
+
+
+class ToyModel(object):
+    """prepare: per-step feature; fuse: mixes in the memory exactly like the real protocol (order-sensitive)."""
+    shape = (1, 16, 2, 3, 4)
+
+    def prepare(self, imgs, poses, K):
+        return {"x": imgs.sum() * torch.ones(self.shape), "pose": poses[:, 1]}
+
+    def fuse(self, prep, pre_costs, pre_poses):
+        v = prep["x"].clone()
+        if pre_costs is not None:
+            for i, (k, p) in enumerate(zip(pre_costs["values"], pre_poses)):
+                v = v + 0.5 ** (i + 1) * k + p.sum()
+        pose = pre_poses[-1] if pre_poses else prep["pose"]          # quirk Q4
+        return {("depth", 0, 2): v.mean().reshape(1)}, {"keys": [v * 2], "values": [v]}, [pose]
+
+
+def _frames(s):
+    g = torch.Generator().manual_seed(s)
+    return torch.rand(1, 3, 3, 4, 4, generator=g), torch.rand(1, 3, 4, 4, generator=g), torch.eye(3).unsqueeze(0)
+
+
+def _sequential(n_frames):
+    m, mem, out = ToyModel(), [], []
+    for s in range(n_frames - 2):
+        pre = sharding._flatten_memory(mem)
+        o, c, p = m.fuse(m.prepare(*_frames(s)), pre[0], pre[1])
+        mem.append((c, p))
+        if len(mem) > 2:
+            mem.pop(0)
+        out.append(o[("depth", 0, 2)])
+    return torch.cat(out)
+
+
+def _worker(rank, world, port, n_frames, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pipe = sharding.EstmClipPipeline(ToyModel(), window=3, memory_size=2)
+    (start, stop), results = pipe.run(n_frames, _frames, ToyModel.shape, torch.device("cpu"))
+    local = torch.cat([r[("depth", 0, 2)] for r in results]).reshape(-1, 1) if results else torch.zeros(0, 1)
+    gathered = sharding.gather_maps(local)
+    if rank == 0:
+        q.put(torch.cat(gathered).reshape(-1).tolist())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [9, 4])
+def test_clip_pipeline_world2_equals_sequential(n_frames):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_frames, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = _sequential(n_frames)
+    assert torch.allclose(torch.tensor(got), want, rtol=0, atol=0)
