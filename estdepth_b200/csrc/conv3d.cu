@@ -14,41 +14,9 @@
 // 64 fp32 accumulators and issues ~21 FFMA per shared-memory load.  Stores are 16-byte, 512 B contiguous per warp.
 #include <cuda.h>
 #include "common.cuh"
+#include "conv3d_common.cuh"
 
 namespace estd {
-
-// ---------------------------------------------------------------- TMA / mbarrier PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a TMA that never lands (bad descriptor) traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
 
 // ---------------------------------------------------------------- kernel
 struct ConvParams {
@@ -266,45 +234,8 @@ conv3d_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = []() -> EncodeTiledFn {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            return nullptr;
-        return reinterpret_cast<EncodeTiledFn>(f);
-    }();
-    return fn;
-}
-
-// vol4 tensor [chunks][D][H][W][4] seen by TMA as 4-D (x = 4W floats, H, D, chunks); box = halo'd tile of one chunk.
 static int make_vol4_map(CUtensorMap* map, const float* base, int chunks, int D, int H, int W, int box_h, int box_d) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return fail(ESTD_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[4] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)chunks};
-    cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-    cuuint32_t box[4] = {(cuuint32_t)(TW + 2) * 4, (cuuint32_t)box_h, (cuuint32_t)box_d, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ESTD_ECUDA, "cuTensorMapEncodeTiled failed (%d) for vol4 [%d][%d][%d][%d][4]", (int)r, chunks, D, H, W);
-    return ESTD_OK;
-}
-
-static int sm_count() {
-    static int n = []() {
-        int dev = 0, v = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        return v > 0 ? v : 148;
-    }();
-    return n;
+    return make_vol4_tensor_map(map, base, chunks, D, H, W, (TW + 2) * 4, box_h, box_d, 1);
 }
 
 template <int CIN_CHUNKS, int COUT_PAD, int RG>
@@ -352,16 +283,19 @@ static int dispatch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_o
     const int cin_chunks = d->in0_chunks + d->in1_chunks;
     ESTD_REQUIRE(d->D > 0 && d->H > 0 && d->W > 0, "estd_conv3d: bad volume %dx%dx%d", d->D, d->H, d->W);
     if (!count_only) {
-        ESTD_REQUIRE(d->in0 && d->weight && d->scale && d->shift && d->out0, "estd_conv3d: null pointer");
+        ESTD_REQUIRE(d->in0 && (d->weight || d->weight_tc) && d->scale && d->shift && d->out0, "estd_conv3d: null pointer");
         ESTD_REQUIRE(d->in0_chunks > 0 && d->in1_chunks >= 0 && (d->in1_chunks == 0 || d->in1), "estd_conv3d: bad input segments");
         ESTD_REQUIRE(d->out0_chunks > 0 && d->out1_chunks >= 0 && (d->out1_chunks == 0 || d->out1), "estd_conv3d: bad output segments");
         ESTD_REQUIRE((d->out0_chunks + d->out1_chunks) * 4 <= d->cout_pad, "estd_conv3d: outputs exceed cout_pad");
         ESTD_REQUIRE(d->act_split >= 0 && (d->act_split % 8) == 0, "estd_conv3d: act_split must be a multiple of 8");
-        ESTD_REQUIRE(aligned16(d->in0) && aligned16(d->out0) && aligned16(d->weight) && (!d->in1 || aligned16(d->in1)) &&
+        ESTD_REQUIRE(aligned16(d->in0) && aligned16(d->out0) && (!d->weight || aligned16(d->weight)) && (!d->in1 || aligned16(d->in1)) &&
                      (!d->out1 || aligned16(d->out1)) && (!d->res0 || aligned16(d->res0)) && (!d->res1 || aligned16(d->res1)),
                      "estd_conv3d: tensors must be 16-byte aligned");
         ESTD_REQUIRE((d->W * 16) % 16 == 0 && d->W * 4 <= (1 << 30), "estd_conv3d: W too large");
     }
+    if (d->precision == ESTD_PREC_3XTF32) return dispatch_tc(d, stream, count_only, n_ctas);
+    ESTD_REQUIRE(d->precision == ESTD_PREC_FP32, "estd_conv3d: unknown precision %d", d->precision);
+    ESTD_REQUIRE(count_only || d->weight, "estd_conv3d: precision=fp32 needs `weight`");
     if (cin_chunks == 8 && d->cout_pad == 32) return launch<8, 32, 2>(d, stream, count_only, n_ctas);
     if (cin_chunks == 9 && d->cout_pad == 40) return launch<9, 40, 2>(d, stream, count_only, n_ctas);
     if (cin_chunks == 9 && d->cout_pad == 32) return launch<9, 32, 2>(d, stream, count_only, n_ctas);

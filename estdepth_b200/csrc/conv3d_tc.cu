@@ -1,0 +1,337 @@
+// K2 on the 5th-generation tensor cores: 3x3x3 convolution as an implicit GEMM with error-compensated TF32
+// ("3xTF32": x = x_hi + x_lo, w = w_hi + w_lo, products x_hi w_hi + x_hi w_lo + x_lo w_hi accumulated in fp32 in
+// TMEM).  Single-pass TF32 or BF16 misses the 1e-3 depth gate by 1-3 orders of magnitude; the
+// split keeps ~21 mantissa bits per product, i.e. fp32-class accuracy, at 3 MMAs per product.
+//
+// Mapping (one CTA per SM, persistent over work units; unit = 16 (h) x 32 (w) output voxels of one depth plane):
+//   GEMM  D[M = voxels, N = Cout] += A[M, K] * B[N, K]^T,  K = 27 taps x Cin, walked as 3 planes x (Cin/8) k-steps
+//   A     never materialised (no im2col): one TMA box per stage brings the halo'd input tile of one input plane and
+//         8 channels, [2 chunks][18 rows][34 cols][4 floats] with hardware zero fill for the padding.  In the
+//         no-swizzle K-major UMMA layout a core matrix is 8 rows x 16 bytes, so 8 consecutive voxels along w (16 B
+//         apart) form its rows, the next 8-row group is the next image row (SBO = row pitch) and the second half of
+//         K is the next channel chunk (LBO = chunk pitch): every one of the 9 in-plane taps of every M tile (16 rows
+//         x 8 columns = 128 voxels) is just a different 16-byte-granular start address into the same tile.
+//   B     per-stage weight block [9 taps][2 k-halves][2*Cout rows (w_hi | w_lo)][4 floats], one bulk copy.
+//   MMA   per tap and M tile: D[:, 0:2C] (+)= A_hi * [W_hi | W_lo]  (N = 2C, one instruction for two products) and
+//         D[:, C:2C] += A_lo * W_hi (N = C); the epilogue adds the two halves.  Accumulators: 4 M tiles x 2C columns
+//         of TMEM, double buffered across units so the epilogue of unit u overlaps the MMAs of unit u+1.
+//   warps 0: TMA producer, 1: MMA issuer, 2: TMEM allocator, 4-7: hi/lo splitter (masks the landed tile to its TF32
+//         part in place and writes the residual tile), 8-11: epilogue (tcgen05.ld -> affine/activation/residual ->
+//         16-byte stores, GroupNorm partial sums).  All hand-offs are mbarriers; waits are bounded (trap, not hang).
+#include <cuda.h>
+#include "common.cuh"
+#include "conv3d_common.cuh"
+
+namespace estd {
+
+namespace tc {
+
+constexpr int TILE_H = 16, TILE_W = 32, HALO_H = TILE_H + 2, HALO_W = TILE_W + 2;
+constexpr int A_CHUNK_BYTES = HALO_H * HALO_W * 16;          // one 4-channel chunk of the halo tile  (9792)
+constexpr int A_BYTES = 2 * A_CHUNK_BYTES;                    // 8 channels                              (19584)
+constexpr int STAGES = 3;
+constexpr int THREADS = 384;
+constexpr uint32_t TF32_MASK = 0xFFFFE000u;
+
+template <int COUT>
+struct Cfg {
+    static constexpr int N_ALL = 2 * COUT;                                 // [W_hi | W_lo]
+    static constexpr int W_TAP_BYTES = 2 * N_ALL * 16;                     // [2 k-halves][N_ALL rows][16 B]
+    static constexpr int W_BYTES = 9 * W_TAP_BYTES;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + W_BYTES;              // A_hi, A_lo, W
+    static constexpr int COLS_PER_UNIT = 4 * N_ALL;                        // 4 M tiles
+    static constexpr int NBUF = (2 * COLS_PER_UNIT <= 512) ? 2 : 1;
+    static constexpr int TMEM_COLS = (NBUF * COLS_PER_UNIT <= 32) ? 32 : (NBUF * COLS_PER_UNIT <= 64) ? 64
+                                   : (NBUF * COLS_PER_UNIT <= 128) ? 128 : (NBUF * COLS_PER_UNIT <= 256) ? 256 : 512;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;     // + barriers / tmem base
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// commit: the mbarrier gets one arrival when every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::tf32, cta_group::1
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread (thread i of the warp reads TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): start address, LBO (byte distance
+// between the two 16-byte K halves), SBO (byte distance between 8-row groups), all >> 4; version = 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+struct Params {
+    const float* weight_tc;                     // [3 dd][NKS][9 taps][2][2*COUT][4]
+    ConvEpilogue ep;
+    int in0_chunks;
+    int D, H, W;
+    int tiles_h, tiles_w, n_units;
+};
+
+template <int NKS, int COUT>
+__global__ void __launch_bounds__(THREADS, 1)
+conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Params p) {
+    using C = Cfg<COUT>;
+    constexpr int N_STAGES_PER_UNIT = 3 * NKS;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;                  // [STAGES] TMA landed
+    uint64_t* ready = bars + STAGES;        // [STAGES] split done
+    uint64_t* empty = bars + 2 * STAGES;    // [STAGES] MMAs done reading
+    uint64_t* acc_full = bars + 3 * STAGES; // [2]
+    uint64_t* acc_empty = acc_full + 2;     // [2]
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    __shared__ double s_red[4][4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_base_smem, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    const int n_mine = (p.n_units > (int)blockIdx.x) ? (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    auto unit_origin = [&](int k, int& d, int& h0, int& w0) {
+        const int u = blockIdx.x + k * gridDim.x;
+        const int tw = u % p.tiles_w;
+        const int th = (u / p.tiles_w) % p.tiles_h;
+        d = u / (p.tiles_w * p.tiles_h);
+        h0 = th * TILE_H; w0 = tw * TILE_W;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int it = 0;
+            for (int k = 0; k < n_mine; ++k) {
+                int d, h0, w0;
+                unit_origin(k, d, h0, w0);
+                for (int st = 0; st < N_STAGES_PER_UNIT; ++st, ++it) {
+                    const int s = it % STAGES;
+                    if (it >= STAGES) mbar_wait(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
+                    const int dd = st / NKS, ks = st % NKS;
+                    unsigned char* stage = smem + (size_t)s * C::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(A_BYTES + C::W_BYTES));
+                    const int chunk = 2 * ks;
+                    if (chunk < p.in0_chunks) tma_load_4d(stage, &map0, &full[s], 4 * (w0 - 1), h0 - 1, d + dd - 1, chunk);
+                    else                      tma_load_4d(stage, &map1, &full[s], 4 * (w0 - 1), h0 - 1, d + dd - 1, chunk - p.in0_chunks);
+                    bulk_load(stage + 2 * A_BYTES, p.weight_tc + (size_t)(dd * NKS + ks) * (C::W_BYTES / 4), (uint32_t)C::W_BYTES, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc_all = make_idesc(C::N_ALL), idesc_hi = make_idesc(COUT);
+            int it = 0;
+            for (int k = 0; k < n_mine; ++k) {
+                const int buf = k % C::NBUF;
+                const int use = k / C::NBUF;                            // how many times this buffer was used before
+                if (use > 0) mbar_wait(&acc_empty[buf], (uint32_t)((use - 1) & 1));
+                tc_fence_after();
+                const uint32_t acc0 = tmem_base + (uint32_t)(buf * C::COLS_PER_UNIT);
+                for (int st = 0; st < N_STAGES_PER_UNIT; ++st, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&ready[s], (uint32_t)((it / STAGES) & 1));
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + A_BYTES;
+                    const uint32_t w_s = a_hi + 2 * A_BYTES;
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int dh = tap / 3, dw = tap % 3;
+                        const uint64_t b_desc = make_desc(w_s + tap * C::W_TAP_BYTES, C::N_ALL * 16, 128);
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) {
+                            const uint32_t off = (uint32_t)((dh * HALO_W + 8 * mt + dw) * 16);
+                            const uint32_t acc = acc0 + (uint32_t)(mt * C::N_ALL);
+                            const uint32_t first = (st == 0 && tap == 0) ? 0u : 1u;
+                            umma_tf32(acc, make_desc(a_hi + off, A_CHUNK_BYTES, HALO_W * 16), b_desc, idesc_all, first);
+                            umma_tf32(acc + COUT, make_desc(a_lo + off, A_CHUNK_BYTES, HALO_W * 16), b_desc, idesc_hi, 1u);
+                        }
+                    }
+                    umma_commit(&empty[s]);                              // stage s may be refilled once these MMAs retire
+                    if (st == N_STAGES_PER_UNIT - 1) umma_commit(&acc_full[buf]);
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== hi/lo splitter =====================
+        const int t = tid - 128;
+        int it = 0;
+        for (int k = 0; k < n_mine; ++k) {
+            for (int st = 0; st < N_STAGES_PER_UNIT; ++st, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+                uint4* hi = reinterpret_cast<uint4*>(smem + (size_t)s * C::STAGE_BYTES);
+                uint4* lo = reinterpret_cast<uint4*>(smem + (size_t)s * C::STAGE_BYTES + A_BYTES);
+                for (int i = t; i < A_BYTES / 16; i += 128) {
+                    const uint4 x = hi[i];
+                    uint4 h, l;
+                    h.x = x.x & TF32_MASK; h.y = x.y & TF32_MASK; h.z = x.z & TF32_MASK; h.w = x.w & TF32_MASK;
+                    l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x)) & TF32_MASK;
+                    l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y)) & TF32_MASK;
+                    l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z)) & TF32_MASK;
+                    l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w)) & TF32_MASK;
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+                fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async proxy
+                mbar_arrive(&ready[s]);
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;                 // row of the M tile = voxel (h = m / 8, w = m % 8)
+        const int mh = m >> 3, mw = m & 7;
+        double gs[2] = {0.0, 0.0}, gq[2] = {0.0, 0.0};
+        const size_t vox = (size_t)p.D * p.H * p.W;
+        for (int k = 0; k < n_mine; ++k) {
+            const int buf = k % C::NBUF;
+            const int use = k / C::NBUF;
+            int d, h0, w0;
+            unit_origin(k, d, h0, w0);
+            mbar_wait(&acc_full[buf], (uint32_t)(use & 1));
+            tc_fence_after();
+            const uint32_t acc0 = tmem_base + (uint32_t)(buf * C::COLS_PER_UNIT) + ((uint32_t)(q * 32) << 16);
+            const int h = h0 + mh;
+#pragma unroll 1
+            for (int mt = 0; mt < 4; ++mt) {
+                const int w = w0 + 8 * mt + mw;
+                const bool ok = (h < p.H) && (w < p.W);
+                const size_t pos = ((size_t)d * p.H + h) * p.W + w;
+#pragma unroll 1
+                for (int c0 = 0; c0 < COUT; c0 += 16) {
+                    float a[16], b[16];
+                    tmem_ld16(acc0 + (uint32_t)(mt * C::N_ALL + c0), a);
+                    tmem_ld16(acc0 + (uint32_t)(mt * C::N_ALL + COUT + c0), b);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) a[i] += b[i];
+                    float ts[2] = {0.f, 0.f}, tq[2] = {0.f, 0.f};
+                    conv_epilogue_store16(p.ep, a, c0, ok, pos, vox, ts, tq);
+                    gs[0] += (double)ts[0]; gq[0] += (double)tq[0];
+                    gs[1] += (double)ts[1]; gq[1] += (double)tq[1];
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);
+        }
+        if (p.ep.gn_partials) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                gs[0] += __shfl_xor_sync(0xffffffffu, gs[0], o); gq[0] += __shfl_xor_sync(0xffffffffu, gq[0], o);
+                gs[1] += __shfl_xor_sync(0xffffffffu, gs[1], o); gq[1] += __shfl_xor_sync(0xffffffffu, gq[1], o);
+            }
+            if (lane == 0) { s_red[q][0] = gs[0]; s_red[q][1] = gq[0]; s_red[q][2] = gs[1]; s_red[q][3] = gq[1]; }
+            asm volatile("bar.sync 1, 128;" ::: "memory");            // the 4 epilogue warps only
+            if (warp == 8 && lane == 0) {
+                double* dst = p.ep.gn_partials + (size_t)blockIdx.x * 4;
+                for (int j = 0; j < 4; ++j) dst[j] = ((s_red[0][j] + s_red[1][j]) + s_red[2][j]) + s_red[3][j];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+static int make_halo_map(CUtensorMap* map, const float* base, int chunks, int D, int H, int W) {
+    return make_vol4_tensor_map(map, base, chunks, D, H, W, HALO_W * 4, HALO_H, 1, 2);
+}
+
+template <int NKS, int COUT>
+static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas) {
+    using C = Cfg<COUT>;
+    const int tiles_h = (d->H + TILE_H - 1) / TILE_H, tiles_w = (d->W + TILE_W - 1) / TILE_W;
+    const int n_units = d->D * tiles_h * tiles_w;
+    const int grid = n_units < sm_count() ? n_units : sm_count();
+    *n_ctas = grid;
+    if (count_only) return ESTD_OK;
+    ESTD_REQUIRE(d->weight_tc && aligned16(d->weight_tc), "estd_conv3d: precision=3xTF32 needs a 16-byte aligned weight_tc");
+    ESTD_REQUIRE(d->in1_chunks == 0 || (d->in0_chunks % 2) == 0, "estd_conv3d(3xTF32): first input segment must hold an even number of chunks");
+    CUtensorMap map0, map1;
+    int rc = make_halo_map(&map0, d->in0, d->in0_chunks, d->D, d->H, d->W);
+    if (rc) return rc;
+    if (d->in1_chunks > 0) rc = make_halo_map(&map1, d->in1, d->in1_chunks, d->D, d->H, d->W);
+    else map1 = map0;
+    if (rc) return rc;
+    Params p;
+    p.weight_tc = d->weight_tc;
+    fill_epilogue(&p.ep, d);
+    p.in0_chunks = d->in0_chunks;
+    p.D = d->D; p.H = d->H; p.W = d->W;
+    p.tiles_h = tiles_h; p.tiles_w = tiles_w; p.n_units = n_units;
+    auto kern = conv3d_tc_kernel<NKS, COUT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return fail(ESTD_ECUDA, "estd_conv3d(3xTF32): cannot reserve %zu B of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    kern<<<grid, THREADS, C::SMEM, stream>>>(map0, map1, p);
+    return check_launch("estd_conv3d(3xTF32)");
+}
+
+}  // namespace tc
+
+int dispatch_tc(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas) {
+    const int cin_chunks = d->in0_chunks + d->in1_chunks;
+    const int nks = (cin_chunks + 1) / 2;
+    if (nks == 4 && d->cout_pad == 32) return tc::launch<4, 32>(d, stream, count_only, n_ctas);
+    if (nks == 5 && d->cout_pad == 48) return tc::launch<5, 48>(d, stream, count_only, n_ctas);
+    if (nks == 5 && d->cout_pad == 32) return tc::launch<5, 32>(d, stream, count_only, n_ctas);
+    if (nks == 2 && d->cout_pad == 16) return tc::launch<2, 16>(d, stream, count_only, n_ctas);
+    if (nks == 4 && d->cout_pad == 16) return tc::launch<4, 16>(d, stream, count_only, n_ctas);
+    return fail(ESTD_EUNSUPPORTED, "estd_conv3d(3xTF32): no kernel for %d input chunks -> cout_pad %d", cin_chunks, d->cout_pad);
+}
+
+}  // namespace estd

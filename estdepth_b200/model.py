@@ -82,12 +82,14 @@ class _Workspace(object):
 
 class DepthNetHybrid(nn.Module):
     def __init__(self, ndepths=64, depth_min=0.01, depth_max=10.0, resnet=50, IF_EST_transformer=True,
-                 align_corners=False, fix_stale_pose=False):
+                 align_corners=False, fix_stale_pose=False, precision="3xtf32"):
         """First five arguments: hybrid_models/model_hybrid.py:15-16.  Extra, keyword-only in practice:
 
         align_corners   grid_sample semantics of the warps: False = torch >= 1.3 (what the reference computes when run
                         today, and what the oracle pins); True = the torch 1.2 it was written for (quirk Q1).
         fix_stale_pose  opt-in fix of quirk Q4 (return the current target's pose with the hidden state).
+        precision       arithmetic of the 3-D convolutions: "3xtf32" = error-compensated TF32 on the tcgen05 tensor cores
+                        (fp32-class accuracy, the default), "fp32" = exact fp32 on the CUDA cores.
         """
         super().__init__()
         self.ndepths = int(ndepths)
@@ -100,6 +102,9 @@ class DepthNetHybrid(nn.Module):
         self.IF_EST_transformer = bool(IF_EST_transformer)
         self.align_corners = bool(align_corners)
         self.fix_stale_pose = bool(fix_stale_pose)
+        if precision not in ops.PRECISION:
+            raise ValueError("precision must be one of %s" % sorted(ops.PRECISION))
+        self.precision = precision
 
         self.matchingFeature = MatchingFeatureNet()
         self.semanticFeature = ContextEncoder(resnet)
@@ -147,9 +152,13 @@ class DepthNetHybrid(nn.Module):
     def _workspace(self, device, D, H, W, L):
         key = (str(device), D, H, W)
         if self._ws is None or self._ws.key != key:
-            rows = max(ops.conv3d_num_ctas(L["head0"], D, H, W), ops.conv3d_num_ctas(L["pre1"], D, H, W)) + 8
+            rows = max(ops.conv3d_num_ctas(L[n], D, H, W, precision=q) for n in ("gate", "output")
+                       for q in ops.PRECISION) + 8
             self._ws = _Workspace(device, D, H, W, rows)
         return self._ws
+
+    def _conv(self, pc, *args, **kwargs):
+        return ops.conv3d(pc, *args, precision=self.precision, **kwargs)
 
     def scale_cam_intr(self, cam_intr, scale):
         out = cam_intr.clone()
@@ -162,27 +171,27 @@ class DepthNetHybrid(nn.Module):
         for n, s in enumerate((t, t + 2)):
             ops.homography_setup(poses[t + 1], poses[s], K4, ws.homo)
             ops.warp_cost(ref_mix[t + 1], src_mix[s], ws.homo, depth_values, ws.x0, self.align_corners)
-            ops.conv3d(L["pre1"], ws.x0, ws.y)
+            self._conv(L["pre1"], ws.x0, ws.y)
             if n == 0:      # cost = x0 + pre2(pre1(x0))
-                ops.conv3d(L["pre2"], ws.y, ws.cost, res0=ws.x0)
+                self._conv(L["pre2"], ws.y, ws.cost, res0=ws.x0)
             else:           # cost = (cost + x0 + pre2(pre1(x0))) / 2
-                ops.conv3d(L["pre2"], ws.y, out, res0=ws.x0, res1=ws.cost, post_scale=0.5)
+                self._conv(L["pre2"], ws.y, out, res0=ws.x0, res1=ws.cost, post_scale=0.5)
         return out
 
     def _matching(self, L, ws, cost, semantic_vs_t, depth_values, logits_out, depth_out, prob_out):
         """dres0..2, value/key heads, stereo_head0 + soft-argmin (hybrid_depth_decoder.py:187-209)."""
         dev = cost.device
         _, D, H, W, _ = cost.shape
-        ops.conv3d(L["dres0.0"], cost, ws.a)
-        ops.conv3d(L["dres0.1"], ws.a, ws.b)
-        ops.conv3d(L["dres1.0"], ws.b, ws.a)
-        ops.conv3d(L["dres1.1"], ws.a, ws.b)
+        self._conv(L["dres0.0"], cost, ws.a)
+        self._conv(L["dres0.1"], ws.a, ws.b)
+        self._conv(L["dres1.0"], ws.b, ws.a)
+        self._conv(L["dres1.1"], ws.a, ws.b)
         ops.scalar_to_vol4(semantic_vs_t, ws.sem)
-        ops.conv3d(L["dres2"], ws.b, ws.z, in1=ws.sem)
+        self._conv(L["dres2"], ws.b, ws.z, in1=ws.sem)
         value = torch.empty(4, D, H, W, 4, device=dev, dtype=torch.float32)
         key = torch.empty(4, D, H, W, 4, device=dev, dtype=torch.float32)
-        ops.conv3d(L["value_key"], ws.z, value, out1=key)
-        ops.conv3d(L["head0"], value, ws.hid)
+        self._conv(L["value_key"], ws.z, value, out1=key)
+        self._conv(L["head0"], value, ws.hid)
         ops.head_softargmin(depth_values, hidden=ws.hid, head_w=L["head0_w"], head_b=L["head0_b"],
                             logits_out=logits_out, depth_out=depth_out, prob_out=prob_out, up=4)
         return value, key
@@ -196,12 +205,12 @@ class DepthNetHybrid(nn.Module):
         ops.est_attend(key_i, src_keys, src_values, ws.warp30, depth_values, self.depth_min, self.depth_interval,
                        out=ws.h, align_corners=self.align_corners)
         count = 16.0 * D * H * W
-        rows_f = ops.conv3d_num_ctas(L["gate"], D, H, W)
-        ops.conv3d(L["gate"], value_i, ws.f, in1=ws.h, gn_partials=ws.part_f)
+        rows_f = ops.conv3d_num_ctas(L["gate"], D, H, W, precision=self.precision)
+        self._conv(L["gate"], value_i, ws.f, in1=ws.h, gn_partials=ws.part_f)
         ops.gn_finalize(ws.part_f[:rows_f], 2, count, out=ws.stats_f)
         ops.gru_reset(ws.f, ws.h, ws.stats_f, L["gn_r_w"], L["gn_r_b"], out=ws.rh)
-        rows_o = ops.conv3d_num_ctas(L["output"], D, H, W)
-        ops.conv3d(L["output"], value_i, ws.o, in1=ws.rh, gn_partials=ws.part_o)
+        rows_o = ops.conv3d_num_ctas(L["output"], D, H, W, precision=self.precision)
+        self._conv(L["output"], value_i, ws.o, in1=ws.rh, gn_partials=ws.part_o)
         ops.gn_finalize(ws.part_o[:rows_o], 1, count, out=ws.stats_o)
         fused = torch.empty_like(value_i)
         ops.gru_blend(ws.f, ws.h, ws.o, ws.stats_f, ws.stats_o, L["gn_u_w"], L["gn_u_b"], L["gn_o_w"], L["gn_o_b"],
@@ -311,7 +320,7 @@ class DepthNetHybrid(nn.Module):
                     fused = self._fuse(L, ws, keys[i], values[i], [keys[j] for j in others], [values[j] for j in others],
                                        all_poses[i], [all_poses[j] for j in others], K4[b], depth_values)
                     values[i] = fused                                             # quirk Q5 (:253)
-                ops.conv3d(L["head1"], values[i], ws.hid)
+                self._conv(L["head1"], values[i], ws.hid)
                 ops.head_softargmin(depth_values, hidden=ws.hid, head_w=L["head1_w"], head_b=L["head1_b"],
                                     logits_out=fused_logits[b * T + i], depth_out=depth2[b, i, 0],
                                     prob_out=fused_prob[b, i, 0], up=4)

@@ -19,7 +19,10 @@ from . import _lib
 from ._lib import ConvDesc, check
 
 ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2}
+PRECISION = {"fp32": 0, "3xtf32": 1}
 MAX_SOURCES = 8
+# default arithmetic of conv3d: "fp32" = exact CUDA-core kernel, "3xtf32" = error-compensated TF32 on tcgen05
+DEFAULT_PRECISION = "fp32"
 
 
 class KernelProfile(object):
@@ -136,26 +139,37 @@ def warp_cost(ref_mix, src_mix, homo12, depth_values, out=None, align_corners=Fa
 class PackedConv(object):
     """Folded, packed parameters of one 3x3x3 layer (see packing.pack_conv3d)."""
     __slots__ = ("weight", "scale", "shift", "cin_chunks", "cout_pad", "out_chunks", "act_split", "act_lo", "act_hi",
-                 "cin", "cout")
+                 "cin", "cout", "weight_tc", "cout_pad_tc")
 
     def __init__(self, weight, scale, shift, cin_chunks, cout_pad, out_chunks, act_split, act_lo, act_hi,
-                 cin=None, cout=None):
+                 cin=None, cout=None, weight_tc=None, cout_pad_tc=None):
         self.weight, self.scale, self.shift = weight, scale, shift
+        self.weight_tc, self.cout_pad_tc = weight_tc, cout_pad_tc      # tcgen05 packing (packing.pack_weight_tc)
         self.cin = cin if cin is not None else 4 * cin_chunks          # real (un-padded) channel counts, for flop accounting
         self.cout = cout if cout is not None else min(cout_pad, 4 * out_chunks)
         self.cin_chunks, self.cout_pad, self.out_chunks = cin_chunks, cout_pad, out_chunks
         self.act_split, self.act_lo, self.act_hi = act_split, ACT[act_lo], ACT[act_hi]
 
 
-def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials):
+def _precision(pc, precision):
+    precision = DEFAULT_PRECISION if precision is None else precision
+    if precision == "3xtf32" and pc.weight_tc is None:
+        raise RuntimeError("conv3d: layer was packed without tensor-core weights (packing.attach_tc)")
+    return precision
+
+
+def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision):
     chunks0, D, H, W, _ = in0.shape
     d = ConvDesc()
+    d.precision = PRECISION[precision]
     d.in0, d.in0_chunks = _ptr(in0), chunks0
     d.in1, d.in1_chunks = (_ptr(in1), in1.shape[0]) if in1 is not None else (None, 0)
     if d.in0_chunks + d.in1_chunks != pc.cin_chunks:
         raise RuntimeError("conv3d: layer packed for %d input chunks, got %d" % (pc.cin_chunks, d.in0_chunks + d.in1_chunks))
-    d.weight, d.scale, d.shift = _ptr(pc.weight), _ptr(pc.scale), _ptr(pc.shift)
-    d.cout_pad, d.act_split, d.act_lo, d.act_hi = pc.cout_pad, pc.act_split, pc.act_lo, pc.act_hi
+    d.weight, d.weight_tc = _ptr(pc.weight), _ptr(pc.weight_tc)
+    d.scale, d.shift = _ptr(pc.scale), _ptr(pc.shift)
+    d.cout_pad = pc.cout_pad_tc if precision == "3xtf32" else pc.cout_pad
+    d.act_split, d.act_lo, d.act_hi = pc.act_split, pc.act_lo, pc.act_hi
     d.res0, d.res1 = _ptr(res0), _ptr(res1)
     d.post_scale = float(post_scale)
     d.out0, d.out0_chunks = _ptr(out0), out0.shape[0]
@@ -167,9 +181,12 @@ def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials):
     return d
 
 
-def conv3d_num_ctas(pc, D, H, W):
+def conv3d_num_ctas(pc, D, H, W, precision=None):
+    precision = _precision(pc, precision)
     d = ConvDesc()
-    d.in0_chunks, d.in1_chunks, d.cout_pad = pc.cin_chunks, 0, pc.cout_pad
+    d.precision = PRECISION[precision]
+    d.in0_chunks, d.in1_chunks = pc.cin_chunks, 0
+    d.cout_pad = pc.cout_pad_tc if precision == "3xtf32" else pc.cout_pad
     d.D, d.H, d.W = D, H, W
     n = _lib.get().estd_conv3d_num_ctas(ctypes.byref(d))
     if n < 0:
@@ -177,13 +194,16 @@ def conv3d_num_ctas(pc, D, H, W):
     return n
 
 
-def conv3d(pc, in0, out0, in1=None, out1=None, res0=None, res1=None, post_scale=1.0, gn_partials=None):
-    """3x3x3 conv + folded affine + activation (+ residuals, x post_scale) over vol4 tensors; returns out0."""
-    d = _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials)
+def conv3d(pc, in0, out0, in1=None, out1=None, res0=None, res1=None, post_scale=1.0, gn_partials=None, precision=None):
+    """3x3x3 conv + folded affine + activation (+ residuals, x post_scale) over vol4 tensors; returns out0.
+
+    precision: "fp32" (exact, CUDA cores) | "3xtf32" (tcgen05 tensor cores, error-compensated) | None = DEFAULT_PRECISION."""
+    precision = _precision(pc, precision)
+    d = _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision)
     t = _pb()
     check(_lib.get().estd_conv3d(ctypes.byref(d), _stream()), "estd_conv3d")
     vox = float(d.D) * d.H * d.W
-    _pe(t, "conv3d", 54.0 * pc.cin * pc.cout * vox, 4.0 * vox * (pc.cin + pc.cout))     # SURVEY 8d (K2)
+    _pe(t, "conv3d_" + precision, 54.0 * pc.cin * pc.cout * vox, 4.0 * vox * (pc.cin + pc.cout))     # SURVEY 8d (K2)
     return out0
 
 

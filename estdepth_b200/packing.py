@@ -54,6 +54,46 @@ def pack_weight(weight, cin_order, cout_order):
     return out.contiguous()
 
 
+TF32_MASK = -8192          # 0xFFFFE000 as int32: keeps sign, exponent and the 10 explicit TF32 mantissa bits
+AFFINE_PAD = 48            # scale/shift arrays are padded to the widest cout_pad of either kernel
+
+
+def tc_cout_pad(cout_pad):
+    """N of the tensor-core kernel: a multiple of 16 (UMMA M=128 needs N % 16 == 0)."""
+    return (cout_pad + 15) // 16 * 16
+
+
+def pack_weight_tc(packed, cout_pad_tc=None):
+    """SIMT packing [27][cin_pad][cout_pad] -> tcgen05 packing [3 dd][nks][9 taps][2 k-halves][2*C rows][4] (fp32).
+
+    Rows 0..C-1 hold w_hi = w truncated to TF32, rows C..2C-1 hold w_lo = (w - w_hi) truncated to TF32; the 4 floats
+    of a row are input channels 8*ks + 4*khalf + (0..3); K is zero padded to a multiple of 8 channels.
+    """
+    taps, cin_pad, cout_pad = packed.shape
+    C = tc_cout_pad(cout_pad) if cout_pad_tc is None else cout_pad_tc
+    nks = (cin_pad + 7) // 8
+    w = torch.zeros(27, 8 * nks, C, dtype=torch.float32, device=packed.device)
+    w[:, :cin_pad, :cout_pad] = packed
+    hi = (w.view(torch.int32) & TF32_MASK).view(torch.float32)
+    lo = ((w - hi).view(torch.int32) & TF32_MASK).view(torch.float32)
+
+    def arrange(x):      # [27 = dd*9+tap9][8*nks = ks*8+k2*4+e][C] -> [dd][ks][tap9][k2][C][e]
+        return x.reshape(3, 9, nks, 2, 4, C).permute(0, 2, 1, 3, 5, 4)
+
+    return torch.cat([arrange(hi), arrange(lo)], dim=4).contiguous()
+
+
+def attach_tc(pc):
+    """Adds the tensor-core packing to a PackedConv and pads its affine arrays."""
+    pc.cout_pad_tc = tc_cout_pad(pc.cout_pad)
+    pc.weight_tc = pack_weight_tc(pc.weight, pc.cout_pad_tc)
+    for name in ("scale", "shift"):
+        v = getattr(pc, name)
+        if v.numel() < AFFINE_PAD:
+            setattr(pc, name, torch.cat([v, torch.zeros(AFFINE_PAD - v.numel(), dtype=v.dtype, device=v.device)]).contiguous())
+    return pc
+
+
 def _affine(scale, shift, cout_order, device):
     s = torch.zeros(len(cout_order), dtype=torch.float32, device=device)
     b = torch.zeros(len(cout_order), dtype=torch.float32, device=device)
@@ -110,6 +150,9 @@ def pack_layers(sd, device):
         for gate, key in (("r", "reset_gate_norm"), ("u", "update_gate_norm"), ("o", "output_norm")):
             layers["gn_%s_w" % gate] = sd["%s.%s.weight" % (est, key)].to(device=device, dtype=torch.float32).contiguous()
             layers["gn_%s_b" % gate] = sd["%s.%s.bias" % (est, key)].to(device=device, dtype=torch.float32).contiguous()
+    for v in layers.values():
+        if isinstance(v, PackedConv):
+            attach_tc(v)
     w_ref, w_src, bias = split_pre0(sd)
     layers["pre0_ref"], layers["pre0_src"], layers["pre0_bias"] = w_ref.to(device), w_src.to(device), bias.to(device)
     return layers

@@ -44,6 +44,9 @@ extern "C" {
 
 #define ESTD_MAX_SOURCES 8          /* max N of the EST attention */
 
+#define ESTD_PREC_FP32   0          /* exact fp32 on the CUDA cores                                          */
+#define ESTD_PREC_3XTF32 1          /* error-compensated TF32 on the tcgen05 tensor cores (fp32-class accuracy) */
+
 ESTD_API int estd_version(void);
 ESTD_API const char* estd_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
@@ -88,10 +91,12 @@ ESTD_API int estd_warp_cost(const float* ref_mix_map4, const float* src_mix_map4
 typedef struct estd_conv3d_desc {
     const float* in0;  int in0_chunks;    /* vol4 input, first channel segment                          */
     const float* in1;  int in1_chunks;    /* optional second segment (torch.cat on channels), or NULL/0  */
-    const float* weight;                  /* packed [27][cin_pad][cout_pad], cin_pad = 4*(in0+in1 chunks) */
+    const float* weight;                  /* packed [27][cin_pad][cout_pad], cin_pad = 4*(in0+in1 chunks) (ESTD_PREC_FP32) */
+    const float* weight_tc;               /* packed [3][nks][9][2][2*cout_pad][4] hi|lo TF32 split (ESTD_PREC_3XTF32), else NULL */
+    int precision;                        /* ESTD_PREC_*; cout_pad is 16/32/40 for FP32 and 16/32/48 for 3XTF32 */
     const float* scale;                   /* [cout_pad] per-channel multiplier (folded BN gamma/sqrt(var+eps)) */
     const float* shift;                   /* [cout_pad] per-channel offset (folded BN beta - mean*scale, or conv bias) */
-    int cout_pad;                         /* 16, 32 or 40 */
+    int cout_pad;                         /* padded number of output channels (see precision) */
     int act_split;                        /* channels [0,act_split) use act_lo, [act_split,cout_pad) act_hi; multiple of 8 */
     int act_lo, act_hi;                   /* ESTD_ACT_* */
     const float* res0; const float* res1; /* optional vol4 tensors (cout_pad/4 chunks) added after the activation */

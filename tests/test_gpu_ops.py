@@ -127,10 +127,12 @@ CONV_CASES = [
 ]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 @pytest.mark.parametrize("shape", [(5, 21, 40), (8, 32, 64)], ids=["ragged", "aligned"])
-def test_conv3d_vs_torch_cpu(case, shape):
-    """K2 against F.conv3d (CPU fp32) + affine + activation + residuals, all channel configurations, ragged edges."""
+def test_conv3d_vs_torch_cpu(case, shape, precision):
+    """K2 (both the exact CUDA-core kernel and the 3xTF32 tcgen05 kernel) against F.conv3d (CPU fp32) + affine +
+    activation + residuals, all channel configurations, ragged edges."""
     name, cin_seg, cout, cout_pad, out_seg, act_split, act_lo, act_hi = case
     D, H, W = shape
     g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)
@@ -146,7 +148,8 @@ def test_conv3d_vs_torch_cpu(case, shape):
     s_pad = torch.zeros(cout_pad)
     b_pad = torch.zeros(cout_pad)
     s_pad[:cout], b_pad[:cout] = scale, shift
-    pc = ops.PackedConv(pw.to(DEV), s_pad.to(DEV), b_pad.to(DEV), sum(cin_seg), cout_pad, sum(out_seg), act_split, act_lo, act_hi)
+    pc = packing.attach_tc(ops.PackedConv(pw.to(DEV), s_pad.to(DEV), b_pad.to(DEV), sum(cin_seg), cout_pad, sum(out_seg),
+                                          act_split, act_lo, act_hi))
 
     y = F.conv3d(x.unsqueeze(0), w, None, 1, 1)[0] * scale.view(-1, 1, 1, 1) + shift.view(-1, 1, 1, 1)
     acts = {"none": lambda t: t, "relu": torch.relu, "tanh": torch.tanh}
@@ -159,14 +162,18 @@ def test_conv3d_vs_torch_cpu(case, shape):
     xin = to_vol4(x).to(DEV)
     ins = [xin[:cin_seg[0]].contiguous()] + ([xin[cin_seg[0]:].contiguous()] if len(cin_seg) > 1 else [])
     outs = [torch.full((c, D, H, W, 4), float("nan"), device=DEV) for c in out_seg]
-    n_ctas = ops.conv3d_num_ctas(pc, D, H, W)
+    n_ctas = ops.conv3d_num_ctas(pc, D, H, W, precision=precision)
     partials = torch.zeros(n_ctas, 2, 2, device=DEV, dtype=torch.float64)
     ops.conv3d(pc, ins[0], outs[0], in1=ins[1] if len(ins) > 1 else None, out1=outs[1] if len(outs) > 1 else None,
-               res0=to_vol4(res0).to(DEV), res1=to_vol4(res1).to(DEV), post_scale=0.5, gn_partials=partials)
+               res0=to_vol4(res0).to(DEV), res1=to_vol4(res1).to(DEV), post_scale=0.5, gn_partials=partials,
+               precision=precision)
     got = from_vol4(torch.cat(outs, 0).cpu())
     assert torch.isfinite(got).all()
-    # K = 27*cin <= 972 fp32 products of O(1)/sqrt(K) terms: round-off ~ 1e-6; 3e-5 leaves margin for tanh
-    assert maxdiff(got, want) < 3e-5
+    err = maxdiff(got, want)
+    print("conv3d %s %s %s: max |err| = %.3e" % (name, shape, precision, err))
+    # K = 27*cin <= 972 fp32 products of O(1)/sqrt(K) terms: round-off ~ 1e-6; 3e-5 leaves margin for tanh.
+    # 3xTF32 drops the x_lo*w_lo products (2^-22 relative each): same bound.
+    assert err < 3e-5
     # deterministic GroupNorm partial sums (over the real, written channels of each group)
     tot = partials.sum(0).cpu()
     real = want.clone()
@@ -178,18 +185,19 @@ def test_conv3d_vs_torch_cpu(case, shape):
         assert abs(tot[1, 1].item() - (g1 ** 2).sum().item()) < 1e-4 * (g1 ** 2).sum().item()
 
 
-def test_conv3d_is_bitwise_deterministic():
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
+def test_conv3d_is_bitwise_deterministic(precision):
     g = torch.Generator().manual_seed(5)
     D, H, W = 6, 24, 64
     x = to_vol4(torch.randn(32, D, H, W, generator=g)).to(DEV)
     w = torch.randn(32, 32, 3, 3, 3, generator=g) / 30
-    pc = ops.PackedConv(packing.pack_weight(w, list(range(32)), list(range(32))).to(DEV), torch.ones(32, device=DEV),
-                        torch.zeros(32, device=DEV), 8, 32, 8, 16, "none", "none")
+    pc = packing.attach_tc(ops.PackedConv(packing.pack_weight(w, list(range(32)), list(range(32))).to(DEV),
+                                          torch.ones(32, device=DEV), torch.zeros(32, device=DEV), 8, 32, 8, 16, "none", "none"))
     outs, parts = [], []
     for _ in range(2):
         y = torch.empty_like(x)
-        p = torch.zeros(ops.conv3d_num_ctas(pc, D, H, W), 2, 2, device=DEV, dtype=torch.float64)
-        ops.conv3d(pc, x, y, gn_partials=p)
+        p = torch.zeros(ops.conv3d_num_ctas(pc, D, H, W, precision=precision), 2, 2, device=DEV, dtype=torch.float64)
+        ops.conv3d(pc, x, y, gn_partials=p, precision=precision)
         outs.append(y.cpu())
         parts.append(p.cpu())
     assert torch.equal(outs[0], outs[1]) and torch.equal(parts[0], parts[1])

@@ -28,7 +28,7 @@ def _emulate(pc, x):
     cin = pc.weight.shape[1]
     w = pc.weight.permute(2, 1, 0).reshape(pc.cout_pad, cin, 3, 3, 3)
     y = F.conv3d(x.unsqueeze(0), w, None, 1, 1)[0]
-    return y * pc.scale.view(-1, 1, 1, 1) + pc.shift.view(-1, 1, 1, 1)
+    return y * pc.scale[:pc.cout_pad].view(-1, 1, 1, 1) + pc.shift[:pc.cout_pad].view(-1, 1, 1, 1)
 
 
 def test_packed_layers_reproduce_the_oracle_chain():
@@ -56,6 +56,23 @@ def test_packed_layers_reproduce_the_oracle_chain():
     p = "CostRegNet.epipolar_transformer"
     want = F.conv3d(x.unsqueeze(0), sd[p + ".gate_conv.weight"], sd[p + ".gate_conv.bias"], 1, 1)[0]
     assert (_emulate(L["gate"], x) - want).abs().max() < 1e-5
+
+
+def test_tensor_core_packing_is_an_exact_two_term_split():
+    g = torch.Generator().manual_seed(2)
+    packed = torch.randn(27, 36, 40, generator=g)
+    tc = packing.pack_weight_tc(packed)                       # [3][5][9][2][96][4]
+    assert tuple(tc.shape) == (3, 5, 9, 2, 96, 4)
+    hi, lo = tc[..., :48, :], tc[..., 48:, :]
+    # both parts are exactly representable in TF32 (13 low mantissa bits clear) ...
+    assert int((hi.contiguous().view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert int((lo.contiguous().view(torch.int32) & 0x1FFF).abs().max()) == 0
+    # ... and hi + lo reproduces the fp32 weight to 2^-21 relative, in the kernel's (dd, ks, tap, khalf, n, e) order
+    w = torch.zeros(27, 40, 48)
+    w[:, :36, :40] = packed
+    want = w.reshape(3, 9, 5, 2, 4, 48).permute(0, 2, 1, 3, 5, 4)
+    assert ((hi + lo) - want).abs().max() <= 2.0 ** -21 * want.abs().max()
+    assert torch.equal(hi[0, 0, 4, 1, 7, 2], (w[4, 6, 7].view(torch.int32) & -8192).view(torch.float32))
 
 
 def test_vol4_helpers_roundtrip():
