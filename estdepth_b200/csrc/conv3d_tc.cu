@@ -55,6 +55,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -167,38 +176,45 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc_all = make_idesc(C::N_ALL), idesc_hi = make_idesc(COUT);
-            int it = 0;
-            for (int k = 0; k < n_mine; ++k) {
-                const int buf = k % C::NBUF;
-                const int use = k / C::NBUF;                            // how many times this buffer was used before
-                if (use > 0) mbar_wait(&acc_empty[buf], (uint32_t)((use - 1) & 1));
+        // Warp-uniform control flow; one elected lane issues.  Descriptors are built once per stage and advanced by
+        // compile-time constants (fully unrolled taps x M tiles) so that the single issuing thread spends a couple of
+        // uniform-datapath instructions per MMA -- with per-MMA descriptor arithmetic the issue rate of that one
+        // thread, not the tensor pipe, bounded the kernel (profiles/README.md, r01 -> r02).
+        const uint32_t idesc_all = make_idesc(C::N_ALL), idesc_hi = make_idesc(COUT);
+        const bool leader = elect_one();
+        int it = 0;
+        for (int k = 0; k < n_mine; ++k) {
+            const int buf = k % C::NBUF;
+            const int use = k / C::NBUF;                            // how many times this buffer was used before
+            if (use > 0) mbar_wait(&acc_empty[buf], (uint32_t)((use - 1) & 1));
+            tc_fence_after();
+            const uint32_t acc0 = tmem_base + (uint32_t)(buf * C::COLS_PER_UNIT);
+            for (int st = 0; st < N_STAGES_PER_UNIT; ++st, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&ready[s], (uint32_t)((it / STAGES) & 1));
                 tc_fence_after();
-                const uint32_t acc0 = tmem_base + (uint32_t)(buf * C::COLS_PER_UNIT);
-                for (int st = 0; st < N_STAGES_PER_UNIT; ++st, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&ready[s], (uint32_t)((it / STAGES) & 1));
-                    tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
-                    const uint32_t a_lo = a_hi + A_BYTES;
-                    const uint32_t w_s = a_hi + 2 * A_BYTES;
-#pragma unroll 1
+                const uint32_t a_hi = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
+                const uint64_t a_hi_desc = make_desc(a_hi, A_CHUNK_BYTES, HALO_W * 16);
+                const uint64_t a_lo_desc = make_desc(a_hi + A_BYTES, A_CHUNK_BYTES, HALO_W * 16);
+                const uint64_t b_desc = make_desc(a_hi + 2 * A_BYTES, C::N_ALL * 16, 128);
+                const uint32_t first = (st == 0) ? 0u : 1u;
+                if (leader) {
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        const int dh = tap / 3, dw = tap % 3;
-                        const uint64_t b_desc = make_desc(w_s + tap * C::W_TAP_BYTES, C::N_ALL * 16, 128);
 #pragma unroll
                         for (int mt = 0; mt < 4; ++mt) {
-                            const uint32_t off = (uint32_t)((dh * HALO_W + 8 * mt + dw) * 16);
+                            // start-address field is in 16-byte units: one voxel (float4) per unit
+                            const uint64_t a_off = (uint64_t)((tap / 3) * HALO_W + 8 * mt + (tap % 3));
+                            const uint64_t b_off = (uint64_t)(tap * (C::W_TAP_BYTES >> 4));
                             const uint32_t acc = acc0 + (uint32_t)(mt * C::N_ALL);
-                            const uint32_t first = (st == 0 && tap == 0) ? 0u : 1u;
-                            umma_tf32(acc, make_desc(a_hi + off, A_CHUNK_BYTES, HALO_W * 16), b_desc, idesc_all, first);
-                            umma_tf32(acc + COUT, make_desc(a_lo + off, A_CHUNK_BYTES, HALO_W * 16), b_desc, idesc_hi, 1u);
+                            umma_tf32(acc, a_hi_desc + a_off, b_desc + b_off, idesc_all, tap == 0 ? first : 1u);
+                            umma_tf32(acc + COUT, a_lo_desc + a_off, b_desc + b_off, idesc_hi, 1u);
                         }
                     }
                     umma_commit(&empty[s]);                              // stage s may be refilled once these MMAs retire
                     if (st == N_STAGES_PER_UNIT - 1) umma_commit(&acc_full[buf]);
                 }
+                __syncwarp();
             }
         }
     } else if (warp >= 4 && warp < 8) {
