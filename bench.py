@@ -200,7 +200,8 @@ def run_ours(args):
     from estdepth_b200 import DepthNetHybrid, synth, ops, _lib
     V, H, W, D, resnet = WORKLOADS[args.workload]
     T = V - 2
-    model = DepthNetHybrid(ndepths=D, depth_min=0.1, depth_max=10.0, resnet=resnet)
+    model = DepthNetHybrid(ndepths=D, depth_min=0.1, depth_max=10.0, resnet=resnet,
+                           **({"precision": args.precision} if args.precision else {}))
     model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=0))
     model.eval().to(dev)
 
@@ -274,13 +275,17 @@ def run_ours(args):
     e2e = frames / (ms_e2e * 1e-3)
     kernels = kernel_rooflines(prof, args.workload, peaks)
     dom = max(kernels.items(), key=lambda kv: kv[1]["share_ms_per_step"])
-    conv = kernels.get("conv3d", dom[1])
-    roofline = {"kernel": "conv3d (3x3x3, fp32 SIMT)" if "conv3d" in kernels else dom[0], "bound": "tensor",
+    conv_name = "conv3d_" + model.precision
+    conv = kernels.get(conv_name, dom[1])
+    mma_per_flop = {"fp32": 0.0, "3xtf32": 3.0, "3xf16": 3.0}[model.precision]
+    roofline = {"kernel": "estd conv3d_tc_kernel (3x3x3 implicit GEMM, %s)" % model.precision if conv_name in kernels else dom[0], "bound": "tensor",
                 "achieved": conv.get("TFLOPps"), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": (conv.get("TFLOPps") or 0.0) / peaks["bf16_sustained"], "traffic": None,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "note": "fp32-exact CUDA-core kernel measured against the dense bf16 tensor peak; share of step = %.1f%%"
-                        % (100.0 * conv["share_ms_per_step"] / sum(k["share_ms_per_step"] for k in kernels.values()))}
+                "note": "achieved = ALGORITHMIC fp32 conv flops (54*Cin*Cout*Vx) / CUDA-event time, averaged over the step's launches; "
+                        "the error-compensated split issues %.0fx that many tensor-core flops; peak = dense bf16 (cuBLAS). "
+                        "share of step = %.1f%%" % (mma_per_flop, 100.0 * conv["share_ms_per_step"] / sum(k["share_ms_per_step"] for k in kernels.values())),
+                "tensor_flops_issued_TFLOPps": (conv.get("TFLOPps") or 0.0) * mma_per_flop}
     cpu_base, _ = (None, None)
     if not args.no_cpu_baseline:
         cpu_base, _ = oracle_sample(args.workload, 1, 1, budget_s=60.0)
@@ -288,7 +293,7 @@ def run_ours(args):
     d2h = sum(t.numel() * t.element_size() for t in host_out)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_resident / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32 (conv3d: %s)" % model.precision, "data": "synthetic",
             "config": {"workload": "%s: 5-frame %dx%d Joint window, D=%d, ResNet-%d, steady-state EST window (1 memory volume), "
                                    "3 depth maps/step, 1 sequence per GPU" % (args.workload, H, W, D, resnet),
                        "l2": "volumes are 157 MB each (> 126 MB L2); no explicit flush", "cudnn_tf32": False},
@@ -306,6 +311,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=None, choices=["fp32", "3xtf32", "3xf16"], help="conv3d arithmetic (default: the model's)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~1 min oracle timing on the host cores")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -18,7 +18,7 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [
         ("in0", c_void_p), ("in0_chunks", ctypes.c_int),
         ("in1", c_void_p), ("in1_chunks", ctypes.c_int),
-        ("weight", c_void_p), ("weight_tc", c_void_p), ("precision", ctypes.c_int),
+        ("weight", c_void_p), ("weight_tc", c_void_p), ("precision", ctypes.c_int), ("status", c_void_p),
         ("scale", c_void_p), ("shift", c_void_p),
         ("cout_pad", ctypes.c_int), ("act_split", ctypes.c_int), ("act_lo", ctypes.c_int), ("act_hi", ctypes.c_int),
         ("res0", c_void_p), ("res1", c_void_p),

@@ -15,10 +15,11 @@
 //   MMA   per tap and M tile: D[:, 0:2C] (+)= A_hi * [W_hi | W_lo]  (N = 2C, one instruction for two products) and
 //         D[:, C:2C] += A_lo * W_hi (N = C); the epilogue adds the two halves.  Accumulators: 4 M tiles x 2C columns
 //         of TMEM, double buffered across units so the epilogue of unit u overlaps the MMAs of unit u+1.
-//   warps 0: TMA producer, 1: MMA issuer, 2: TMEM allocator, 4-7: hi/lo splitter (masks the landed tile to its TF32
-//         part in place and writes the residual tile), 8-11: epilogue (tcgen05.ld -> affine/activation/residual ->
-//         16-byte stores, GroupNorm partial sums).  All hand-offs are mbarriers; waits are bounded (trap, not hang).
+//   warps 0: TMA producer, 1: MMA issuer, 2: TMEM allocator, 4-7: epilogue (tcgen05.ld -> affine/activation/residual ->
+//         16-byte stores, GroupNorm partial sums), 8-15: hi/lo splitter (turns the landed fp32 tile into its two
+//         low-precision terms in place).  All hand-offs are mbarriers; waits are bounded (trap, not hang).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "conv3d_common.cuh"
 
@@ -27,18 +28,44 @@ namespace estd {
 namespace tc {
 
 constexpr int TILE_H = 16, TILE_W = 32, HALO_H = TILE_H + 2, HALO_W = TILE_W + 2;
-constexpr int A_CHUNK_BYTES = HALO_H * HALO_W * 16;          // one 4-channel chunk of the halo tile  (9792)
-constexpr int A_BYTES = 2 * A_CHUNK_BYTES;                    // 8 channels                              (19584)
+constexpr int HALO_VOX = HALO_H * HALO_W;                     // 612 voxels in the halo tile
+constexpr int A_CHUNK_BYTES = HALO_VOX * 16;                  // one 16-byte K-group of the halo tile        (9792)
+constexpr int A_BYTES = 4 * A_CHUNK_BYTES;                    // operand area of one stage: 4 K-groups       (39168)
 constexpr int STAGES = 3;
-constexpr int THREADS = 384;
+constexpr int SPLIT_WARPS = 8, SPLIT_THREADS = SPLIT_WARPS * 32;
+constexpr int THREADS = 256 + SPLIT_THREADS;          // warps 0-3 control, 4-7 epilogue, 8.. splitters
 constexpr uint32_t TF32_MASK = 0xFFFFE000u;
+
+// Two split arithmetics share the kernel (template parameter KIND):
+//   KIND_TF32  stage = 8 channels.  TMA lands 2 fp32 chunks in K-groups 0,1; the splitter masks them to TF32 in place
+//              (x_hi) and writes x_lo = tf32(x - x_hi) to K-groups 2,3.  kind::tf32, K = 8 per MMA.
+//   KIND_F16   stage = 16 channels.  TMA lands 4 fp32 chunks; the splitter turns each pair of chunks (8 channels of
+//              a voxel = 32 B of fp32) IN PLACE into one K-group of x_hi = fp16(x) and one of x_lo = fp16(x - x_hi)
+//              (8 x fp16 = 16 B each): same bytes, twice the channels per MMA.  kind::f16, K = 16 per MMA.  Weights
+//              are pre-scaled by a power of two so that w_lo stays a normal fp16; activations beyond the fp16 range
+//              raise the status flag.  x_hi*w_hi, x_hi*w_lo, x_lo*w_hi are exact in the fp32 accumulator either way.
+constexpr int KIND_TF32 = 0, KIND_F16 = 1;
+
+template <int KIND> struct KindTraits;
+template <> struct KindTraits<KIND_TF32> {
+    static constexpr int CHUNKS = 2;                                  // fp32 chunks landed per stage
+    static constexpr uint32_t A_LO_OFFSET = 2 * A_CHUNK_BYTES;        // x_lo K-groups start here
+    static constexpr uint32_t A_LBO = A_CHUNK_BYTES;                  // distance between the two K-groups of one MMA
+    static constexpr uint32_t FORMAT = 2;                             // UMMA a/b format: TF32
+};
+template <> struct KindTraits<KIND_F16> {
+    static constexpr int CHUNKS = 4;
+    static constexpr uint32_t A_LO_OFFSET = A_CHUNK_BYTES;            // pair p: [hi K-group | lo K-group]
+    static constexpr uint32_t A_LBO = 2 * A_CHUNK_BYTES;
+    static constexpr uint32_t FORMAT = 0;                             // F16
+};
 
 template <int COUT>
 struct Cfg {
     static constexpr int N_ALL = 2 * COUT;                                 // [W_hi | W_lo]
-    static constexpr int W_TAP_BYTES = 2 * N_ALL * 16;                     // [2 k-halves][N_ALL rows][16 B]
+    static constexpr int W_TAP_BYTES = 2 * N_ALL * 16;                     // [2 K-groups][N_ALL rows][16 B]
     static constexpr int W_BYTES = 9 * W_TAP_BYTES;
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + W_BYTES;              // A_hi, A_lo, W
+    static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;                  // operand area (x_hi, x_lo), W
     static constexpr int COLS_PER_UNIT = 4 * N_ALL;                        // 4 M tiles
     static constexpr int NBUF = (2 * COLS_PER_UNIT <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (NBUF * COLS_PER_UNIT <= 32) ? 32 : (NBUF * COLS_PER_UNIT <= 64) ? 64
@@ -78,13 +105,22 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::tf32, cta_group::1
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, cta_group::1
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (KIND == KIND_TF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    }
 }
 // 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread (thread i of the warp reads TMEM lane base+i)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -96,6 +132,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ uint32_t h2u(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): start address, LBO (byte distance
@@ -104,23 +141,25 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
            (1ull << 46);
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = n.
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = fmt (2 TF32 / 0 F16), K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t make_idesc(uint32_t fmt, int n) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 struct Params {
-    const float* weight_tc;                     // [3 dd][NKS][9 taps][2][2*COUT][4]
+    const float* weight_tc;                     // [3 dd][NKS][9 taps][2 K-groups][2*COUT rows][16 bytes]
+    int* status;                                // optional: set to 1 when an activation leaves the fp16 range (KIND_F16)
     ConvEpilogue ep;
     int in0_chunks;
     int D, H, W;
     int tiles_h, tiles_w, n_units;
 };
 
-template <int NKS, int COUT>
+template <int KIND, int NKS, int COUT>
 __global__ void __launch_bounds__(THREADS, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Params p) {
     using C = Cfg<COUT>;
+    using KT = KindTraits<KIND>;
     constexpr int N_STAGES_PER_UNIT = 3 * NKS;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * C::STAGE_BYTES);
@@ -135,7 +174,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], SPLIT_THREADS); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
         fence_mbar_init();
     }
@@ -166,11 +205,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                     if (it >= STAGES) mbar_wait(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
                     const int dd = st / NKS, ks = st % NKS;
                     unsigned char* stage = smem + (size_t)s * C::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)(A_BYTES + C::W_BYTES));
-                    const int chunk = 2 * ks;
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(KT::CHUNKS * A_CHUNK_BYTES + C::W_BYTES));
+                    const int chunk = KT::CHUNKS * ks;
                     if (chunk < p.in0_chunks) tma_load_4d(stage, &map0, &full[s], 4 * (w0 - 1), h0 - 1, d + dd - 1, chunk);
                     else                      tma_load_4d(stage, &map1, &full[s], 4 * (w0 - 1), h0 - 1, d + dd - 1, chunk - p.in0_chunks);
-                    bulk_load(stage + 2 * A_BYTES, p.weight_tc + (size_t)(dd * NKS + ks) * (C::W_BYTES / 4), (uint32_t)C::W_BYTES, &full[s]);
+                    bulk_load(stage + A_BYTES, p.weight_tc + (size_t)(dd * NKS + ks) * (C::W_BYTES / 4), (uint32_t)C::W_BYTES, &full[s]);
                 }
             }
         }
@@ -180,7 +219,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         // compile-time constants (fully unrolled taps x M tiles) so that the single issuing thread spends a couple of
         // uniform-datapath instructions per MMA -- with per-MMA descriptor arithmetic the issue rate of that one
         // thread, not the tensor pipe, bounded the kernel (profiles/README.md, r01 -> r02).
-        const uint32_t idesc_all = make_idesc(C::N_ALL), idesc_hi = make_idesc(COUT);
+        const uint32_t idesc_all = make_idesc(KT::FORMAT, C::N_ALL), idesc_hi = make_idesc(KT::FORMAT, COUT);
         const bool leader = elect_one();
         int it = 0;
         for (int k = 0; k < n_mine; ++k) {
@@ -194,9 +233,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                 mbar_wait(&ready[s], (uint32_t)((it / STAGES) & 1));
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
-                const uint64_t a_hi_desc = make_desc(a_hi, A_CHUNK_BYTES, HALO_W * 16);
-                const uint64_t a_lo_desc = make_desc(a_hi + A_BYTES, A_CHUNK_BYTES, HALO_W * 16);
-                const uint64_t b_desc = make_desc(a_hi + 2 * A_BYTES, C::N_ALL * 16, 128);
+                const uint64_t a_hi_desc = make_desc(a_hi, KT::A_LBO, HALO_W * 16);
+                const uint64_t a_lo_desc = make_desc(a_hi + KT::A_LO_OFFSET, KT::A_LBO, HALO_W * 16);
+                const uint64_t b_desc = make_desc(a_hi + A_BYTES, C::N_ALL * 16, 128);
                 const uint32_t first = (st == 0) ? 0u : 1u;
                 if (leader) {
 #pragma unroll
@@ -207,8 +246,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                             const uint64_t a_off = (uint64_t)((tap / 3) * HALO_W + 8 * mt + (tap % 3));
                             const uint64_t b_off = (uint64_t)(tap * (C::W_TAP_BYTES >> 4));
                             const uint32_t acc = acc0 + (uint32_t)(mt * C::N_ALL);
-                            umma_tf32(acc, a_hi_desc + a_off, b_desc + b_off, idesc_all, tap == 0 ? first : 1u);
-                            umma_tf32(acc + COUT, a_lo_desc + a_off, b_desc + b_off, idesc_hi, 1u);
+                            umma<KIND>(acc, a_hi_desc + a_off, b_desc + b_off, idesc_all, tap == 0 ? first : 1u);
+                            umma<KIND>(acc + COUT, a_lo_desc + a_off, b_desc + b_off, idesc_hi, 1u);
                         }
                     }
                     umma_commit(&empty[s]);                              // stage s may be refilled once these MMAs retire
@@ -217,32 +256,57 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                 __syncwarp();
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 8) {
         // ===================== hi/lo splitter =====================
-        const int t = tid - 128;
+        const int t = tid - 256;
         int it = 0;
         for (int k = 0; k < n_mine; ++k) {
             for (int st = 0; st < N_STAGES_PER_UNIT; ++st, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
-                uint4* hi = reinterpret_cast<uint4*>(smem + (size_t)s * C::STAGE_BYTES);
-                uint4* lo = reinterpret_cast<uint4*>(smem + (size_t)s * C::STAGE_BYTES + A_BYTES);
-                for (int i = t; i < A_BYTES / 16; i += 128) {
-                    const uint4 x = hi[i];
-                    uint4 h, l;
-                    h.x = x.x & TF32_MASK; h.y = x.y & TF32_MASK; h.z = x.z & TF32_MASK; h.w = x.w & TF32_MASK;
-                    l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x)) & TF32_MASK;
-                    l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y)) & TF32_MASK;
-                    l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z)) & TF32_MASK;
-                    l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w)) & TF32_MASK;
-                    hi[i] = h;
-                    lo[i] = l;
+                unsigned char* area = smem + (size_t)s * C::STAGE_BYTES;
+                if constexpr (KIND == KIND_TF32) {
+                    uint4* hi = reinterpret_cast<uint4*>(area);
+                    uint4* lo = reinterpret_cast<uint4*>(area + KT::A_LO_OFFSET);
+                    for (int i = t; i < 2 * HALO_VOX; i += SPLIT_THREADS) {
+                        const uint4 x = hi[i];
+                        uint4 h, l;
+                        h.x = x.x & TF32_MASK; h.y = x.y & TF32_MASK; h.z = x.z & TF32_MASK; h.w = x.w & TF32_MASK;
+                        l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x)) & TF32_MASK;
+                        l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y)) & TF32_MASK;
+                        l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z)) & TF32_MASK;
+                        l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w)) & TF32_MASK;
+                        hi[i] = h;
+                        lo[i] = l;
+                    }
+                } else {
+                    float amax = 0.0f;
+                    for (int i = t; i < 2 * HALO_VOX; i += SPLIT_THREADS) {
+                        const int pair = i / HALO_VOX, v = i - pair * HALO_VOX;
+                        float4* c0 = reinterpret_cast<float4*>(area + (size_t)pair * 2 * A_CHUNK_BYTES) + v;     // channels 8p..8p+3
+                        float4* c1 = c0 + HALO_VOX;                                                                // channels 8p+4..8p+7
+                        const float4 a = *c0, b = *c1;
+                        amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                                                 fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+                        const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+                        const __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+                        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+                        const __half2 l0 = __floats2half2_rn(a.x - f0.x, a.y - f0.y), l1 = __floats2half2_rn(a.z - f1.x, a.w - f1.y);
+                        const __half2 l2 = __floats2half2_rn(b.x - f2.x, b.y - f2.y), l3 = __floats2half2_rn(b.z - f3.x, b.w - f3.y);
+                        uint4 hv, lv;
+                        hv.x = h2u(h0); hv.y = h2u(h1); hv.z = h2u(h2); hv.w = h2u(h3);
+                        lv.x = h2u(l0); lv.y = h2u(l1); lv.z = h2u(l2); lv.w = h2u(l3);
+                        *reinterpret_cast<uint4*>(c0) = hv;          // x_hi K-group of this pair
+                        *reinterpret_cast<uint4*>(c1) = lv;          // x_lo K-group of this pair
+                    }
+                    const bool bad = !(amax <= 65504.0f);            // Inf included; NaN propagates through fp16 as NaN, like the reference
+                    if (bad && p.status) atomicOr(p.status, 1);
                 }
                 fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async proxy
                 mbar_arrive(&ready[s]);
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;                 // row of the M tile = voxel (h = m / 8, w = m % 8)
@@ -288,7 +352,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             }
             if (lane == 0) { s_red[q][0] = gs[0]; s_red[q][1] = gq[0]; s_red[q][2] = gs[1]; s_red[q][3] = gq[1]; }
             asm volatile("bar.sync 1, 128;" ::: "memory");            // the 4 epilogue warps only
-            if (warp == 8 && lane == 0) {
+            if (warp == 4 && lane == 0) {
                 double* dst = p.ep.gn_partials + (size_t)blockIdx.x * 4;
                 for (int j = 0; j < 4; ++j) dst[j] = ((s_red[0][j] + s_red[1][j]) + s_red[2][j]) + s_red[3][j];
             }
@@ -300,11 +364,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-static int make_halo_map(CUtensorMap* map, const float* base, int chunks, int D, int H, int W) {
-    return make_vol4_tensor_map(map, base, chunks, D, H, W, HALO_W * 4, HALO_H, 1, 2);
+static int make_halo_map(CUtensorMap* map, const float* base, int chunks, int D, int H, int W, int box_chunks) {
+    return make_vol4_tensor_map(map, base, chunks, D, H, W, HALO_W * 4, HALO_H, 1, box_chunks);
 }
 
-template <int NKS, int COUT>
+template <int KIND, int NKS, int COUT>
 static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas) {
     using C = Cfg<COUT>;
     const int tiles_h = (d->H + TILE_H - 1) / TILE_H, tiles_w = (d->W + TILE_W - 1) / TILE_W;
@@ -313,20 +377,23 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
     *n_ctas = grid;
     if (count_only) return ESTD_OK;
     ESTD_REQUIRE(d->weight_tc && aligned16(d->weight_tc), "estd_conv3d: precision=3xTF32 needs a 16-byte aligned weight_tc");
-    ESTD_REQUIRE(d->in1_chunks == 0 || (d->in0_chunks % 2) == 0, "estd_conv3d(3xTF32): first input segment must hold an even number of chunks");
+    using KT = KindTraits<KIND>;
+    ESTD_REQUIRE(d->in1_chunks == 0 || (d->in0_chunks % KT::CHUNKS) == 0,
+                 "estd_conv3d(tensor cores): first input segment must hold a multiple of %d chunks", KT::CHUNKS);
     CUtensorMap map0, map1;
-    int rc = make_halo_map(&map0, d->in0, d->in0_chunks, d->D, d->H, d->W);
+    int rc = make_halo_map(&map0, d->in0, d->in0_chunks, d->D, d->H, d->W, KT::CHUNKS);
     if (rc) return rc;
-    if (d->in1_chunks > 0) rc = make_halo_map(&map1, d->in1, d->in1_chunks, d->D, d->H, d->W);
+    if (d->in1_chunks > 0) rc = make_halo_map(&map1, d->in1, d->in1_chunks, d->D, d->H, d->W, KT::CHUNKS);
     else map1 = map0;
     if (rc) return rc;
     Params p;
     p.weight_tc = d->weight_tc;
+    p.status = d->status;
     fill_epilogue(&p.ep, d);
     p.in0_chunks = d->in0_chunks;
     p.D = d->D; p.H = d->H; p.W = d->W;
     p.tiles_h = tiles_h; p.tiles_w = tiles_w; p.n_units = n_units;
-    auto kern = conv3d_tc_kernel<NKS, COUT>;
+    auto kern = conv3d_tc_kernel<KIND, NKS, COUT>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -341,13 +408,23 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
 
 int dispatch_tc(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas) {
     const int cin_chunks = d->in0_chunks + d->in1_chunks;
-    const int nks = (cin_chunks + 1) / 2;
-    if (nks == 4 && d->cout_pad == 32) return tc::launch<4, 32>(d, stream, count_only, n_ctas);
-    if (nks == 5 && d->cout_pad == 48) return tc::launch<5, 48>(d, stream, count_only, n_ctas);
-    if (nks == 5 && d->cout_pad == 32) return tc::launch<5, 32>(d, stream, count_only, n_ctas);
-    if (nks == 2 && d->cout_pad == 16) return tc::launch<2, 16>(d, stream, count_only, n_ctas);
-    if (nks == 4 && d->cout_pad == 16) return tc::launch<4, 16>(d, stream, count_only, n_ctas);
-    return fail(ESTD_EUNSUPPORTED, "estd_conv3d(3xTF32): no kernel for %d input chunks -> cout_pad %d", cin_chunks, d->cout_pad);
+    if (d->precision == ESTD_PREC_3XTF32) {
+        const int nks = (cin_chunks + 1) / 2;                     // 8 channels per stage
+        if (nks == 4 && d->cout_pad == 32) return tc::launch<tc::KIND_TF32, 4, 32>(d, stream, count_only, n_ctas);
+        if (nks == 5 && d->cout_pad == 48) return tc::launch<tc::KIND_TF32, 5, 48>(d, stream, count_only, n_ctas);
+        if (nks == 5 && d->cout_pad == 32) return tc::launch<tc::KIND_TF32, 5, 32>(d, stream, count_only, n_ctas);
+        if (nks == 2 && d->cout_pad == 16) return tc::launch<tc::KIND_TF32, 2, 16>(d, stream, count_only, n_ctas);
+        if (nks == 4 && d->cout_pad == 16) return tc::launch<tc::KIND_TF32, 4, 16>(d, stream, count_only, n_ctas);
+    } else {
+        const int nks = (cin_chunks + 3) / 4;                     // 16 channels per stage
+        if (nks == 2 && d->cout_pad == 32) return tc::launch<tc::KIND_F16, 2, 32>(d, stream, count_only, n_ctas);
+        if (nks == 3 && d->cout_pad == 48) return tc::launch<tc::KIND_F16, 3, 48>(d, stream, count_only, n_ctas);
+        if (nks == 3 && d->cout_pad == 32) return tc::launch<tc::KIND_F16, 3, 32>(d, stream, count_only, n_ctas);
+        if (nks == 1 && d->cout_pad == 16) return tc::launch<tc::KIND_F16, 1, 16>(d, stream, count_only, n_ctas);
+        if (nks == 2 && d->cout_pad == 16) return tc::launch<tc::KIND_F16, 2, 16>(d, stream, count_only, n_ctas);
+    }
+    return fail(ESTD_EUNSUPPORTED, "estd_conv3d(tensor cores): no kernel for %d input chunks -> cout_pad %d (precision %d)",
+                cin_chunks, d->cout_pad, d->precision);
 }
 
 }  // namespace estd

@@ -88,8 +88,9 @@ class DepthNetHybrid(nn.Module):
         align_corners   grid_sample semantics of the warps: False = torch >= 1.3 (what the reference computes when run
                         today, and what the oracle pins); True = the torch 1.2 it was written for (quirk Q1).
         fix_stale_pose  opt-in fix of quirk Q4 (return the current target's pose with the hidden state).
-        precision       arithmetic of the 3-D convolutions: "3xtf32" = error-compensated TF32 on the tcgen05 tensor cores
-                        (fp32-class accuracy, the default), "fp32" = exact fp32 on the CUDA cores.
+        precision       arithmetic of the 3-D convolutions: "3xf16" / "3xtf32" = error-compensated two-term splits on the
+                        tcgen05 tensor cores (fp32-class accuracy; "3xf16" moves half the operand bytes and needs
+                        |activation| <= 65504, which is checked), "fp32" = exact fp32 on the CUDA cores.
         """
         super().__init__()
         self.ndepths = int(ndepths)
@@ -237,6 +238,8 @@ class DepthNetHybrid(nn.Module):
             raise NotImplementedError("estdepth_b200 implements the inference path (mode='val'); got mode=%r" % (mode,))
         if not imgs.is_cuda:
             raise RuntimeError("estdepth_b200.DepthNetHybrid runs on CUDA only (no CPU fallback); imgs is on %s" % imgs.device)
+        if self.precision == "3xf16":
+            ops.check_status(imgs.device)       # range flag of the previous call (its work has been consumed by now)
         with torch.no_grad():
             return self._forward_val(imgs, cam_poses, cam_intr, pre_costs, pre_cam_poses)
 

@@ -19,9 +19,9 @@ from . import _lib
 from ._lib import ConvDesc, check
 
 ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2}
-PRECISION = {"fp32": 0, "3xtf32": 1}
+PRECISION = {"fp32": 0, "3xtf32": 1, "3xf16": 2}
 MAX_SOURCES = 8
-# default arithmetic of conv3d: "fp32" = exact CUDA-core kernel, "3xtf32" = error-compensated TF32 on tcgen05
+# default arithmetic of conv3d: "fp32" = exact CUDA-core kernel, "3xtf32" / "3xf16" = error-compensated splits on tcgen05
 DEFAULT_PRECISION = "fp32"
 
 
@@ -139,12 +139,13 @@ def warp_cost(ref_mix, src_mix, homo12, depth_values, out=None, align_corners=Fa
 class PackedConv(object):
     """Folded, packed parameters of one 3x3x3 layer (see packing.pack_conv3d)."""
     __slots__ = ("weight", "scale", "shift", "cin_chunks", "cout_pad", "out_chunks", "act_split", "act_lo", "act_hi",
-                 "cin", "cout", "weight_tc", "cout_pad_tc")
+                 "cin", "cout", "weight_tc", "cout_pad_tc", "weight_f16", "scale_f16")
 
     def __init__(self, weight, scale, shift, cin_chunks, cout_pad, out_chunks, act_split, act_lo, act_hi,
                  cin=None, cout=None, weight_tc=None, cout_pad_tc=None):
         self.weight, self.scale, self.shift = weight, scale, shift
-        self.weight_tc, self.cout_pad_tc = weight_tc, cout_pad_tc      # tcgen05 packing (packing.pack_weight_tc)
+        self.weight_tc, self.cout_pad_tc = weight_tc, cout_pad_tc      # tcgen05 packings (packing.attach_tc)
+        self.weight_f16, self.scale_f16 = None, None
         self.cin = cin if cin is not None else 4 * cin_chunks          # real (un-padded) channel counts, for flop accounting
         self.cout = cout if cout is not None else min(cout_pad, 4 * out_chunks)
         self.cin_chunks, self.cout_pad, self.out_chunks = cin_chunks, cout_pad, out_chunks
@@ -153,9 +154,31 @@ class PackedConv(object):
 
 def _precision(pc, precision):
     precision = DEFAULT_PRECISION if precision is None else precision
-    if precision == "3xtf32" and pc.weight_tc is None:
+    if precision not in PRECISION:
+        raise RuntimeError("conv3d: unknown precision %r" % (precision,))
+    if (precision == "3xtf32" and pc.weight_tc is None) or (precision == "3xf16" and pc.weight_f16 is None):
         raise RuntimeError("conv3d: layer was packed without tensor-core weights (packing.attach_tc)")
     return precision
+
+
+_STATUS = {}
+
+
+def status_flag(device):
+    """Per-device int32 flag the fp16-split kernels raise when an activation leaves the fp16 range."""
+    key = str(device)
+    if key not in _STATUS:
+        _STATUS[key] = torch.zeros(1, device=device, dtype=torch.int32)
+    return _STATUS[key]
+
+
+def check_status(device):
+    """Raises if any 3xf16 convolution saw |x| > 65504 since the last check (one 4-byte D2H read)."""
+    flag = _STATUS.get(str(device))
+    if flag is not None and int(flag.item()) != 0:
+        flag.zero_()
+        raise RuntimeError("estdepth_b200: an activation exceeded the fp16 range in a 3xf16 convolution; "
+                           "results are invalid -- use precision='3xtf32' or 'fp32' for this model")
 
 
 def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision):
@@ -166,9 +189,12 @@ def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, pr
     d.in1, d.in1_chunks = (_ptr(in1), in1.shape[0]) if in1 is not None else (None, 0)
     if d.in0_chunks + d.in1_chunks != pc.cin_chunks:
         raise RuntimeError("conv3d: layer packed for %d input chunks, got %d" % (pc.cin_chunks, d.in0_chunks + d.in1_chunks))
-    d.weight, d.weight_tc = _ptr(pc.weight), _ptr(pc.weight_tc)
-    d.scale, d.shift = _ptr(pc.scale), _ptr(pc.shift)
-    d.cout_pad = pc.cout_pad_tc if precision == "3xtf32" else pc.cout_pad
+    tc = precision != "fp32"
+    d.weight = _ptr(pc.weight)
+    d.weight_tc = _ptr(pc.weight_f16 if precision == "3xf16" else pc.weight_tc)
+    d.scale, d.shift = _ptr(pc.scale_f16 if precision == "3xf16" else pc.scale), _ptr(pc.shift)
+    d.cout_pad = pc.cout_pad_tc if tc else pc.cout_pad
+    d.status = _ptr(status_flag(in0.device), torch.int32) if precision == "3xf16" else None
     d.act_split, d.act_lo, d.act_hi = pc.act_split, pc.act_lo, pc.act_hi
     d.res0, d.res1 = _ptr(res0), _ptr(res1)
     d.post_scale = float(post_scale)
@@ -186,7 +212,7 @@ def conv3d_num_ctas(pc, D, H, W, precision=None):
     d = ConvDesc()
     d.precision = PRECISION[precision]
     d.in0_chunks, d.in1_chunks = pc.cin_chunks, 0
-    d.cout_pad = pc.cout_pad_tc if precision == "3xtf32" else pc.cout_pad
+    d.cout_pad = pc.cout_pad_tc if precision != "fp32" else pc.cout_pad
     d.D, d.H, d.W = D, H, W
     n = _lib.get().estd_conv3d_num_ctas(ctypes.byref(d))
     if n < 0:
@@ -197,7 +223,8 @@ def conv3d_num_ctas(pc, D, H, W, precision=None):
 def conv3d(pc, in0, out0, in1=None, out1=None, res0=None, res1=None, post_scale=1.0, gn_partials=None, precision=None):
     """3x3x3 conv + folded affine + activation (+ residuals, x post_scale) over vol4 tensors; returns out0.
 
-    precision: "fp32" (exact, CUDA cores) | "3xtf32" (tcgen05 tensor cores, error-compensated) | None = DEFAULT_PRECISION."""
+    precision: "fp32" (exact, CUDA cores) | "3xtf32" | "3xf16" (tcgen05 tensor cores, error-compensated splits) |
+    None = DEFAULT_PRECISION."""
     precision = _precision(pc, precision)
     d = _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision)
     t = _pb()

@@ -83,14 +83,42 @@ def pack_weight_tc(packed, cout_pad_tc=None):
     return torch.cat([arrange(hi), arrange(lo)], dim=4).contiguous()
 
 
+def pack_weight_f16(packed, cout_pad_tc=None):
+    """SIMT packing -> fp16-split tcgen05 packing [3 dd][nks][9 taps][2 K-groups][2*C rows][8 x fp16], returned as a
+    float32-typed byte buffer ([...,4]) plus the power-of-two exponent k the weights were scaled by.
+
+    w * 2^k = w_hi + w_lo with both parts NORMAL fp16 numbers (k puts max|w| just below 1024, so w_lo ~ 2^-11 w_hi
+    stays far above the fp16 subnormal threshold for every weight that matters); the kernel's output must be
+    multiplied by 2^-k, which ``attach_tc`` folds into the per-channel scale.  K is zero padded to 16 channels.
+    """
+    taps, cin_pad, cout_pad = packed.shape
+    C = tc_cout_pad(cout_pad) if cout_pad_tc is None else cout_pad_tc
+    nks = (cin_pad + 15) // 16
+    w = torch.zeros(27, 16 * nks, C, dtype=torch.float32, device=packed.device)
+    w[:, :cin_pad, :cout_pad] = packed
+    wmax = float(w.abs().max())
+    k = 0 if wmax == 0.0 else max(-14, min(24, int(torch.floor(torch.log2(torch.tensor(1023.0 / wmax))))))
+    ws = w * (2.0 ** k)
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.to(torch.float32)).to(torch.float16)
+
+    def arrange(x):      # [27 = dd*9+tap9][16*nks = ks*16+kg*8+e][C] -> [dd][ks][tap9][kg][C][e]
+        return x.reshape(3, 9, nks, 2, 8, C).permute(0, 2, 1, 3, 5, 4)
+
+    both = torch.cat([arrange(hi), arrange(lo)], dim=4).contiguous()          # [3][nks][9][2][2C][8] fp16
+    return both.view(torch.float32), k
+
+
 def attach_tc(pc):
-    """Adds the tensor-core packing to a PackedConv and pads its affine arrays."""
+    """Adds the tensor-core packings (3xTF32 and fp16-split) to a PackedConv and pads its affine arrays."""
     pc.cout_pad_tc = tc_cout_pad(pc.cout_pad)
     pc.weight_tc = pack_weight_tc(pc.weight, pc.cout_pad_tc)
+    pc.weight_f16, k = pack_weight_f16(pc.weight, pc.cout_pad_tc)
     for name in ("scale", "shift"):
         v = getattr(pc, name)
         if v.numel() < AFFINE_PAD:
             setattr(pc, name, torch.cat([v, torch.zeros(AFFINE_PAD - v.numel(), dtype=v.dtype, device=v.device)]).contiguous())
+    pc.scale_f16 = (pc.scale * (2.0 ** -k)).contiguous()
     return pc
 
 

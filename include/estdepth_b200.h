@@ -46,6 +46,8 @@ extern "C" {
 
 #define ESTD_PREC_FP32   0          /* exact fp32 on the CUDA cores                                          */
 #define ESTD_PREC_3XTF32 1          /* error-compensated TF32 on the tcgen05 tensor cores (fp32-class accuracy) */
+#define ESTD_PREC_3XF16  2          /* error-compensated FP16 split on tcgen05: same accuracy class, half the operand bytes;
+                                       activations must stay within the fp16 range (|x| <= 65504, reported through `status`) */
 
 ESTD_API int estd_version(void);
 ESTD_API const char* estd_last_error(void);
@@ -92,8 +94,9 @@ typedef struct estd_conv3d_desc {
     const float* in0;  int in0_chunks;    /* vol4 input, first channel segment                          */
     const float* in1;  int in1_chunks;    /* optional second segment (torch.cat on channels), or NULL/0  */
     const float* weight;                  /* packed [27][cin_pad][cout_pad], cin_pad = 4*(in0+in1 chunks) (ESTD_PREC_FP32) */
-    const float* weight_tc;               /* packed [3][nks][9][2][2*cout_pad][4] hi|lo TF32 split (ESTD_PREC_3XTF32), else NULL */
-    int precision;                        /* ESTD_PREC_*; cout_pad is 16/32/40 for FP32 and 16/32/48 for 3XTF32 */
+    const float* weight_tc;               /* tensor-core packing [3][nks][9][2][2*cout_pad rows][16 bytes] (hi|lo split), else NULL */
+    int precision;                        /* ESTD_PREC_*; cout_pad is 16/32/40 for FP32 and 16/32/48 for the tensor-core paths */
+    int* status;                          /* optional device int, OR-ed with 1 on an fp16 range violation (ESTD_PREC_3XF16) */
     const float* scale;                   /* [cout_pad] per-channel multiplier (folded BN gamma/sqrt(var+eps)) */
     const float* shift;                   /* [cout_pad] per-channel offset (folded BN beta - mean*scale, or conv bias) */
     int cout_pad;                         /* padded number of output channels (see precision) */

@@ -36,14 +36,16 @@ def _run_joint(model, height, width, starts=(0, 3)):
     return results
 
 
+@pytest.mark.parametrize("precision", ["3xf16", "3xtf32", "fp32"])
 @pytest.mark.parametrize("resnet,ndepths,height,width,name", [
     (18, 32, 128, 160, "joint_r18_d32_128x160.npz"),
     (50, 64, 128, 128, "joint_r50_d64_128x128.npz"),
 ])
-def test_joint_windows_match_reference_golden(resnet, ndepths, height, width, name):
+def test_joint_windows_match_reference_golden(resnet, ndepths, height, width, name, precision):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     model, _ = synth_model_and_state(resnet, ndepths)
+    model.precision = precision
     model.cuda()
     gold = np.load(os.path.join(GOLDEN, name))
     results = _run_joint(model, height, width)
@@ -63,7 +65,7 @@ def test_joint_windows_match_reference_golden(resnet, ndepths, height, width, na
         assert np.abs(sv - gold["w%d/state_value" % w]).max() < STATE_TOL
         # quirk Q4: the pose returned with window 2's state is window 1's (stale) pose
         assert np.abs(pstate[0].cpu().numpy() - gold["w%d/state_pose" % w]).max() == 0.0
-    print("max |diff| vs reference golden:", worst)
+    print("max |diff| vs reference golden (%s, R%d):" % (precision, resnet), {k: "%.1e" % v for k, v in worst.items()})
 
 
 def test_estm_protocol_matches_reference_golden():
@@ -135,6 +137,23 @@ def test_argmax_bit_exact_where_unambiguous_and_oracle_agreement():
     safe = (top2[:, 0] - top2[:, 1]) > 1e-3
     print("argmax check: excluded fraction %.5f" % (1.0 - safe.float().mean().item()))
     assert safe.float().mean().item() > 0.98
+
+
+def test_fp16_range_violation_is_reported():
+    """3xf16 convs flag activations beyond the fp16 range instead of silently saturating."""
+    from estdepth_b200 import ops, packing
+    w = torch.randn(32, 32, 3, 3, 3) / 30
+    pc = packing.attach_tc(ops.PackedConv(packing.pack_weight(w, list(range(32)), list(range(32))).cuda(),
+                                          torch.ones(32).cuda(), torch.zeros(32).cuda(), 8, 32, 8, 32, "none", "none"))
+    x = torch.randn(8, 4, 16, 32, 4).cuda()
+    y = torch.empty_like(x)
+    ops.conv3d(pc, x, y, precision="3xf16")
+    ops.check_status(x.device)                       # in range: no error
+    x[3, 2, 5, 7, 1] = 1.0e5
+    ops.conv3d(pc, x, y, precision="3xf16")
+    with pytest.raises(RuntimeError, match="fp16 range"):
+        ops.check_status(x.device)
+    ops.check_status(x.device)                       # flag was cleared
 
 
 def test_cpu_tensors_are_rejected_loudly():

@@ -127,7 +127,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 @pytest.mark.parametrize("shape", [(5, 21, 40), (8, 32, 64)], ids=["ragged", "aligned"])
 def test_conv3d_vs_torch_cpu(case, shape, precision):
@@ -185,7 +185,7 @@ def test_conv3d_vs_torch_cpu(case, shape, precision):
         assert abs(tot[1, 1].item() - (g1 ** 2).sum().item()) < 1e-4 * (g1 ** 2).sum().item()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16"])
 def test_conv3d_is_bitwise_deterministic(precision):
     g = torch.Generator().manual_seed(5)
     D, H, W = 6, 24, 64
