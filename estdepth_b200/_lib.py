@@ -19,6 +19,7 @@ class ConvDesc(ctypes.Structure):
         ("in0", c_void_p), ("in0_chunks", ctypes.c_int),
         ("in1", c_void_p), ("in1_chunks", ctypes.c_int),
         ("weight", c_void_p), ("weight_tc", c_void_p), ("precision", ctypes.c_int), ("status", c_void_p),
+        ("planar", ctypes.c_int), ("dilation", ctypes.c_int),
         ("scale", c_void_p), ("shift", c_void_p),
         ("cout_pad", ctypes.c_int), ("act_split", ctypes.c_int), ("act_lo", ctypes.c_int), ("act_hi", ctypes.c_int),
         ("res0", c_void_p), ("res1", c_void_p),
@@ -51,6 +52,8 @@ SIGNATURES = {
     "estd_vol4_to_ncdhw": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "estd_ncdhw_to_vol4": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "estd_scalar_to_vol4": (_I, [_P, _P, _I, _I, _I, _P]),
+    "estd_nchw_to_vol4": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "estd_vol4_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -27,11 +27,6 @@ namespace estd {
 
 namespace tc {
 
-constexpr int TILE_H = 16, TILE_W = 32, HALO_H = TILE_H + 2, HALO_W = TILE_W + 2;
-constexpr int HALO_VOX = HALO_H * HALO_W;                     // 612 voxels in the halo tile
-constexpr int A_CHUNK_BYTES = HALO_VOX * 16;                  // one 16-byte K-group of the halo tile        (9792)
-constexpr int A_BYTES = 4 * A_CHUNK_BYTES;                    // operand area of one stage: 4 K-groups       (39168)
-constexpr int STAGES = 3;
 constexpr int SPLIT_WARPS = 8, SPLIT_THREADS = SPLIT_WARPS * 32;
 constexpr int THREADS = 256 + SPLIT_THREADS;          // warps 0-3 control, 4-7 epilogue, 8.. splitters
 constexpr uint32_t TF32_MASK = 0xFFFFE000u;
@@ -46,31 +41,39 @@ constexpr uint32_t TF32_MASK = 0xFFFFE000u;
 //              raise the status flag.  x_hi*w_hi, x_hi*w_lo, x_lo*w_hi are exact in the fp32 accumulator either way.
 constexpr int KIND_TF32 = 0, KIND_F16 = 1;
 
-template <int KIND> struct KindTraits;
-template <> struct KindTraits<KIND_TF32> {
-    static constexpr int CHUNKS = 2;                                  // fp32 chunks landed per stage
-    static constexpr uint32_t A_LO_OFFSET = 2 * A_CHUNK_BYTES;        // x_lo K-groups start here
-    static constexpr uint32_t A_LBO = A_CHUNK_BYTES;                  // distance between the two K-groups of one MMA
-    static constexpr uint32_t FORMAT = 2;                             // UMMA a/b format: TF32
-};
-template <> struct KindTraits<KIND_F16> {
-    static constexpr int CHUNKS = 4;
-    static constexpr uint32_t A_LO_OFFSET = A_CHUNK_BYTES;            // pair p: [hi K-group | lo K-group]
-    static constexpr uint32_t A_LBO = 2 * A_CHUNK_BYTES;
-    static constexpr uint32_t FORMAT = 0;                             // F16
-};
-
-template <int COUT>
-struct Cfg {
-    static constexpr int N_ALL = 2 * COUT;                                 // [W_hi | W_lo]
+// Compile-time shape of one specialisation.
+//   NKS     k-steps per input plane (8 channels each for TF32, 16 for F16)
+//   COUT    padded output channels (multiple of 16); N of the MMAs is 2*COUT ([W_hi | W_lo]) and COUT
+//   MT      M tiles (16 rows x 8 columns = 128 voxels each) per work unit: unit = 16 x 8*MT voxels of one plane
+//   DIL     dilation of the in-plane taps (1 or 2)
+//   PLANAR  true: 1x3x3 filter applied to every plane independently (2-D convolution over a stack of feature maps);
+//           false: full 3x3x3 filter (3 input planes per output plane)
+template <int KIND_, int NKS_, int COUT_, int MT_, int DIL_, bool PLANAR_>
+struct Shape {
+    static constexpr int KIND = KIND_, NKS = NKS_, COUT = COUT_, MT = MT_, DIL = DIL_;
+    static constexpr bool PLANAR = PLANAR_;
+    static constexpr int TILE_H = 16, TILE_W = 8 * MT;
+    static constexpr int HALO_H = TILE_H + 2 * DIL, HALO_W = TILE_W + 2 * DIL, HALO_VOX = HALO_H * HALO_W;
+    static constexpr int KGROUP_BYTES = HALO_VOX * 16;                     // one 16-byte K-group of the halo tile
+    static constexpr int A_BYTES = 4 * KGROUP_BYTES;                       // operand area of a stage (x_hi and x_lo)
+    static constexpr int CHUNKS = (KIND == KIND_TF32) ? 2 : 4;             // fp32 chunks landed per stage
+    static constexpr uint32_t A_LO_OFFSET = (KIND == KIND_TF32) ? 2 * KGROUP_BYTES : KGROUP_BYTES;
+    static constexpr uint32_t A_LBO = (KIND == KIND_TF32) ? KGROUP_BYTES : 2 * KGROUP_BYTES;
+    static constexpr uint32_t FORMAT = (KIND == KIND_TF32) ? 2 : 0;        // UMMA a/b format: TF32 / F16
+    static constexpr int N_ALL = 2 * COUT;
     static constexpr int W_TAP_BYTES = 2 * N_ALL * 16;                     // [2 K-groups][N_ALL rows][16 B]
     static constexpr int W_BYTES = 9 * W_TAP_BYTES;
-    static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;                  // operand area (x_hi, x_lo), W
-    static constexpr int COLS_PER_UNIT = 4 * N_ALL;                        // 4 M tiles
+    static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES + 127) / 128 * 128;
+    static constexpr int STAGES = (3 * STAGE_BYTES <= 224 * 1024) ? 3 : 2;
+    static constexpr int COLS_PER_UNIT = MT * N_ALL;
     static constexpr int NBUF = (2 * COLS_PER_UNIT <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (NBUF * COLS_PER_UNIT <= 32) ? 32 : (NBUF * COLS_PER_UNIT <= 64) ? 64
                                    : (NBUF * COLS_PER_UNIT <= 128) ? 128 : (NBUF * COLS_PER_UNIT <= 256) ? 256 : 512;
+    static constexpr int PLANES = PLANAR ? 1 : 3;
+    static constexpr int N_STAGES_PER_UNIT = PLANES * NKS;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;     // + barriers / tmem base
+    static_assert(COLS_PER_UNIT <= 512, "accumulators of one unit must fit TMEM");
+    static_assert(2 * STAGE_BYTES + 256 <= 227 * 1024, "two stages must fit shared memory");
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -147,7 +150,7 @@ __device__ __forceinline__ uint32_t make_idesc(uint32_t fmt, int n) {
 }
 
 struct Params {
-    const float* weight_tc;                     // [3 dd][NKS][9 taps][2 K-groups][2*COUT rows][16 bytes]
+    const float* weight_tc;                     // [PLANES][NKS][9 taps][2 K-groups][2*COUT rows][16 bytes]
     int* status;                                // optional: set to 1 when an activation leaves the fp16 range (KIND_F16)
     ConvEpilogue ep;
     int in0_chunks;
@@ -155,12 +158,14 @@ struct Params {
     int tiles_h, tiles_w, n_units;
 };
 
-template <int KIND, int NKS, int COUT>
+template <class S>
 __global__ void __launch_bounds__(THREADS, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Params p) {
-    using C = Cfg<COUT>;
-    using KT = KindTraits<KIND>;
-    constexpr int N_STAGES_PER_UNIT = 3 * NKS;
+    using C = S;
+    using KT = S;
+    constexpr int KIND = S::KIND, NKS = S::NKS, COUT = S::COUT, STAGES = S::STAGES;
+    constexpr int N_STAGES_PER_UNIT = S::N_STAGES_PER_UNIT;
+    constexpr int HALO_W = S::HALO_W, HALO_VOX = S::HALO_VOX, A_BYTES = S::A_BYTES;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * C::STAGE_BYTES);
     uint64_t* full = bars;                  // [STAGES] TMA landed
@@ -190,7 +195,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         const int tw = u % p.tiles_w;
         const int th = (u / p.tiles_w) % p.tiles_h;
         d = u / (p.tiles_w * p.tiles_h);
-        h0 = th * TILE_H; w0 = tw * TILE_W;
+        h0 = th * S::TILE_H; w0 = tw * S::TILE_W;
     };
 
     if (warp == 0) {
@@ -205,10 +210,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                     if (it >= STAGES) mbar_wait(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
                     const int dd = st / NKS, ks = st % NKS;
                     unsigned char* stage = smem + (size_t)s * C::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)(KT::CHUNKS * A_CHUNK_BYTES + C::W_BYTES));
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(KT::CHUNKS * S::KGROUP_BYTES + C::W_BYTES));
                     const int chunk = KT::CHUNKS * ks;
-                    if (chunk < p.in0_chunks) tma_load_4d(stage, &map0, &full[s], 4 * (w0 - 1), h0 - 1, d + dd - 1, chunk);
-                    else                      tma_load_4d(stage, &map1, &full[s], 4 * (w0 - 1), h0 - 1, d + dd - 1, chunk - p.in0_chunks);
+                    const int z = S::PLANAR ? d : d + dd - 1;
+                    if (chunk < p.in0_chunks) tma_load_4d(stage, &map0, &full[s], 4 * (w0 - S::DIL), h0 - S::DIL, z, chunk);
+                    else                      tma_load_4d(stage, &map1, &full[s], 4 * (w0 - S::DIL), h0 - S::DIL, z, chunk - p.in0_chunks);
                     bulk_load(stage + A_BYTES, p.weight_tc + (size_t)(dd * NKS + ks) * (C::W_BYTES / 4), (uint32_t)C::W_BYTES, &full[s]);
                 }
             }
@@ -241,9 +247,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-                        for (int mt = 0; mt < 4; ++mt) {
+                        for (int mt = 0; mt < S::MT; ++mt) {
                             // start-address field is in 16-byte units: one voxel (float4) per unit
-                            const uint64_t a_off = (uint64_t)((tap / 3) * HALO_W + 8 * mt + (tap % 3));
+                            const uint64_t a_off = (uint64_t)((tap / 3) * S::DIL * HALO_W + 8 * mt + (tap % 3) * S::DIL);
                             const uint64_t b_off = (uint64_t)(tap * (C::W_TAP_BYTES >> 4));
                             const uint32_t acc = acc0 + (uint32_t)(mt * C::N_ALL);
                             umma<KIND>(acc, a_hi_desc + a_off, b_desc + b_off, idesc_all, tap == 0 ? first : 1u);
@@ -283,7 +289,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                     float amax = 0.0f;
                     for (int i = t; i < 2 * HALO_VOX; i += SPLIT_THREADS) {
                         const int pair = i / HALO_VOX, v = i - pair * HALO_VOX;
-                        float4* c0 = reinterpret_cast<float4*>(area + (size_t)pair * 2 * A_CHUNK_BYTES) + v;     // channels 8p..8p+3
+                        float4* c0 = reinterpret_cast<float4*>(area + (size_t)pair * 2 * S::KGROUP_BYTES) + v;   // channels 8p..8p+3
                         float4* c1 = c0 + HALO_VOX;                                                                // channels 8p+4..8p+7
                         const float4 a = *c0, b = *c1;
                         amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
@@ -323,7 +329,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             const uint32_t acc0 = tmem_base + (uint32_t)(buf * C::COLS_PER_UNIT) + ((uint32_t)(q * 32) << 16);
             const int h = h0 + mh;
 #pragma unroll 1
-            for (int mt = 0; mt < 4; ++mt) {
+            for (int mt = 0; mt < S::MT; ++mt) {
                 const int w = w0 + 8 * mt + mw;
                 const bool ok = (h < p.H) && (w < p.W);
                 const size_t pos = ((size_t)d * p.H + h) * p.W + w;
@@ -364,26 +370,20 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-static int make_halo_map(CUtensorMap* map, const float* base, int chunks, int D, int H, int W, int box_chunks) {
-    return make_vol4_tensor_map(map, base, chunks, D, H, W, HALO_W * 4, HALO_H, 1, box_chunks);
-}
-
-template <int KIND, int NKS, int COUT>
+template <class S>
 static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas) {
-    using C = Cfg<COUT>;
-    const int tiles_h = (d->H + TILE_H - 1) / TILE_H, tiles_w = (d->W + TILE_W - 1) / TILE_W;
+    const int tiles_h = (d->H + S::TILE_H - 1) / S::TILE_H, tiles_w = (d->W + S::TILE_W - 1) / S::TILE_W;
     const int n_units = d->D * tiles_h * tiles_w;
     const int grid = n_units < sm_count() ? n_units : sm_count();
     *n_ctas = grid;
     if (count_only) return ESTD_OK;
-    ESTD_REQUIRE(d->weight_tc && aligned16(d->weight_tc), "estd_conv3d: precision=3xTF32 needs a 16-byte aligned weight_tc");
-    using KT = KindTraits<KIND>;
-    ESTD_REQUIRE(d->in1_chunks == 0 || (d->in0_chunks % KT::CHUNKS) == 0,
-                 "estd_conv3d(tensor cores): first input segment must hold a multiple of %d chunks", KT::CHUNKS);
+    ESTD_REQUIRE(d->weight_tc && aligned16(d->weight_tc), "estd_conv3d: tensor-core precision needs a 16-byte aligned weight_tc");
+    ESTD_REQUIRE(d->in1_chunks == 0 || (d->in0_chunks % S::CHUNKS) == 0,
+                 "estd_conv3d(tensor cores): first input segment must hold a multiple of %d chunks", S::CHUNKS);
     CUtensorMap map0, map1;
-    int rc = make_halo_map(&map0, d->in0, d->in0_chunks, d->D, d->H, d->W, KT::CHUNKS);
+    int rc = make_vol4_tensor_map(&map0, d->in0, d->in0_chunks, d->D, d->H, d->W, S::HALO_W * 4, S::HALO_H, 1, S::CHUNKS);
     if (rc) return rc;
-    if (d->in1_chunks > 0) rc = make_halo_map(&map1, d->in1, d->in1_chunks, d->D, d->H, d->W, KT::CHUNKS);
+    if (d->in1_chunks > 0) rc = make_vol4_tensor_map(&map1, d->in1, d->in1_chunks, d->D, d->H, d->W, S::HALO_W * 4, S::HALO_H, 1, S::CHUNKS);
     else map1 = map0;
     if (rc) return rc;
     Params p;
@@ -393,35 +393,47 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
     p.in0_chunks = d->in0_chunks;
     p.D = d->D; p.H = d->H; p.W = d->W;
     p.tiles_h = tiles_h; p.tiles_w = tiles_w; p.n_units = n_units;
-    auto kern = conv3d_tc_kernel<KIND, NKS, COUT>;
+    auto kern = conv3d_tc_kernel<S>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) return fail(ESTD_ECUDA, "estd_conv3d(3xTF32): cannot reserve %zu B of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM);
+        if (e != cudaSuccess) return fail(ESTD_ECUDA, "estd_conv3d(tensor cores): cannot reserve %zu B of shared memory: %s", S::SMEM, cudaGetErrorString(e));
         attr_set = true;
     }
-    kern<<<grid, THREADS, C::SMEM, stream>>>(map0, map1, p);
-    return check_launch("estd_conv3d(3xTF32)");
+    kern<<<grid, THREADS, S::SMEM, stream>>>(map0, map1, p);
+    return check_launch("estd_conv3d(tensor cores)");
 }
 
 }  // namespace tc
 
 int dispatch_tc(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas) {
+    using namespace tc;
     const int cin_chunks = d->in0_chunks + d->in1_chunks;
+    const int C = d->cout_pad;
+    const int dil = d->dilation > 0 ? d->dilation : 1;
+    if (d->planar) {
+        // 2-D (1x3x3 per plane) convolutions of the matching-feature net: fp16 split only, 16x16-voxel units
+        ESTD_REQUIRE(d->precision == ESTD_PREC_3XF16, "estd_conv3d: planar convolutions are implemented for ESTD_PREC_3XF16 only");
+        const int nks = (cin_chunks + 3) / 4;
+#define ESTD_PLANAR(NKS, COUT, DIL) if (nks == NKS && C == COUT && dil == DIL) \
+            return launch<Shape<KIND_F16, NKS, COUT, 2, DIL, true>>(d, stream, count_only, n_ctas)
+        ESTD_PLANAR(2, 32, 1); ESTD_PLANAR(2, 64, 1); ESTD_PLANAR(4, 64, 1); ESTD_PLANAR(8, 64, 1); ESTD_PLANAR(8, 64, 2);
+        ESTD_PLANAR(20, 64, 1);
+#undef ESTD_PLANAR
+        return fail(ESTD_EUNSUPPORTED, "estd_conv3d(planar): no kernel for %d input chunks -> cout_pad %d, dilation %d",
+                    cin_chunks, C, dil);
+    }
+    ESTD_REQUIRE(dil == 1, "estd_conv3d: dilation is supported for planar convolutions only");
     if (d->precision == ESTD_PREC_3XTF32) {
         const int nks = (cin_chunks + 1) / 2;                     // 8 channels per stage
-        if (nks == 4 && d->cout_pad == 32) return tc::launch<tc::KIND_TF32, 4, 32>(d, stream, count_only, n_ctas);
-        if (nks == 5 && d->cout_pad == 48) return tc::launch<tc::KIND_TF32, 5, 48>(d, stream, count_only, n_ctas);
-        if (nks == 5 && d->cout_pad == 32) return tc::launch<tc::KIND_TF32, 5, 32>(d, stream, count_only, n_ctas);
-        if (nks == 2 && d->cout_pad == 16) return tc::launch<tc::KIND_TF32, 2, 16>(d, stream, count_only, n_ctas);
-        if (nks == 4 && d->cout_pad == 16) return tc::launch<tc::KIND_TF32, 4, 16>(d, stream, count_only, n_ctas);
+#define ESTD_TF32(NKS, COUT) if (nks == NKS && C == COUT) return launch<Shape<KIND_TF32, NKS, COUT, 4, 1, false>>(d, stream, count_only, n_ctas)
+        ESTD_TF32(4, 32); ESTD_TF32(5, 48); ESTD_TF32(5, 32); ESTD_TF32(2, 16); ESTD_TF32(4, 16);
+#undef ESTD_TF32
     } else {
         const int nks = (cin_chunks + 3) / 4;                     // 16 channels per stage
-        if (nks == 2 && d->cout_pad == 32) return tc::launch<tc::KIND_F16, 2, 32>(d, stream, count_only, n_ctas);
-        if (nks == 3 && d->cout_pad == 48) return tc::launch<tc::KIND_F16, 3, 48>(d, stream, count_only, n_ctas);
-        if (nks == 3 && d->cout_pad == 32) return tc::launch<tc::KIND_F16, 3, 32>(d, stream, count_only, n_ctas);
-        if (nks == 1 && d->cout_pad == 16) return tc::launch<tc::KIND_F16, 1, 16>(d, stream, count_only, n_ctas);
-        if (nks == 2 && d->cout_pad == 16) return tc::launch<tc::KIND_F16, 2, 16>(d, stream, count_only, n_ctas);
+#define ESTD_F16(NKS, COUT) if (nks == NKS && C == COUT) return launch<Shape<KIND_F16, NKS, COUT, 4, 1, false>>(d, stream, count_only, n_ctas)
+        ESTD_F16(2, 32); ESTD_F16(3, 48); ESTD_F16(3, 32); ESTD_F16(1, 16); ESTD_F16(2, 16);
+#undef ESTD_F16
     }
     return fail(ESTD_EUNSUPPORTED, "estd_conv3d(tensor cores): no kernel for %d input chunks -> cout_pad %d (precision %d)",
                 cin_chunks, d->cout_pad, d->precision);

@@ -95,6 +95,30 @@ __global__ void __launch_bounds__(256) ncdhw_to_vol4_kernel(const float* __restr
     }
 }
 
+// [N][C][H][W] (torch NCHW) <-> vol4 [C/4][N][H][W][4]: the stack of N feature maps seen as a volume with D = N planes
+__global__ void __launch_bounds__(256) nchw_to_vol4_kernel(const float* __restrict__ nchw, float* __restrict__ vol4,
+                                                           int C, int N, size_t HW, size_t total) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = i % HW;
+        const size_t n = (i / HW) % N;
+        const size_t j = i / (HW * N);
+        const float* s = nchw + (n * C + j * 4) * HW + p;
+        st4(vol4 + i * 4, make_float4(__ldg(s), __ldg(s + HW), __ldg(s + 2 * HW), __ldg(s + 3 * HW)));
+    }
+}
+
+__global__ void __launch_bounds__(256) vol4_to_nchw_kernel(const float* __restrict__ vol4, float* __restrict__ nchw,
+                                                           int C, int N, size_t HW, size_t total) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = i % HW;
+        const size_t n = (i / HW) % N;
+        const size_t j = i / (HW * N);
+        const float4 x = ldg4(vol4 + i * 4);
+        float* o = nchw + (n * C + j * 4) * HW + p;
+        o[0] = x.x; o[HW] = x.y; o[2 * HW] = x.z; o[3 * HW] = x.w;
+    }
+}
+
 __global__ void __launch_bounds__(256) scalar_to_vol4_kernel(const float* __restrict__ in, float* __restrict__ out, size_t vox) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vox; i += (size_t)gridDim.x * blockDim.x)
         st4(out + i * 4, make_float4(__ldg(in + i), 0.0f, 0.0f, 0.0f));
@@ -133,6 +157,20 @@ extern "C" int estd_ncdhw_to_vol4(const float* ncdhw, float* vol4, int C, int D,
     const size_t vox = (size_t)D * H * W, total = vox * (C / 4);
     estd::ncdhw_to_vol4_kernel<<<estd::ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(ncdhw, vol4, vox, total);
     return estd::check_launch("estd_ncdhw_to_vol4");
+}
+
+extern "C" int estd_nchw_to_vol4(const float* nchw, float* vol4, int N, int C, int H, int W, void* stream) {
+    ESTD_REQUIRE(vol4 && nchw && C > 0 && (C % 4) == 0 && N > 0 && H > 0 && W > 0, "estd_nchw_to_vol4: bad arguments");
+    const size_t HW = (size_t)H * W, total = HW * N * (C / 4);
+    estd::nchw_to_vol4_kernel<<<estd::ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(nchw, vol4, C, N, HW, total);
+    return estd::check_launch("estd_nchw_to_vol4");
+}
+
+extern "C" int estd_vol4_to_nchw(const float* vol4, float* nchw, int N, int C, int H, int W, void* stream) {
+    ESTD_REQUIRE(vol4 && nchw && C > 0 && (C % 4) == 0 && N > 0 && H > 0 && W > 0, "estd_vol4_to_nchw: bad arguments");
+    const size_t HW = (size_t)H * W, total = HW * N * (C / 4);
+    estd::vol4_to_nchw_kernel<<<estd::ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(vol4, nchw, C, N, HW, total);
+    return estd::check_launch("estd_vol4_to_nchw");
 }
 
 extern "C" int estd_scalar_to_vol4(const float* dhw, float* vol4_1chunk, int D, int H, int W, void* stream) {

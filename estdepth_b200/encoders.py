@@ -76,7 +76,85 @@ class MatchingFeatureNet(nn.Module):
                                       nn.Conv2d(128, 32, 1, bias=False))
         self.out_channels = [32]
 
+    # ------------------------------------------------------------------ tensor-core path (3x3 convs of layers 2-4, fuse conv)
+    def _bn_affine(self, bn):
+        scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        shift = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+        return scale.float(), shift.float()
+
+    def _packed(self, device):
+        from . import packing
+        probe = self.layer2[1].conv1[0][0].weight
+        key = (str(device), probe.data_ptr(), probe._version, self.layer4[2].conv2[0].weight._version,
+               self.lastconv[0][0].weight._version)
+        if getattr(self, "_tc_key", None) != key:
+            def pack(seq, act):          # seq = Sequential(conv, bn)
+                s, b = self._bn_affine(seq[1])
+                return packing.pack_conv2d(seq[0].weight.detach(), s, b, act, device)
+            P = {}
+            for name in ("layer2", "layer3", "layer4"):
+                for i, blk in enumerate(getattr(self, name)):
+                    if blk.conv1[0][0].stride == (1, 1):
+                        P[(name, i, 1)] = pack(blk.conv1[0], "relu")
+                    P[(name, i, 2)] = pack(blk.conv2, "none")
+            P["fuse"] = pack(self.lastconv[0], "relu")
+            self._tc_packed, self._tc_key = P, key
+        return self._tc_packed
+
+    @staticmethod
+    def _conv_tc(pcs, x4, out4, res4=None, dilation=1):
+        """Runs a (possibly output-sliced) packed 3x3 layer: slice i writes chunks [16i, 16i+16) of out4."""
+        from . import ops
+        for i, pc in enumerate(pcs):
+            lo, hi = 16 * i, 16 * i + pc.out_chunks
+            ops.conv_planar(pc, x4, out4[lo:hi], res0=None if res4 is None else res4[lo:hi], dilation=dilation)
+        return out4
+
+    def forward_tc(self, x):
+        """Same arithmetic as ``forward`` with the stride-1 3x3 convolutions of layer2/3/4 and the 320->128 fuse conv
+        (538 + 70 of the net's 679 GFLOP at 480x640) on the tcgen05 tensor cores (fp16 two-term split, fp32-class
+        accuracy) with BN / ReLU / residual add fused into their epilogues; activations stay in vol4 between them."""
+        from . import ops
+        P = self._packed(x.device)
+        x = self.layer1(self.firstconv(x))
+        N = x.shape[0]
+        blk = self.layer2[0]
+        y = blk.conv1(x)                                            # stride-2 conv: cuDNN
+        H, W = y.shape[-2:]
+        dev = x.device
+
+        def vol(chunks):
+            return torch.empty(chunks, N, H, W, 4, device=dev, dtype=torch.float32)
+
+        cat = vol(80)                                               # [raw 64 | skip 128 | branch4..1 32 each]
+        cur = self._conv_tc(P[("layer2", 0, 2)], ops.nchw_to_vol4(y), vol(16), ops.nchw_to_vol4(blk.downsample(x)))
+        tmp = vol(16)
+        n2 = len(self.layer2)
+        for i in range(1, n2):
+            self._conv_tc(P[("layer2", i, 1)], cur, tmp)
+            nxt = cat[0:16] if i == n2 - 1 else vol(16)
+            cur = self._conv_tc(P[("layer2", i, 2)], tmp, nxt, cur)
+        raw = cur
+        # layer3: block 0 changes the width (64 -> 128) and projects the shortcut with a 1x1 conv (cuDNN)
+        blk = self.layer3[0]
+        shortcut = ops.nchw_to_vol4(blk.downsample(ops.vol4_to_nchw(raw)))
+        tmp = self._conv_tc(P[("layer3", 0, 1)], raw, vol(32))
+        cur = self._conv_tc(P[("layer3", 0, 2)], tmp, vol(32), shortcut)
+        stages = [("layer3", i, 1) for i in range(1, len(self.layer3))] + [("layer4", i, 2) for i in range(len(self.layer4))]
+        for k, (name, i, dil) in enumerate(stages):
+            self._conv_tc(P[(name, i, 1)], cur, tmp, dilation=dil)
+            nxt = cat[16:48] if k == len(stages) - 1 else vol(32)
+            cur = self._conv_tc(P[(name, i, 2)], tmp, nxt, cur, dilation=dil)
+        deep = ops.vol4_to_nchw(cur)                                # SPP pooling / 1x1 / bilinear resize: torch
+        for slot, idx in enumerate((4, 3, 2, 1)):
+            b = F.interpolate(getattr(self, "branch%d" % idx)(deep), size=(H, W), mode="bilinear", align_corners=False)
+            ops.nchw_to_vol4(b.contiguous(), cat[48 + 8 * slot:56 + 8 * slot])
+        fused = self._conv_tc(P["fuse"], cat, vol(32))
+        return self.lastconv[2](ops.vol4_to_nchw(fused))
+
     def forward(self, x):
+        if x.is_cuda and getattr(self, "tensor_cores", False):
+            return self.forward_tc(x)
         x = self.layer1(self.firstconv(x))
         quarter = self.layer2(x)
         deep = self.layer4(self.layer3(quarter))

@@ -82,7 +82,7 @@ class _Workspace(object):
 
 class DepthNetHybrid(nn.Module):
     def __init__(self, ndepths=64, depth_min=0.01, depth_max=10.0, resnet=50, IF_EST_transformer=True,
-                 align_corners=False, fix_stale_pose=False, precision="3xtf32"):
+                 align_corners=False, fix_stale_pose=False, precision="3xf16", feature_precision="3xf16"):
         """First five arguments: hybrid_models/model_hybrid.py:15-16.  Extra, keyword-only in practice:
 
         align_corners   grid_sample semantics of the warps: False = torch >= 1.3 (what the reference computes when run
@@ -103,11 +103,17 @@ class DepthNetHybrid(nn.Module):
         self.IF_EST_transformer = bool(IF_EST_transformer)
         self.align_corners = bool(align_corners)
         self.fix_stale_pose = bool(fix_stale_pose)
+        # feature_precision: "3xf16" = the 3x3 convolutions of the matching-feature net on the tensor cores (fp32-class
+        # accuracy), "fp32" = the whole 2-D net on cuDNN's strict-fp32 kernels
+        if feature_precision not in ("3xf16", "fp32"):
+            raise ValueError("feature_precision must be '3xf16' or 'fp32'")
+        self.feature_precision = feature_precision
         if precision not in ops.PRECISION:
             raise ValueError("precision must be one of %s" % sorted(ops.PRECISION))
         self.precision = precision
 
         self.matchingFeature = MatchingFeatureNet()
+        self.matchingFeature.tensor_cores = (feature_precision == "3xf16")
         self.semanticFeature = ContextEncoder(resnet)
         self.CostRegNet = HybridDecoder(self.semanticFeature.num_ch_enc, self.ndepths, self.depth_max,
                                         self.IF_EST_transformer)

@@ -181,10 +181,11 @@ def check_status(device):
                            "results are invalid -- use precision='3xtf32' or 'fp32' for this model")
 
 
-def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision):
+def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision, planar=0, dilation=1):
     chunks0, D, H, W, _ = in0.shape
     d = ConvDesc()
     d.precision = PRECISION[precision]
+    d.planar, d.dilation = int(planar), int(dilation)
     d.in0, d.in0_chunks = _ptr(in0), chunks0
     d.in1, d.in1_chunks = (_ptr(in1), in1.shape[0]) if in1 is not None else (None, 0)
     if d.in0_chunks + d.in1_chunks != pc.cin_chunks:
@@ -232,6 +233,36 @@ def conv3d(pc, in0, out0, in1=None, out1=None, res0=None, res1=None, post_scale=
     vox = float(d.D) * d.H * d.W
     _pe(t, "conv3d_" + precision, 54.0 * pc.cin * pc.cout * vox, 4.0 * vox * (pc.cin + pc.cout))
     return out0
+
+
+def conv_planar(pc, in0, out0, res0=None, dilation=1, in1=None):
+    """2-D 3x3 convolution (stride 1, padding = dilation) over a stack of N maps held as vol4 [C/4,N,H,W,4], with folded
+    affine + activation (+ residual), on the tensor cores (fp16 two-term split).  Returns out0."""
+    d = _conv_desc(pc, in0, in1, out0, None, res0, None, 1.0, None, "3xf16", planar=1, dilation=dilation)
+    t = _pb()
+    check(_lib.get().estd_conv3d(ctypes.byref(d), _stream()), "estd_conv3d(planar)")
+    vox = float(d.D) * d.H * d.W
+    _pe(t, "conv2d_3xf16", 18.0 * pc.cin * pc.cout * vox, 4.0 * vox * (pc.cin + pc.cout))
+    return out0
+
+
+def nchw_to_vol4(x, out=None):
+    """[N,C,H,W] -> vol4 [C/4,N,H,W,4] (``out`` may be a chunk slice of a wider vol4 buffer)."""
+    N, C, H, W = x.shape
+    out = torch.empty(C // 4, N, H, W, 4, device=x.device, dtype=torch.float32) if out is None else out
+    t = _pb()
+    check(_lib.get().estd_nchw_to_vol4(_ptr(x), _ptr(out), N, C, H, W, _stream()), "estd_nchw_to_vol4")
+    _pe(t, "layout", 0.0, 8.0 * N * C * H * W)
+    return out
+
+
+def vol4_to_nchw(v, out=None):
+    chunks, N, H, W, _ = v.shape
+    out = torch.empty(N, chunks * 4, H, W, device=v.device, dtype=torch.float32) if out is None else out
+    t = _pb()
+    check(_lib.get().estd_vol4_to_nchw(_ptr(v), _ptr(out), N, chunks * 4, H, W, _stream()), "estd_vol4_to_nchw")
+    _pe(t, "layout", 0.0, 8.0 * N * chunks * 4 * H * W)
+    return out
 
 
 def est_attend(key_t, src_keys, src_values, warp30, depth_values, depth_min, depth_interval, out=None,

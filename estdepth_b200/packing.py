@@ -91,10 +91,10 @@ def pack_weight_f16(packed, cout_pad_tc=None):
     stays far above the fp16 subnormal threshold for every weight that matters); the kernel's output must be
     multiplied by 2^-k, which ``attach_tc`` folds into the per-channel scale.  K is zero padded to 16 channels.
     """
-    taps, cin_pad, cout_pad = packed.shape
+    taps, cin_pad, cout_pad = packed.shape             # taps = 27 (3x3x3) or 9 (planar 3x3)
     C = tc_cout_pad(cout_pad) if cout_pad_tc is None else cout_pad_tc
     nks = (cin_pad + 15) // 16
-    w = torch.zeros(27, 16 * nks, C, dtype=torch.float32, device=packed.device)
+    w = torch.zeros(taps, 16 * nks, C, dtype=torch.float32, device=packed.device)
     w[:, :cin_pad, :cout_pad] = packed
     wmax = float(w.abs().max())
     k = 0 if wmax == 0.0 else max(-14, min(24, int(torch.floor(torch.log2(torch.tensor(1023.0 / wmax))))))
@@ -102,10 +102,10 @@ def pack_weight_f16(packed, cout_pad_tc=None):
     hi = ws.to(torch.float16)
     lo = (ws - hi.to(torch.float32)).to(torch.float16)
 
-    def arrange(x):      # [27 = dd*9+tap9][16*nks = ks*16+kg*8+e][C] -> [dd][ks][tap9][kg][C][e]
-        return x.reshape(3, 9, nks, 2, 8, C).permute(0, 2, 1, 3, 5, 4)
+    def arrange(x):      # [taps = dd*9+tap9][16*nks = ks*16+kg*8+e][C] -> [dd][ks][tap9][kg][C][e]
+        return x.reshape(taps // 9, 9, nks, 2, 8, C).permute(0, 2, 1, 3, 5, 4)
 
-    both = torch.cat([arrange(hi), arrange(lo)], dim=4).contiguous()          # [3][nks][9][2][2C][8] fp16
+    both = torch.cat([arrange(hi), arrange(lo)], dim=4).contiguous()          # [planes][nks][9][2][2C][8] fp16
     return both.view(torch.float32), k
 
 
@@ -120,6 +120,27 @@ def attach_tc(pc):
             setattr(pc, name, torch.cat([v, torch.zeros(AFFINE_PAD - v.numel(), dtype=v.dtype, device=v.device)]).contiguous())
     pc.scale_f16 = (pc.scale * (2.0 ** -k)).contiguous()
     return pc
+
+
+def pack_conv2d(weight, scale, shift, act, device, cout_slice=64):
+    """2-D 3x3 conv [Cout,Cin,3,3] with folded per-channel affine -> list of PackedConv, one per ``cout_slice`` output
+    channels (the planar tensor-core kernel is specialised for 64 / 32 output channels; wider layers run as slices
+    writing adjacent chunk ranges of the output tensor)."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    out = []
+    for c0 in range(0, cout, cout_slice):
+        n = min(cout_slice, cout - c0)
+        w = weight[c0:c0 + n].reshape(n, cin, 9).permute(2, 1, 0).to(device=device, dtype=torch.float32).contiguous()   # [9][Cin][n]
+        wf16, k = pack_weight_f16(w, cout_slice)
+        s = torch.zeros(cout_slice, dtype=torch.float32, device=device)
+        b = torch.zeros(cout_slice, dtype=torch.float32, device=device)
+        s[:n] = scale[c0:c0 + n].to(device)
+        b[:n] = shift[c0:c0 + n].to(device)
+        pc = PackedConv(None, s, b, (cin + 3) // 4, cout_slice, (n + 3) // 4, cout_slice, act, act, cin=cin, cout=n,
+                        cout_pad_tc=cout_slice)
+        pc.weight_f16, pc.scale_f16 = wf16, (s * (2.0 ** -k)).contiguous()
+        out.append(pc)
+    return out
 
 
 def _affine(scale, shift, cout_order, device):

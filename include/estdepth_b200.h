@@ -97,6 +97,10 @@ typedef struct estd_conv3d_desc {
     const float* weight_tc;               /* tensor-core packing [3][nks][9][2][2*cout_pad rows][16 bytes] (hi|lo split), else NULL */
     int precision;                        /* ESTD_PREC_*; cout_pad is 16/32/40 for FP32 and 16/32/48 for the tensor-core paths */
     int* status;                          /* optional device int, OR-ed with 1 on an fp16 range violation (ESTD_PREC_3XF16) */
+    int planar;                           /* 0: 3x3x3 filter.  1: 1x3x3 filter applied per plane = 2-D 3x3 convolution over a stack of
+                                             D feature maps (the matching-feature net); weight_tc is [nks][9][2][2*cout_pad][16 B];
+                                             ESTD_PREC_3XF16 only */
+    int dilation;                         /* in-plane tap dilation, 1 or 2 (2: planar only); 0 is read as 1 */
     const float* scale;                   /* [cout_pad] per-channel multiplier (folded BN gamma/sqrt(var+eps)) */
     const float* shift;                   /* [cout_pad] per-channel offset (folded BN beta - mean*scale, or conv bias) */
     int cout_pad;                         /* padded number of output channels (see precision) */
@@ -148,6 +152,10 @@ ESTD_API int estd_head_softargmin(const float* hidden_vol4, const float* head_w,
 /* ---- layout helpers at the boundary (hidden state / context channel) ---- */
 ESTD_API int estd_vol4_to_ncdhw(const float* vol4, float* ncdhw, int C, int D, int H, int W, void* stream);
 ESTD_API int estd_ncdhw_to_vol4(const float* ncdhw, float* vol4, int C, int D, int H, int W, void* stream);
+/* stack of N feature maps: torch NCHW [N][C][H][W] <-> vol4 [C/4][N][H][W][4] (planes = maps), for the planar
+ * tensor-core convolutions of the matching-feature net (networks/psm_submodule.py:14-37,51-54) */
+ESTD_API int estd_nchw_to_vol4(const float* nchw, float* vol4, int N, int C, int H, int W, void* stream);
+ESTD_API int estd_vol4_to_nchw(const float* vol4, float* nchw, int N, int C, int H, int W, void* stream);
 /* out vol4 (1 chunk) = (in[d,h,w], 0, 0, 0): the 2-D context map entering dres2 as one 3-D channel
  * (hybrid_depth_decoder.py:195, quirk Q13) */
 ESTD_API int estd_scalar_to_vol4(const float* dhw, float* vol4_1chunk, int D, int H, int W, void* stream);

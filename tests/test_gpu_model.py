@@ -163,3 +163,23 @@ def test_cpu_tensors_are_rejected_loudly():
         model(imgs, poses, K, sample, mode="val")
     with pytest.raises(NotImplementedError):
         model(imgs, poses, K, sample, mode="train")
+
+
+def test_matching_feature_net_tensor_core_path_equals_cudnn_fp32():
+    """The planar tcgen05 convolutions (layers 2-4 + fuse conv of the PSM net) against cuDNN strict fp32 and the CPU oracle."""
+    torch.backends.cudnn.allow_tf32 = False
+    model, sd = synth_model_and_state(18, 32)
+    net = model.matchingFeature.cuda().eval()
+    imgs, _, _, _ = synth.synth_inputs(3, 128, 160, seed=3)
+    x = (2 * (imgs[0] / 255.) - 1.)
+    with torch.no_grad():
+        want = orc.psm_features(sd, x)
+        net.tensor_cores = False
+        ref = net(x.cuda())
+        net.tensor_cores = True
+        got = net(x.cuda())
+    scale = want.abs().max().item()
+    e_cudnn = (ref.cpu() - want).abs().max().item()
+    e_tc = (got.cpu() - want).abs().max().item()
+    print("psm features: max|.|=%.2f  cuDNN fp32 err %.2e  tensor-core err %.2e" % (scale, e_cudnn, e_tc))
+    assert e_tc < 2e-5 * max(1.0, scale)          # fp32 round-off through ~45 layers
