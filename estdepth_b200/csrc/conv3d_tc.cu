@@ -65,7 +65,12 @@ struct Shape {
     static constexpr int W_BYTES = 9 * W_TAP_BYTES;
     static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES + 127) / 128 * 128;
     static constexpr int STAGES = (3 * STAGE_BYTES <= 224 * 1024) ? 3 : 2;
-    static constexpr int COLS_PER_UNIT = MT * N_ALL;
+    // Accumulator sets: the tensor core adds into the fp32 accumulator with truncation, so the error of a long K loop
+    // grows with the number of accumulating MMAs.  Planar layers (all-positive post-ReLU inputs, up to 180 MMAs per
+    // accumulator) alternate k-steps between two sets that the epilogue adds in fp32 round-to-nearest.
+    static constexpr int ASETS = PLANAR ? 2 : 1;
+    static constexpr int COLS_PER_SET = MT * N_ALL;
+    static constexpr int COLS_PER_UNIT = ASETS * COLS_PER_SET;
     static constexpr int NBUF = (2 * COLS_PER_UNIT <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (NBUF * COLS_PER_UNIT <= 32) ? 32 : (NBUF * COLS_PER_UNIT <= 64) ? 64
                                    : (NBUF * COLS_PER_UNIT <= 128) ? 128 : (NBUF * COLS_PER_UNIT <= 256) ? 256 : 512;
@@ -242,7 +247,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                 const uint64_t a_hi_desc = make_desc(a_hi, KT::A_LBO, HALO_W * 16);
                 const uint64_t a_lo_desc = make_desc(a_hi + KT::A_LO_OFFSET, KT::A_LBO, HALO_W * 16);
                 const uint64_t b_desc = make_desc(a_hi + A_BYTES, C::N_ALL * 16, 128);
-                const uint32_t first = (st == 0) ? 0u : 1u;
+                const uint32_t aset = (S::ASETS > 1) ? (uint32_t)(st % S::ASETS) : 0u;
+                const uint32_t first = (st < S::ASETS) ? 0u : 1u;          // first MMA into this accumulator set
+                const uint32_t acc_set = acc0 + aset * (uint32_t)S::COLS_PER_SET;
                 if (leader) {
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
@@ -251,7 +258,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                             // start-address field is in 16-byte units: one voxel (float4) per unit
                             const uint64_t a_off = (uint64_t)((tap / 3) * S::DIL * HALO_W + 8 * mt + (tap % 3) * S::DIL);
                             const uint64_t b_off = (uint64_t)(tap * (C::W_TAP_BYTES >> 4));
-                            const uint32_t acc = acc0 + (uint32_t)(mt * C::N_ALL);
+                            const uint32_t acc = acc_set + (uint32_t)(mt * C::N_ALL);
                             umma<KIND>(acc, a_hi_desc + a_off, b_desc + b_off, idesc_all, tap == 0 ? first : 1u);
                             umma<KIND>(acc + COUT, a_lo_desc + a_off, b_desc + b_off, idesc_hi, 1u);
                         }
@@ -339,6 +346,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                     tmem_ld16(acc0 + (uint32_t)(mt * C::N_ALL + c0), a);
                     tmem_ld16(acc0 + (uint32_t)(mt * C::N_ALL + COUT + c0), b);
                     tmem_ld_wait();
+                    if constexpr (S::ASETS == 2) {
+                        float a2[16], b2[16];
+                        tmem_ld16(acc0 + (uint32_t)(S::COLS_PER_SET + mt * C::N_ALL + c0), a2);
+                        tmem_ld16(acc0 + (uint32_t)(S::COLS_PER_SET + mt * C::N_ALL + COUT + c0), b2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { a[i] += a2[i]; b[i] += b2[i]; }
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) a[i] += b[i];
                     float ts[2] = {0.f, 0.f}, tq[2] = {0.f, 0.f};

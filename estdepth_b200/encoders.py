@@ -90,8 +90,12 @@ class MatchingFeatureNet(nn.Module):
         if getattr(self, "_tc_key", None) != key:
             def pack(seq, act):          # seq = Sequential(conv, bn)
                 s, b = self._bn_affine(seq[1])
-                return packing.pack_conv2d(seq[0].weight.detach(), s, b, act, device)
+                w = seq[0].weight.detach()
+                return packing.pack_conv2d(w, s, b, act, device, cout_slice=64 if w.shape[0] >= 64 else 32)
             P = {}
+            P["stem2"], P["stem4"] = pack(self.firstconv[2], "relu"), pack(self.firstconv[4], "relu")
+            for i, blk in enumerate(self.layer1):
+                P[("layer1", i, 1)], P[("layer1", i, 2)] = pack(blk.conv1[0], "relu"), pack(blk.conv2, "none")
             for name in ("layer2", "layer3", "layer4"):
                 for i, blk in enumerate(getattr(self, name)):
                     if blk.conv1[0][0].stride == (1, 1):
@@ -106,7 +110,7 @@ class MatchingFeatureNet(nn.Module):
         """Runs a (possibly output-sliced) packed 3x3 layer: slice i writes chunks [16i, 16i+16) of out4."""
         from . import ops
         for i, pc in enumerate(pcs):
-            lo, hi = 16 * i, 16 * i + pc.out_chunks
+            lo, hi = 16 * i, 16 * i + pc.out_chunks                 # (single-slice layers: i == 0)
             ops.conv_planar(pc, x4, out4[lo:hi], res0=None if res4 is None else res4[lo:hi], dilation=dilation)
         return out4
 
@@ -116,8 +120,15 @@ class MatchingFeatureNet(nn.Module):
         accuracy) with BN / ReLU / residual add fused into their epilogues; activations stay in vol4 between them."""
         from . import ops
         P = self._packed(x.device)
-        x = self.layer1(self.firstconv(x))
-        N = x.shape[0]
+        x = self.firstconv[1](self.firstconv[0](x))                 # 3->32 stride-2 stem conv: cuDNN
+        N, _, Hh, Wh = x.shape
+        half = lambda: torch.empty(8, N, Hh, Wh, 4, device=x.device, dtype=torch.float32)  # noqa: E731
+        cur = self._conv_tc(P["stem4"], self._conv_tc(P["stem2"], ops.nchw_to_vol4(x), half()), half())
+        tmp = half()
+        for i in range(len(self.layer1)):
+            self._conv_tc(P[("layer1", i, 1)], cur, tmp)
+            cur = self._conv_tc(P[("layer1", i, 2)], tmp, half(), cur)
+        x = ops.vol4_to_nchw(cur)
         blk = self.layer2[0]
         y = blk.conv1(x)                                            # stride-2 conv: cuDNN
         H, W = y.shape[-2:]

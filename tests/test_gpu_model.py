@@ -61,6 +61,9 @@ def test_joint_windows_match_reference_golden(resnet, ndepths, height, width, na
             assert d < tol, (w, key, d)
         sk = state["keys"][0][..., ::STATE_STRIDE, ::STATE_STRIDE].cpu().numpy()
         sv = state["values"][0][..., ::STATE_STRIDE, ::STATE_STRIDE].cpu().numpy()
+        worst["state_value"] = max(worst.get("state_value", 0.0), float(np.abs(sv - gold["w%d/state_value" % w]).max()))
+        worst["state_key_rel"] = max(worst.get("state_key_rel", 0.0), float(np.abs(sk - gold["w%d/state_key" % w]).max()
+                                                                           / max(1.0, np.abs(gold["w%d/state_key" % w]).max())))
         assert np.abs(sk - gold["w%d/state_key" % w]).max() < STATE_TOL * max(1.0, np.abs(gold["w%d/state_key" % w]).max())
         assert np.abs(sv - gold["w%d/state_value" % w]).max() < STATE_TOL
         # quirk Q4: the pose returned with window 2's state is window 1's (stale) pose
