@@ -21,6 +21,43 @@ import torch.nn.functional as F
 import torchvision.models as tvm
 
 
+class _FoldedConv(object):
+    """Eval-mode conv+BN pairs of the cuDNN-side layers run as ONE convolution with the BN affine folded into weight and
+    bias (w' = w * gamma/sqrt(var+eps), b' = beta - mean * gamma/sqrt(var+eps)), optionally with cuDNN's fused
+    bias(+residual)+ReLU epilogue.  Saves one full read+write of every feature map per BN and per ReLU.  Folded
+    parameters are cached and re-derived when the underlying parameters change (``_version`` counters)."""
+
+    def __init__(self):
+        self.cache = {}
+
+    def params(self, conv, bn):
+        ver = (conv.weight.data_ptr(), conv.weight._version, bn.weight._version, bn.bias._version,
+               bn.running_mean._version, bn.running_var._version)
+        ent = self.cache.get(id(conv))
+        if ent is None or ent[0] != ver:
+            with torch.no_grad():
+                s = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
+                w = (conv.weight.double() * s.view(-1, 1, 1, 1)).float().contiguous()
+                b = (bn.bias.double() - bn.running_mean.double() * s).float().contiguous()
+            ent = (ver, w, b)
+            self.cache[id(conv)] = ent
+        return ent[1], ent[2]
+
+    def __call__(self, x, conv, bn, relu=False, residual=None):
+        w, b = self.params(conv, bn)
+        if x.is_cuda and relu and conv.groups == 1:
+            if residual is not None:
+                return torch.cudnn_convolution_add_relu(x, w, residual, 1.0, b, conv.stride, conv.padding, conv.dilation, 1)
+            return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, 1)
+        y = F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+        if residual is not None:
+            y = y + residual
+        return F.relu_(y) if relu else y
+
+
+_folded = _FoldedConv()
+
+
 def _conv_bn(cin, cout, k, stride, pad, dilation):
     """conv(bias=False)+BN pair; padding rule of networks/layers_op.py:10-14 (pad = dilation if dilation>1)."""
     return nn.Sequential(
@@ -120,7 +157,7 @@ class MatchingFeatureNet(nn.Module):
         accuracy) with BN / ReLU / residual add fused into their epilogues; activations stay in vol4 between them."""
         from . import ops
         P = self._packed(x.device)
-        x = self.firstconv[1](self.firstconv[0](x))                 # 3->32 stride-2 stem conv: cuDNN
+        x = _folded(x, self.firstconv[0][0], self.firstconv[0][1], relu=True)   # 3->32 stride-2 stem conv: cuDNN
         N, _, Hh, Wh = x.shape
         half = lambda: torch.empty(8, N, Hh, Wh, 4, device=x.device, dtype=torch.float32)  # noqa: E731
         cur = self._conv_tc(P["stem4"], self._conv_tc(P["stem2"], ops.nchw_to_vol4(x), half()), half())
@@ -130,7 +167,7 @@ class MatchingFeatureNet(nn.Module):
             cur = self._conv_tc(P[("layer1", i, 2)], tmp, half(), cur)
         x = ops.vol4_to_nchw(cur)
         blk = self.layer2[0]
-        y = blk.conv1(x)                                            # stride-2 conv: cuDNN
+        y = _folded(x, blk.conv1[0][0], blk.conv1[0][1], relu=True)  # stride-2 conv: cuDNN
         H, W = y.shape[-2:]
         dev = x.device
 
@@ -138,7 +175,7 @@ class MatchingFeatureNet(nn.Module):
             return torch.empty(chunks, N, H, W, 4, device=dev, dtype=torch.float32)
 
         cat = vol(80)                                               # [raw 64 | skip 128 | branch4..1 32 each]
-        cur = self._conv_tc(P[("layer2", 0, 2)], ops.nchw_to_vol4(y), vol(16), ops.nchw_to_vol4(blk.downsample(x)))
+        cur = self._conv_tc(P[("layer2", 0, 2)], ops.nchw_to_vol4(y), vol(16), ops.nchw_to_vol4(_folded(x, blk.downsample[0], blk.downsample[1])))
         tmp = vol(16)
         n2 = len(self.layer2)
         for i in range(1, n2):
@@ -148,7 +185,7 @@ class MatchingFeatureNet(nn.Module):
         raw = cur
         # layer3: block 0 changes the width (64 -> 128) and projects the shortcut with a 1x1 conv (cuDNN)
         blk = self.layer3[0]
-        shortcut = ops.nchw_to_vol4(blk.downsample(ops.vol4_to_nchw(raw)))
+        shortcut = ops.nchw_to_vol4(_folded(ops.vol4_to_nchw(raw), blk.downsample[0], blk.downsample[1]))
         tmp = self._conv_tc(P[("layer3", 0, 1)], raw, vol(32))
         cur = self._conv_tc(P[("layer3", 0, 2)], tmp, vol(32), shortcut)
         stages = [("layer3", i, 1) for i in range(1, len(self.layer3))] + [("layer4", i, 2) for i in range(len(self.layer4))]
@@ -157,8 +194,12 @@ class MatchingFeatureNet(nn.Module):
             nxt = cat[16:48] if k == len(stages) - 1 else vol(32)
             cur = self._conv_tc(P[(name, i, 2)], tmp, nxt, cur, dilation=dil)
         deep = ops.vol4_to_nchw(cur)                                # SPP pooling / 1x1 / bilinear resize: torch
+        pooled = None
         for slot, idx in enumerate((4, 3, 2, 1)):
-            b = F.interpolate(getattr(self, "branch%d" % idx)(deep), size=(H, W), mode="bilinear", align_corners=False)
+            br = getattr(self, "branch%d" % idx)
+            # the pooling windows nest (4, 8, 16, 32): each level is the 2x2 average of the previous one
+            pooled = F.avg_pool2d(deep, 4, 4) if pooled is None else F.avg_pool2d(pooled, 2, 2)
+            b = F.interpolate(_folded(pooled, br[1][0], br[1][1], relu=True), size=(H, W), mode="bilinear", align_corners=False)
             ops.nchw_to_vol4(b.contiguous(), cat[48 + 8 * slot:56 + 8 * slot])
         fused = self._conv_tc(P["fuse"], cat, vol(32))
         return self.lastconv[2](ops.vol4_to_nchw(fused))
@@ -194,12 +235,30 @@ class ContextEncoder(nn.Module):
             self.num_ch_enc[1:] *= 4
         self.encoder = ctor[num_layers](weights=None)
 
+    @staticmethod
+    def _block(blk, x):
+        """torchvision BasicBlock / Bottleneck in eval mode with folded BN and fused bias/residual/ReLU epilogues."""
+        identity = x if blk.downsample is None else _folded(x, blk.downsample[0], blk.downsample[1])
+        y = _folded(x, blk.conv1, blk.bn1, relu=True)
+        if hasattr(blk, "conv3"):
+            y = _folded(y, blk.conv2, blk.bn2, relu=True)
+            return _folded(y, blk.conv3, blk.bn3, relu=True, residual=identity)
+        return _folded(y, blk.conv2, blk.bn2, relu=True, residual=identity)
+
     def forward(self, x):
         e = self.encoder
-        maps = [e.relu(e.bn1(e.conv1(x)))]
-        maps.append(e.layer1(e.maxpool(maps[-1])))
-        for stage in (e.layer2, e.layer3, e.layer4):
-            maps.append(stage(maps[-1]))
+        if self.training:
+            maps = [e.relu(e.bn1(e.conv1(x)))]
+            maps.append(e.layer1(e.maxpool(maps[-1])))
+            for stage in (e.layer2, e.layer3, e.layer4):
+                maps.append(stage(maps[-1]))
+            return maps
+        maps = [_folded(x, e.conv1, e.bn1, relu=True)]
+        x = e.maxpool(maps[-1])
+        for stage in (e.layer1, e.layer2, e.layer3, e.layer4):
+            for blk in stage:
+                x = self._block(blk, x)
+            maps.append(x)
         return maps
 
 
@@ -211,7 +270,9 @@ class _UpBlock(nn.Module):
         self.conv = _conv_bn(int(cin), int(cout), 3, 1, 1, 1)
 
     def forward(self, x):
-        return F.relu(self.conv(x), inplace=True)
+        if self.training:
+            return F.relu(self.conv(x), inplace=True)
+        return _folded(x, self.conv[0], self.conv[1], relu=True)
 
 
 def _up2(x):
