@@ -10,16 +10,41 @@
 
 namespace estd {
 
-__global__ void __launch_bounds__(128) head_softargmin_kernel(const float* __restrict__ hidden, const float* __restrict__ head_w,
+// Block = 32 pixels (lanes, consecutive w) x kSlices depth slices (warps).  Each warp owns a contiguous range of planes and
+// keeps an online (max, sum, weighted sum, argmax); the 8 partial states of a pixel are merged in plane order by warp 0, so
+// "first maximum wins" (torch.max) is preserved.  (v1 walked all D planes in one thread: 150 blocks, latency bound, 12 % of HBM.)
+constexpr int kSlices = 8;
+
+struct SoftState { float m, s, ws; int best; };
+
+__device__ __forceinline__ void soft_update(SoftState& st, float l, float dv, int d) {
+    if (l > st.m) {                                    // strict: first maximum wins, like torch.max
+        const float scale = expf(st.m - l);            // exp(-inf) = 0 on the first plane
+        st.s = fmaf(st.s, scale, 1.0f);
+        st.ws = fmaf(st.ws, scale, dv);
+        st.m = l;
+        st.best = d;
+    } else {
+        const float e = expf(l - st.m);
+        st.s += e;
+        st.ws = fmaf(e, dv, st.ws);
+    }
+}
+
+__global__ void __launch_bounds__(32 * kSlices) head_softargmin_kernel(const float* __restrict__ hidden, const float* __restrict__ head_w,
                                                               const float* __restrict__ head_b, const float* __restrict__ logits_in,
                                                               const float* __restrict__ depth_values, float* __restrict__ logits_out,
                                                               float* __restrict__ depth_out, float* __restrict__ prob_out,
                                                               int* __restrict__ argmax_out, int D, int H, int W, int up) {
+    __shared__ SoftState part[kSlices][32];
     const int HW = H * W;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= HW) return;
-    const int h = p / W, w = p - h * W;
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + lane;
+    const bool valid = p < HW;
+    const int pc = valid ? p : HW - 1;
     const size_t vox = (size_t)D * HW;
+    const int per = (D + kSlices - 1) / kSlices;
+    const int d_begin = slice * per, d_end = min(D, d_begin + per);
     float4 hw4[4];
     float bias = 0.0f;
     if (hidden) {
@@ -27,38 +52,47 @@ __global__ void __launch_bounds__(128) head_softargmin_kernel(const float* __res
         for (int j = 0; j < 4; ++j) hw4[j] = ldg4(head_w + j * 4);
         bias = __ldg(head_b);
     }
-    float m = -INFINITY, s = 0.0f, ws = 0.0f;
-    int best = 0;
-    for (int d = 0; d < D; ++d) {
+    SoftState st = {-INFINITY, 0.0f, 0.0f, d_begin};
+#pragma unroll 4
+    for (int d = d_begin; d < d_end; ++d) {
         float l;
         if (hidden) {
             l = 0.0f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float4 x = ldg4(hidden + (j * vox + (size_t)d * HW + p) * 4);
+                const float4 x = ldg4(hidden + (j * vox + (size_t)d * HW + pc) * 4);
                 l = fmaf(x.x, hw4[j].x, l); l = fmaf(x.y, hw4[j].y, l);
                 l = fmaf(x.z, hw4[j].z, l); l = fmaf(x.w, hw4[j].w, l);
             }
             l += bias;
         } else {
-            l = __ldg(logits_in + (size_t)d * HW + p);
+            l = __ldg(logits_in + (size_t)d * HW + pc);
         }
-        if (logits_out) logits_out[(size_t)d * HW + p] = l;
-        const float dv = __ldg(depth_values + d);
-        if (l > m) {                                   // strict: first maximum wins, like torch.max
-            const float scale = expf(m - l);           // exp(-inf) = 0 on the first plane
-            s = fmaf(s, scale, 1.0f);
-            ws = fmaf(ws, scale, dv);
-            m = l;
-            best = d;
+        if (logits_out && valid) logits_out[(size_t)d * HW + p] = l;
+        soft_update(st, l, __ldg(depth_values + d), d);
+    }
+    part[slice][lane] = st;
+    __syncthreads();
+    if (slice != 0 || !valid) return;
+    for (int k = 1; k < kSlices; ++k) {                // merge in plane order
+        const SoftState o = part[k][lane];
+        if (o.s == 0.0f) continue;                     // empty slice (D < kSlices * per)
+        if (o.m > st.m) {
+            const float scale = expf(st.m - o.m);
+            st.s = fmaf(st.s, scale, o.s);
+            st.ws = fmaf(st.ws, scale, o.ws);
+            st.m = o.m;
+            st.best = o.best;
         } else {
-            const float e = expf(l - m);
-            s += e;
-            ws = fmaf(e, dv, ws);
+            const float scale = expf(o.m - st.m);
+            st.s = fmaf(o.s, scale, st.s);
+            st.ws = fmaf(o.ws, scale, st.ws);
         }
     }
-    const float depth = __fdiv_rn(ws, s);
-    const float prob = __fdiv_rn(1.0f, s);
+    const int h = p / W, w = p - h * W;
+    const float depth = __fdiv_rn(st.ws, st.s);
+    const float prob = __fdiv_rn(1.0f, st.s);
+    const int best = st.best;
     const int WU = W * up;
     for (int r = 0; r < up; ++r) {
         const size_t row = ((size_t)(h * up + r)) * WU + (size_t)w * up;
@@ -139,7 +173,7 @@ extern "C" int estd_head_softargmin(const float* hidden_vol4, const float* head_
     ESTD_REQUIRE((hidden_vol4 && head_w && head_b) || logits_in, "estd_head_softargmin: need hidden+head or logits_in");
     if (up == 4) ESTD_REQUIRE((!depth_out || aligned16(depth_out)) && (!prob_out || aligned16(prob_out)) &&
                               (!argmax_out || aligned16(argmax_out)), "estd_head_softargmin: outputs must be 16-byte aligned");
-    head_softargmin_kernel<<<(H * W + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    head_softargmin_kernel<<<(H * W + 31) / 32, 32 * kSlices, 0, (cudaStream_t)stream>>>(
         hidden_vol4, head_w, head_b, hidden_vol4 ? nullptr : logits_in, depth_values, logits_out, depth_out, prob_out,
         argmax_out, D, H, W, up);
     return check_launch("estd_head_softargmin");

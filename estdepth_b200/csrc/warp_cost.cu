@@ -91,29 +91,31 @@ __device__ __forceinline__ Taps2 plane_sweep_taps(const float (&hm)[12], float f
     return t;
 }
 
-// Block = 8 rows x 32 columns of target pixels, kPlanes consecutive depth planes per thread.  The target-side value is
-// loaded once per chunk and reused for all planes, vertically adjacent warps share source rows in L1, and each thread
-// keeps 4*kPlanes+1 independent 16-byte loads in flight per chunk.  (The first version, one voxel per thread and one
-// plane per block, re-fetched both maps from L2 for every plane and was L2-bandwidth bound: profiles/README.md.)
-constexpr int kPlanes = 4;
-
-template <int ALIGN>
-__global__ void __launch_bounds__(256) warp_cost_kernel(const float* __restrict__ ref_mix, const float* __restrict__ src_mix,
-                                                        const float* __restrict__ homo12,
-                                                        const float* __restrict__ depth_values,
-                                                        float* __restrict__ x0, int chunks, int D, int H, int W) {
+// Block = 8 rows x 32 columns of target pixels x KP consecutive depth planes per thread.  The target-side value is
+// loaded once per chunk and reused for all KP planes, vertically adjacent warps share source rows in L1, and each thread
+// keeps 4*KP+1 independent 16-byte loads in flight per chunk.  KP is chosen per launch so that the number of (equal)
+// blocks fills whole waves of the 4-blocks-per-SM residency (480x640/D=64: KP=3 -> 1650 blocks = 2.8 waves; KP=4 gave
+// 1200 blocks = 2.03 waves, i.e. a third of the time was an almost empty tail).
+// History (profiles/README.md): v1 one voxel per thread, one plane per block -> L2-bandwidth bound (L1 hit 42 %);
+// a persistent one-plane-at-a-time variant was slower (fewer loads in flight); the kernel is L1-pipe bound (ncu:
+// l1tex 68 % of peak, 6 x 16 B through the L1 pipe per 16 B stored).
+template <int ALIGN, int KP>
+__global__ void __launch_bounds__(256, 4) warp_cost_kernel(const float* __restrict__ ref_mix, const float* __restrict__ src_mix,
+                                                           const float* __restrict__ homo12,
+                                                           const float* __restrict__ depth_values,
+                                                           float* __restrict__ x0, int chunks, int D, int H, int W) {
     const int w = blockIdx.x * 32 + (threadIdx.x & 31);
     const int h = blockIdx.y * 8 + (threadIdx.x >> 5);
-    const int d0 = blockIdx.z * kPlanes;
+    const int d0 = blockIdx.z * KP;
     if (w >= W || h >= H) return;
     const int HW = H * W;
     const int p = h * W + w;
     float hm[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) hm[i] = __ldg(homo12 + i);
-    Taps2 taps[kPlanes];
+    Taps2 taps[KP];
 #pragma unroll
-    for (int k = 0; k < kPlanes; ++k) {
+    for (int k = 0; k < KP; ++k) {
         const int d = min(d0 + k, D - 1);
         taps[k] = plane_sweep_taps<ALIGN>(hm, (float)w, (float)h, __ldg(depth_values + d), H, W);
     }
@@ -125,14 +127,14 @@ __global__ void __launch_bounds__(256) warp_cost_kernel(const float* __restrict_
     for (int j = 0; j < chunks; ++j) {
         const float* s = src_mix + j * plane;
         const float4 r = ldg4(refp + j * plane);
-        float4 a[kPlanes], b[kPlanes], c[kPlanes], e[kPlanes];
+        float4 a[KP], b[KP], c[KP], e[KP];
 #pragma unroll
-        for (int k = 0; k < kPlanes; ++k) {
+        for (int k = 0; k < KP; ++k) {
             a[k] = ldg4(s + taps[k].o_nw); b[k] = ldg4(s + taps[k].o_ne);
             c[k] = ldg4(s + taps[k].o_sw); e[k] = ldg4(s + taps[k].o_se);
         }
 #pragma unroll
-        for (int k = 0; k < kPlanes; ++k) {
+        for (int k = 0; k < KP; ++k) {
             if (d0 + k >= D) break;
             const Taps2& t = taps[k];
             float4 o;
@@ -143,6 +145,13 @@ __global__ void __launch_bounds__(256) warp_cost_kernel(const float* __restrict_
             st4(outp + j * out_chunk + (size_t)k * plane, o);
         }
     }
+}
+
+template <int KP>
+static void launch_warp_cost(int align, dim3 grid, cudaStream_t st, const float* ref, const float* src, const float* homo,
+                             const float* dv, float* x0, int chunks, int D, int H, int W) {
+    if (align) warp_cost_kernel<1, KP><<<grid, 256, 0, st>>>(ref, src, homo, dv, x0, chunks, D, H, W);
+    else       warp_cost_kernel<0, KP><<<grid, 256, 0, st>>>(ref, src, homo, dv, x0, chunks, D, H, W);
 }
 
 }  // namespace estd
@@ -164,16 +173,33 @@ extern "C" int estd_warp_cost(const float* ref_mix_map4, const float* src_mix_ma
                               const float* depth_values, float* x0_vol4, int C, int D, int H, int W,
                               int align_corners, void* stream) {
     ESTD_REQUIRE(ref_mix_map4 && src_mix_map4 && homo12 && depth_values && x0_vol4, "estd_warp_cost: null pointer");
-    ESTD_REQUIRE(C > 0 && (C % 4) == 0 && D > 0 && D <= 65535 * 4 && H > 1 && W > 1 && H <= 65535 * 8,
+    ESTD_REQUIRE(C > 0 && (C % 4) == 0 && D > 0 && H > 1 && W > 1 && (long long)D * H * W < (1ll << 30),
                  "estd_warp_cost: unsupported shape C=%d D=%d H=%d W=%d", C, D, H, W);
     ESTD_REQUIRE(estd::aligned16(ref_mix_map4) && estd::aligned16(src_mix_map4) && estd::aligned16(x0_vol4),
                  "estd_warp_cost: tensors must be 16-byte aligned");
-    dim3 grid((W + 31) / 32, (H + 7) / 8, (D + estd::kPlanes - 1) / estd::kPlanes);
-    if (align_corners)
-        estd::warp_cost_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(ref_mix_map4, src_mix_map4, homo12,
-                                                                          depth_values, x0_vol4, C / 4, D, H, W);
-    else
-        estd::warp_cost_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(ref_mix_map4, src_mix_map4, homo12,
-                                                                          depth_values, x0_vol4, C / 4, D, H, W);
+    const int tiles_w = (W + 31) / 32, tiles_h = (H + 7) / 8;
+    int sms = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // planes per thread: the value in 2..5 whose block count fills whole waves of 4 resident blocks per SM best
+    int best_kp = 4;
+    double best_eff = -1.0;
+    for (int kp = 5; kp >= 2; --kp) {
+        const long long blocks = (long long)tiles_w * tiles_h * ((D + kp - 1) / kp);
+        const long long slots = (long long)sms * 4;
+        const double eff = (double)D / (double)(((D + kp - 1) / kp) * kp) * (double)blocks / (double)(((blocks + slots - 1) / slots) * slots);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_kp = kp; }
+    }
+    const dim3 grid(tiles_w, tiles_h, (D + best_kp - 1) / best_kp);
+    ESTD_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "estd_warp_cost: volume too large");
+    const cudaStream_t st = (cudaStream_t)stream;
+    switch (best_kp) {
+        case 2: estd::launch_warp_cost<2>(align_corners, grid, st, ref_mix_map4, src_mix_map4, homo12, depth_values, x0_vol4, C / 4, D, H, W); break;
+        case 3: estd::launch_warp_cost<3>(align_corners, grid, st, ref_mix_map4, src_mix_map4, homo12, depth_values, x0_vol4, C / 4, D, H, W); break;
+        case 4: estd::launch_warp_cost<4>(align_corners, grid, st, ref_mix_map4, src_mix_map4, homo12, depth_values, x0_vol4, C / 4, D, H, W); break;
+        default: estd::launch_warp_cost<5>(align_corners, grid, st, ref_mix_map4, src_mix_map4, homo12, depth_values, x0_vol4, C / 4, D, H, W); break;
+    }
     return estd::check_launch("estd_warp_cost");
 }
