@@ -317,7 +317,7 @@ def run_ours(args):
     dom = max(kernels.items(), key=lambda kv: kv[1]["share_ms_per_step"])
     conv_name = "conv3d_" + model.precision
     conv = kernels.get(conv_name, dom[1])
-    mma_per_flop = {"fp32": 0.0, "3xtf32": 3.0, "3xf16": 3.0}[model.precision]
+    mma_per_flop = {"fp32": 0.0, "3xtf32": 3.0, "3xf16": 3.0, "3xf16r": 3.0}[model.precision]
     roofline = {"kernel": "estd conv3d_tc_kernel (3x3x3 implicit GEMM, %s)" % model.precision if conv_name in kernels else dom[0], "bound": "tensor",
                 "achieved": conv.get("TFLOPps"), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": (conv.get("TFLOPps") or 0.0) / peaks["bf16_sustained"], "traffic": None,
@@ -351,7 +351,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=None, choices=["fp32", "3xtf32", "3xf16"], help="conv3d arithmetic (default: the model's)")
+    ap.add_argument("--precision", default=None, choices=["fp32", "3xtf32", "3xf16", "3xf16r"], help="conv3d arithmetic (default: the model's)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~1 min oracle timing on the host cores")
     args = ap.parse_args()
     if args.impl == "reference":

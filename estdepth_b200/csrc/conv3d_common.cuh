@@ -33,6 +33,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
+// Same bound without reading the clock in the loop (the spinning roles of the ring kernel poll from 16 warps at once and
+// CS2R competes for the XU pipe): try_wait suspends for a hardware-chosen time slice, 2^27 slices is seconds.
+__device__ __forceinline__ void mbar_wait_polls(uint64_t* bar, uint32_t parity) {
+    for (uint32_t i = 0; !mbar_try_wait(bar, parity); ++i) {
+        if (i > (1u << 27)) __trap();
+    }
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -138,5 +145,7 @@ inline int sm_count() {
 
 // implemented in conv3d_tc.cu
 int dispatch_tc(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas);
+// implemented in conv3d_ring.cu
+int dispatch_ring(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas);
 
 }  // namespace estd

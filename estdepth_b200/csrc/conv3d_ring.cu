@@ -1,0 +1,414 @@
+// K2, plane-ring schedule: 3x3x3 convolution on the tcgen05 tensor cores with the fp16 two-term split of conv3d_tc.cu
+// (x = x_hi + x_lo, w * 2^k = w_hi + w_lo; x_hi w_hi + x_hi w_lo + x_lo w_hi accumulated in fp32 in TMEM), re-scheduled so
+// that the depth taps ride in the N dimension of the MMA.
+//
+// Why: with N = Cout = 32 the output-stationary kernel reads a 4 KB A operand from shared memory for every 32 accumulator
+// columns and is bound by shared-memory bandwidth (tensor pipe 35 % busy, profiles/README.md).  Here the INPUT plane is
+// stationary: one halo tile of input plane z is loaded and split once and multiplied against the weights of all three
+// depth taps at once, N = 3*Cout -- the three column blocks are the accumulators of output planes z+1, z, z-1.  Per
+// product that is one third of the A reads, one third of the TMA traffic and one third of the split work.
+//
+//   unit      a column of 16 x 32 voxels walked along depth; accumulators of the three output planes in flight live in a
+//             ring of 3 TMEM slots (slot = z mod 3) per M tile: 4 M tiles x 3 slots x Cout columns.
+//   weights   the slot <-> depth-tap assignment rotates with z mod 3, and B rows map 1:1 onto D columns, so the packed
+//             weights come in the 3 rotations; the stage of input plane z streams rotation z mod 3 (55 KB per 16 channels).
+//   MMA       per in-plane tap and M tile: A_hi x W_hi, A_hi x W_lo, A_lo x W_hi, each M = 128, N = 3*Cout, K = 16, all
+//             accumulating (slots are zeroed by the epilogue after it has read them, so there is no "first" MMA).
+//   epilogue  the column is two half tiles (M tiles 0,1 | 2,3).  After the MMAs of plane z, output plane z-1 is complete:
+//             the issuer commits half A, then issues half B; the 8 epilogue warps drain + zero half A's slot while the
+//             tensor core works on half B, and vice versa -- no second accumulator buffer needed.
+//   balance   the flat list of (column, plane) pairs is cut into one contiguous range per CTA; a range that starts or
+//             ends inside a column pays one partial extra input plane (a single depth tap, N = Cout) on that side.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "conv3d_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace estd {
+namespace ring {
+
+using namespace tc;
+
+constexpr int EPI_WARPS = 8, SPLIT_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32, SPLIT_THREADS = SPLIT_WARPS * 32;
+constexpr int THREADS = 128 + EPI_THREADS + SPLIT_THREADS;       // warps 0-3 control, 4-11 epilogue, 12-19 splitters
+constexpr int FIRST_SPLIT_WARP = 4 + EPI_WARPS;
+
+template <int NKS_, int COUT_>
+struct Shape {
+    static constexpr int NKS = NKS_, COUT = COUT_, MT = 4;
+    static constexpr int TILE_H = 16, TILE_W = 8 * MT;
+    static constexpr int HALO_H = TILE_H + 2, HALO_W = TILE_W + 2, HALO_VOX = HALO_H * HALO_W;
+    static constexpr int KGROUP_BYTES = HALO_VOX * 16;            // one 16-byte K-group (8 x fp16) of the halo tile
+    static constexpr int A_BYTES = 4 * KGROUP_BYTES;              // 16 channels: lands as 4 fp32 chunks, becomes hi|lo|hi|lo
+    static constexpr int N3 = 3 * COUT;                           // columns of one M tile: 3 ring slots
+    static constexpr int W_PART_BYTES = 2 * N3 * 16;              // [2 K-groups][N3 rows][16 B] of w_hi (or w_lo)
+    static constexpr int W_TAP_BYTES = 2 * W_PART_BYTES;          // w_hi block, then w_lo block
+    static constexpr int W_BYTES = 9 * W_TAP_BYTES;
+    static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES + 127) / 128 * 128;
+    static constexpr int STAGES = 2;
+    static constexpr int COLS = MT * N3;
+    static constexpr int TMEM_COLS = (COLS <= 128) ? 128 : (COLS <= 256) ? 256 : 512;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;
+    static_assert(COLS <= 512, "ring accumulators must fit TMEM");
+    static_assert(SMEM <= 227 * 1024, "stages must fit shared memory");
+    static_assert(COUT % 16 == 0 && N3 <= 256, "bad N");
+};
+
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+                 ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+struct Params {
+    const float* weight_ring;                   // [3 rotations][NKS][9 taps][hi,lo][2 K-groups][3*COUT rows][16 bytes]
+    int* status;
+    ConvEpilogue ep;
+    int in0_chunks;
+    int D, H, W;
+    int tiles_h, tiles_w;
+    int total;                                  // columns * D  (flat (column, plane) index space)
+};
+
+// The contiguous piece [f0, f1) of the flat (column, plane) list owned by this CTA, walked segment by segment.
+struct Segment { int col, z0, z1; };
+__device__ __forceinline__ bool next_segment(int& f, int f1, int D, Segment& s) {
+    if (f >= f1) return false;
+    s.col = f / D;
+    s.z0 = f - s.col * D;
+    const int n = min(D - s.z0, f1 - f);
+    s.z1 = s.z0 + n;
+    f += n;
+    return true;
+}
+
+template <class S>
+__global__ void __launch_bounds__(THREADS, 1)
+conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Params p) {
+    constexpr int NKS = S::NKS, COUT = S::COUT, STAGES = S::STAGES, N3 = S::N3;
+    constexpr int HALO_W = S::HALO_W, HALO_VOX = S::HALO_VOX, A_BYTES = S::A_BYTES;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * S::STAGE_BYTES);
+    uint64_t* full = bars;                  // [STAGES] TMA landed
+    uint64_t* ready = bars + STAGES;        // [STAGES] split done
+    uint64_t* empty = bars + 2 * STAGES;    // [STAGES] MMAs done reading
+    uint64_t* acc_full = bars + 3 * STAGES; // [2 halves] an output plane of this half tile is complete
+    uint64_t* acc_empty = acc_full + 2;     // [2 halves] its slot has been read and zeroed
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    __shared__ double s_red[EPI_WARPS][4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], SPLIT_THREADS); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_THREADS); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_base_smem, S::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    // every ring slot starts at zero: all MMAs accumulate
+    if (warp >= 4 && warp < FIRST_SPLIT_WARP) {
+        const int e = warp - 4, q = e & 3, half = e >> 2;
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (S::COLS / 2));
+#pragma unroll
+        for (int c = 0; c < S::COLS / 2; c += 16) tmem_st16_zero(t0 + (uint32_t)c);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const int f_begin = (int)(((long long)p.total * blockIdx.x) / gridDim.x);
+    const int f_end = (int)(((long long)p.total * (blockIdx.x + 1)) / gridDim.x);
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int it = 0, f = f_begin;
+            Segment sg;
+            while (next_segment(f, f_end, p.D, sg)) {
+                const int h0 = (sg.col / p.tiles_w) * S::TILE_H, w0 = (sg.col % p.tiles_w) * S::TILE_W;
+                const int zin_hi = min(sg.z1, p.D - 1);
+                for (int z = max(sg.z0 - 1, 0); z <= zin_hi; ++z) {
+                    const int rot = z % 3;
+                    for (int ks = 0; ks < NKS; ++ks, ++it) {
+                        const int s = it % STAGES;
+                        if (it >= STAGES) mbar_wait(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
+                        unsigned char* stage = smem + (size_t)s * S::STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)(A_BYTES + S::W_BYTES));
+                        const int chunk = 4 * ks;
+                        if (chunk < p.in0_chunks) tma_load_4d(stage, &map0, &full[s], 4 * (w0 - 1), h0 - 1, z, chunk);
+                        else                      tma_load_4d(stage, &map1, &full[s], 4 * (w0 - 1), h0 - 1, z, chunk - p.in0_chunks);
+                        bulk_load(stage + A_BYTES, p.weight_ring + (size_t)(rot * NKS + ks) * (S::W_BYTES / 4), (uint32_t)S::W_BYTES, &full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const bool leader = elect_one();
+        int it = 0, f = f_begin;
+        int n_full[2] = {0, 0};
+        Segment sg;
+        while (next_segment(f, f_end, p.D, sg)) {
+            for (int z = max(sg.z0 - 1, 0); z <= sg.z1; ++z) {
+                const bool real = z < p.D;                       // z == D: nothing to add, only the last plane to hand over
+                const bool completes = (z - 1) >= sg.z0;         // output plane z-1 is finished after this input plane
+                // active output planes and their ring slots
+                const int o_lo = max(z - 1, sg.z0), o_hi = min(z + 1, sg.z1 - 1);
+                uint32_t mask = 0;
+                for (int o = o_lo; o <= o_hi; ++o) mask |= 1u << (o % 3);
+                // maximal runs of adjacent slots: (first, count) x up to 2 (only slots {0,2} need two)
+                const int n_runs = (mask == 5u) ? 2 : 1;
+                const int run0_first = (mask & 1u) ? 0 : (mask & 2u) ? 1 : 2;
+                const int run0_n = (mask == 5u) ? 1 : __popc(mask);
+                if (!real) {
+                    for (int half = 0; half < 2; ++half) {
+                        if (n_full[half] > 0) mbar_wait(&acc_empty[half], (uint32_t)((n_full[half] - 1) & 1));
+                        if (leader) umma_commit(&acc_full[half]);
+                        ++n_full[half];
+                    }
+                    __syncwarp();
+                    continue;
+                }
+                for (int ks = 0; ks < NKS; ++ks, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&ready[s], (uint32_t)((it / STAGES) & 1));
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + (size_t)s * S::STAGE_BYTES);
+                    const uint64_t a_hi_desc = make_desc(a_hi, 2 * S::KGROUP_BYTES, HALO_W * 16);
+                    const uint64_t a_lo_desc = make_desc(a_hi + S::KGROUP_BYTES, 2 * S::KGROUP_BYTES, HALO_W * 16);
+                    const uint64_t w_hi_desc = make_desc(a_hi + A_BYTES, N3 * 16, 128);
+                    const uint64_t w_lo_desc = make_desc(a_hi + A_BYTES + S::W_PART_BYTES, N3 * 16, 128);
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        if (ks == 0 && n_full[half] > 0) {
+                            // the slot that starts a new output plane now was handed to the epilogue one plane ago
+                            mbar_wait(&acc_empty[half], (uint32_t)((n_full[half] - 1) & 1));
+                            tc_fence_after();
+                        }
+                        if (leader) {
+#pragma unroll 1
+                            for (int r = 0; r < n_runs; ++r) {
+                                const int first = (r == 0) ? run0_first : 2, count = (r == 0) ? run0_n : 1;
+                                const uint32_t idesc = make_idesc(0u, count * COUT);
+                                const uint32_t acc0 = tmem_base + (uint32_t)(half * 2 * N3 + first * COUT);
+                                const uint64_t w_off = (uint64_t)(first * COUT);                 // rows = 16-byte units
+                                const uint64_t a_base = (uint64_t)(half * 16);                   // 2 M tiles x 8 voxels
+#pragma unroll
+                                for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                                    for (int m2 = 0; m2 < 2; ++m2) {
+                                        const uint64_t a_off = a_base + (uint64_t)((tap / 3) * HALO_W + 8 * m2 + (tap % 3));
+                                        const uint64_t b_off = w_off + (uint64_t)(tap * (S::W_TAP_BYTES >> 4));
+                                        const uint32_t acc = acc0 + (uint32_t)(m2 * N3);
+                                        umma<KIND_F16>(acc, a_hi_desc + a_off, w_hi_desc + b_off, idesc, 1u);
+                                        umma<KIND_F16>(acc, a_hi_desc + a_off, w_lo_desc + b_off, idesc, 1u);
+                                        umma<KIND_F16>(acc, a_lo_desc + a_off, w_hi_desc + b_off, idesc, 1u);
+                                    }
+                                }
+                            }
+                            if (ks == NKS - 1 && completes) umma_commit(&acc_full[half]);
+                        }
+                        if (ks == NKS - 1 && completes) ++n_full[half];
+                        __syncwarp();
+                    }
+                    if (leader) umma_commit(&empty[s]);
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= FIRST_SPLIT_WARP) {
+        // ===================== hi/lo splitter =====================
+        const int t = tid - FIRST_SPLIT_WARP * 32;
+        int it = 0, f = f_begin;
+        float amax = 0.0f;
+        Segment sg;
+        while (next_segment(f, f_end, p.D, sg)) {
+            const int n_planes = min(sg.z1, p.D - 1) - max(sg.z0 - 1, 0) + 1;
+            for (int st = 0; st < n_planes * NKS; ++st, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+                unsigned char* area = smem + (size_t)s * S::STAGE_BYTES;
+                for (int i = t; i < 2 * HALO_VOX; i += SPLIT_THREADS) {
+                    const int pair = i / HALO_VOX, v = i - pair * HALO_VOX;
+                    float4* c0 = reinterpret_cast<float4*>(area + (size_t)pair * 2 * S::KGROUP_BYTES) + v;   // channels 8p..8p+3
+                    float4* c1 = c0 + HALO_VOX;                                                                // channels 8p+4..8p+7
+                    const float4 a = *c0, b = *c1;
+                    amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                                             fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+                    const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+                    const __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+                    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+                    const __half2 l0 = __floats2half2_rn(a.x - f0.x, a.y - f0.y), l1 = __floats2half2_rn(a.z - f1.x, a.w - f1.y);
+                    const __half2 l2 = __floats2half2_rn(b.x - f2.x, b.y - f2.y), l3 = __floats2half2_rn(b.z - f3.x, b.w - f3.y);
+                    uint4 hv, lv;
+                    hv.x = h2u(h0); hv.y = h2u(h1); hv.z = h2u(h2); hv.w = h2u(h3);
+                    lv.x = h2u(l0); lv.y = h2u(l1); lv.z = h2u(l2); lv.w = h2u(l3);
+                    *reinterpret_cast<uint4*>(c0) = hv;          // x_hi K-group of this pair
+                    *reinterpret_cast<uint4*>(c1) = lv;          // x_lo K-group of this pair
+                }
+                fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async proxy
+                mbar_arrive(&ready[s]);
+            }
+        }
+        const bool bad = !(amax <= 65504.0f);        // Inf included; NaN propagates through fp16 as NaN, like the reference
+        if (bad && p.status) atomicOr(p.status, 1);
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int e = warp - 4, q = e & 3, m2 = e >> 2;          // TMEM lane quarter; which M tile of the half tile
+        const int m = q * 32 + lane;                             // row of the M tile = voxel (h = m / 8, w = m % 8)
+        const int mh = m >> 3, mw = m & 7;
+        double gs[2] = {0.0, 0.0}, gq[2] = {0.0, 0.0};
+        const size_t vox = (size_t)p.D * p.H * p.W;
+        const ConvEpilogue& ep = p.ep;
+        int n_seen[2] = {0, 0};
+        int f = f_begin;
+        Segment sg;
+        while (next_segment(f, f_end, p.D, sg)) {
+            const int h0 = (sg.col / p.tiles_w) * S::TILE_H, w0 = (sg.col % p.tiles_w) * S::TILE_W;
+            const int h = h0 + mh;
+            for (int z = sg.z0; z < sg.z1; ++z) {
+                const int slot = z % 3;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    const int mt = 2 * half + m2;
+                    const int w = w0 + 8 * mt + mw;
+                    const bool ok = (h < p.H) && (w < p.W);
+                    const size_t pos = ((size_t)z * p.H + h) * p.W + w;
+                    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N3 + slot * COUT);
+                    // residuals of the first 16 channels are requested before the wait so that they are in flight meanwhile
+                    float4 r0[4], r1[4];
+                    auto load_res = [&](int c0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int ch = (c0 >> 2) + j;
+                            const bool valid = ok && ch < ep.out_chunks;
+                            const size_t off = ((size_t)ch * vox + pos) * 4;
+                            r0[j] = (ep.res0 && valid) ? ldg4(ep.res0 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            r1[j] = (ep.res1 && valid) ? ldg4(ep.res1 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    };
+                    load_res(0);
+                    mbar_wait(&acc_full[half], (uint32_t)(n_seen[half] & 1));
+                    ++n_seen[half];
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int c0 = 0; c0 < COUT; c0 += 16) {
+                        float a[16];
+                        tmem_ld16(t0 + (uint32_t)c0, a);
+                        tmem_ld_wait();
+                        tmem_st16_zero(t0 + (uint32_t)c0);
+                        float ts[2] = {0.f, 0.f}, tq[2] = {0.f, 0.f};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int c = c0 + 4 * j;
+                            const int ch = c >> 2;
+                            if (!ok || ch >= ep.out_chunks) continue;
+                            const int act = (c < ep.act_split) ? ep.act_lo : ep.act_hi;
+                            const int grp = (c < ep.act_split) ? 0 : 1;
+                            const float4 sc = ldg4(ep.scale + c), sh = ldg4(ep.shift + c);
+                            float v[4];
+                            v[0] = apply_act(fmaf(a[4 * j + 0], sc.x, sh.x), act) + r0[j].x;
+                            v[1] = apply_act(fmaf(a[4 * j + 1], sc.y, sh.y), act) + r0[j].y;
+                            v[2] = apply_act(fmaf(a[4 * j + 2], sc.z, sh.z), act) + r0[j].z;
+                            v[3] = apply_act(fmaf(a[4 * j + 3], sc.w, sh.w), act) + r0[j].w;
+                            v[0] += r1[j].x; v[1] += r1[j].y; v[2] += r1[j].z; v[3] += r1[j].w;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                v[k] *= ep.post_scale;
+                                ts[grp] += v[k];
+                                tq[grp] = fmaf(v[k], v[k], tq[grp]);
+                            }
+                            const size_t off = ((size_t)ch * vox + pos) * 4;
+                            float* dst = (ch < ep.out0_chunks) ? ep.out0 + off : ep.out1 + (off - (size_t)ep.out0_chunks * vox * 4);
+                            st4(dst, make_float4(v[0], v[1], v[2], v[3]));
+                        }
+                        gs[0] += (double)ts[0]; gq[0] += (double)tq[0];
+                        gs[1] += (double)ts[1]; gq[1] += (double)tq[1];
+                        if (c0 + 16 < COUT) load_res(c0 + 16);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[half]);
+                }
+            }
+        }
+        if (ep.gn_partials) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                gs[0] += __shfl_xor_sync(0xffffffffu, gs[0], o); gq[0] += __shfl_xor_sync(0xffffffffu, gq[0], o);
+                gs[1] += __shfl_xor_sync(0xffffffffu, gs[1], o); gq[1] += __shfl_xor_sync(0xffffffffu, gq[1], o);
+            }
+            if (lane == 0) { s_red[e][0] = gs[0]; s_red[e][1] = gq[0]; s_red[e][2] = gs[1]; s_red[e][3] = gq[1]; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps only
+            if (e == 0 && lane == 0) {
+                double* dst = ep.gn_partials + (size_t)blockIdx.x * 4;
+                for (int j = 0; j < 4; ++j) {
+                    double acc = s_red[0][j];
+                    for (int k = 1; k < EPI_WARPS; ++k) acc += s_red[k][j];
+                    dst[j] = acc;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+template <class S>
+static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas) {
+    const int tiles_h = (d->H + S::TILE_H - 1) / S::TILE_H, tiles_w = (d->W + S::TILE_W - 1) / S::TILE_W;
+    const long long total = (long long)tiles_h * tiles_w * d->D;
+    ESTD_REQUIRE(total < (1ll << 30), "estd_conv3d(ring): volume too large");
+    const int grid = total < sm_count() ? (int)total : sm_count();
+    *n_ctas = grid;
+    if (count_only) return ESTD_OK;
+    ESTD_REQUIRE(d->weight_tc && aligned16(d->weight_tc), "estd_conv3d(ring): needs a 16-byte aligned ring weight packing in weight_tc");
+    ESTD_REQUIRE(d->in1_chunks == 0 || (d->in0_chunks % 4) == 0, "estd_conv3d(ring): first input segment must hold a multiple of 4 chunks");
+    CUtensorMap map0, map1;
+    int rc = make_vol4_tensor_map(&map0, d->in0, d->in0_chunks, d->D, d->H, d->W, S::HALO_W * 4, S::HALO_H, 1, 4);
+    if (rc) return rc;
+    if (d->in1_chunks > 0) rc = make_vol4_tensor_map(&map1, d->in1, d->in1_chunks, d->D, d->H, d->W, S::HALO_W * 4, S::HALO_H, 1, 4);
+    else map1 = map0;
+    if (rc) return rc;
+    Params p;
+    p.weight_ring = d->weight_tc;
+    p.status = d->status;
+    fill_epilogue(&p.ep, d);
+    p.in0_chunks = d->in0_chunks;
+    p.D = d->D; p.H = d->H; p.W = d->W;
+    p.tiles_h = tiles_h; p.tiles_w = tiles_w; p.total = (int)total;
+    auto kern = conv3d_ring_kernel<S>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM);
+        if (e != cudaSuccess) return fail(ESTD_ECUDA, "estd_conv3d(ring): cannot reserve %zu B of shared memory: %s", S::SMEM, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    kern<<<grid, THREADS, S::SMEM, stream>>>(map0, map1, p);
+    return check_launch("estd_conv3d(ring)");
+}
+
+}  // namespace ring
+
+int dispatch_ring(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas) {
+    using namespace ring;
+    const int cin_chunks = d->in0_chunks + d->in1_chunks;
+    const int nks = (cin_chunks + 3) / 4;                         // 16 channels per stage
+    ESTD_REQUIRE(!d->planar && (d->dilation == 0 || d->dilation == 1), "estd_conv3d(ring): 3x3x3, dilation 1 only");
+#define ESTD_RING(NKS, COUT) if (nks == NKS && d->cout_pad == COUT) return launch<Shape<NKS, COUT>>(d, stream, count_only, n_ctas)
+    ESTD_RING(2, 32); ESTD_RING(3, 32);
+#undef ESTD_RING
+    return fail(ESTD_EUNSUPPORTED, "estd_conv3d(ring): no kernel for %d input chunks -> cout_pad %d", cin_chunks, d->cout_pad);
+}
+
+}  // namespace estd

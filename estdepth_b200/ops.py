@@ -19,9 +19,11 @@ from . import _lib
 from ._lib import ConvDesc, check
 
 ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2}
-PRECISION = {"fp32": 0, "3xtf32": 1, "3xf16": 2}
+PRECISION = {"fp32": 0, "3xtf32": 1, "3xf16": 2, "3xf16r": 3}
 MAX_SOURCES = 8
-# default arithmetic of conv3d: "fp32" = exact CUDA-core kernel, "3xtf32" / "3xf16" = error-compensated splits on tcgen05
+# default arithmetic of conv3d: "fp32" = exact CUDA-core kernel, "3xtf32" / "3xf16" = error-compensated splits on tcgen05,
+# "3xf16r" = the 3xf16 arithmetic on the plane-ring schedule (conv3d_ring.cu) for the layers it is specialised for, the
+# output-stationary 3xf16 kernel for the rest
 DEFAULT_PRECISION = "fp32"
 
 
@@ -139,13 +141,14 @@ def warp_cost(ref_mix, src_mix, homo12, depth_values, out=None, align_corners=Fa
 class PackedConv(object):
     """Folded, packed parameters of one 3x3x3 layer (see packing.pack_conv3d)."""
     __slots__ = ("weight", "scale", "shift", "cin_chunks", "cout_pad", "out_chunks", "act_split", "act_lo", "act_hi",
-                 "cin", "cout", "weight_tc", "cout_pad_tc", "weight_f16", "scale_f16")
+                 "cin", "cout", "weight_tc", "cout_pad_tc", "weight_f16", "scale_f16", "weight_ring")
 
     def __init__(self, weight, scale, shift, cin_chunks, cout_pad, out_chunks, act_split, act_lo, act_hi,
                  cin=None, cout=None, weight_tc=None, cout_pad_tc=None):
         self.weight, self.scale, self.shift = weight, scale, shift
         self.weight_tc, self.cout_pad_tc = weight_tc, cout_pad_tc      # tcgen05 packings (packing.attach_tc)
         self.weight_f16, self.scale_f16 = None, None
+        self.weight_ring = None                                        # plane-ring packing (packing.pack_weight_ring)
         self.cin = cin if cin is not None else 4 * cin_chunks          # real (un-padded) channel counts, for flop accounting
         self.cout = cout if cout is not None else min(cout_pad, 4 * out_chunks)
         self.cin_chunks, self.cout_pad, self.out_chunks = cin_chunks, cout_pad, out_chunks
@@ -156,6 +159,8 @@ def _precision(pc, precision):
     precision = DEFAULT_PRECISION if precision is None else precision
     if precision not in PRECISION:
         raise RuntimeError("conv3d: unknown precision %r" % (precision,))
+    if precision == "3xf16r" and pc.weight_ring is None:
+        precision = "3xf16"            # same arithmetic, output-stationary schedule: no ring specialisation for this shape
     if (precision == "3xtf32" and pc.weight_tc is None) or (precision == "3xf16" and pc.weight_f16 is None):
         raise RuntimeError("conv3d: layer was packed without tensor-core weights (packing.attach_tc)")
     return precision
@@ -192,10 +197,11 @@ def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, pr
         raise RuntimeError("conv3d: layer packed for %d input chunks, got %d" % (pc.cin_chunks, d.in0_chunks + d.in1_chunks))
     tc = precision != "fp32"
     d.weight = _ptr(pc.weight)
-    d.weight_tc = _ptr(pc.weight_f16 if precision == "3xf16" else pc.weight_tc)
-    d.scale, d.shift = _ptr(pc.scale_f16 if precision == "3xf16" else pc.scale), _ptr(pc.shift)
+    f16 = precision in ("3xf16", "3xf16r")
+    d.weight_tc = _ptr(pc.weight_ring if precision == "3xf16r" else pc.weight_f16 if precision == "3xf16" else pc.weight_tc)
+    d.scale, d.shift = _ptr(pc.scale_f16 if f16 else pc.scale), _ptr(pc.shift)
     d.cout_pad = pc.cout_pad_tc if tc else pc.cout_pad
-    d.status = _ptr(status_flag(in0.device), torch.int32) if precision == "3xf16" else None
+    d.status = _ptr(status_flag(in0.device), torch.int32) if f16 else None
     d.act_split, d.act_lo, d.act_hi = pc.act_split, pc.act_lo, pc.act_hi
     d.res0, d.res1 = _ptr(res0), _ptr(res1)
     d.post_scale = float(post_scale)

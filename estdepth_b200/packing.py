@@ -109,6 +109,41 @@ def pack_weight_f16(packed, cout_pad_tc=None):
     return both.view(torch.float32), k
 
 
+RING_COUT = (32,)            # cout_pad values the plane-ring kernel (conv3d_ring.cu) is specialised for
+RING_NKS = (2, 3)
+
+
+def pack_weight_ring(packed, cout_pad_tc=None):
+    """SIMT packing [27][cin_pad][cout_pad] -> plane-ring packing of conv3d_ring.cu,
+    [3 rotations][nks][9 taps][hi,lo][2 K-groups][3*C rows][8 x fp16] (returned as a float32-typed byte buffer) + the
+    power-of-two exponent of ``pack_weight_f16``.
+
+    Row ``slot*C + c`` of rotation ``r`` holds depth tap ``kd = (r - slot + 1) mod 3``: while input plane z (r = z mod 3)
+    is stationary, ring slot ``j`` accumulates output plane ``z + 1 - kd`` == j (mod 3).
+    """
+    taps, cin_pad, cout_pad = packed.shape
+    assert taps == 27
+    C = tc_cout_pad(cout_pad) if cout_pad_tc is None else cout_pad_tc
+    nks = (cin_pad + 15) // 16
+    w = torch.zeros(27, 16 * nks, C, dtype=torch.float32, device=packed.device)
+    w[:, :cin_pad, :cout_pad] = packed
+    wmax = float(w.abs().max())
+    k = 0 if wmax == 0.0 else max(-14, min(24, int(torch.floor(torch.log2(torch.tensor(1023.0 / wmax))))))
+    ws = w * (2.0 ** k)
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.to(torch.float32)).to(torch.float16)
+
+    def arrange(x):      # [kd*9+tap9][ks*16+kg*8+e][C] -> [kd][ks][tap9][kg][C][e]
+        return x.reshape(3, 9, nks, 2, 8, C).permute(0, 2, 1, 3, 5, 4)
+
+    parts = torch.stack([arrange(hi), arrange(lo)], dim=3)                    # [kd][ks][tap9][prod][kg][C][e]
+    rots = []
+    for r in range(3):
+        slots = [parts[(r - j + 1) % 3] for j in range(3)]                    # each [ks][tap9][prod][kg][C][e]
+        rots.append(torch.cat(slots, dim=4))                                  # [ks][tap9][prod][kg][3C][e]
+    return torch.stack(rots, dim=0).contiguous().view(torch.float32), k
+
+
 def attach_tc(pc):
     """Adds the tensor-core packings (3xTF32 and fp16-split) to a PackedConv and pads its affine arrays."""
     pc.cout_pad_tc = tc_cout_pad(pc.cout_pad)
@@ -119,6 +154,9 @@ def attach_tc(pc):
         if v.numel() < AFFINE_PAD:
             setattr(pc, name, torch.cat([v, torch.zeros(AFFINE_PAD - v.numel(), dtype=v.dtype, device=v.device)]).contiguous())
     pc.scale_f16 = (pc.scale * (2.0 ** -k)).contiguous()
+    if pc.weight.shape[0] == 27 and pc.cout_pad_tc in RING_COUT and (pc.weight.shape[1] + 15) // 16 in RING_NKS:
+        pc.weight_ring, k_ring = pack_weight_ring(pc.weight, pc.cout_pad_tc)
+        assert k_ring == k
     return pc
 
 

@@ -127,7 +127,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16", "3xf16r"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 @pytest.mark.parametrize("shape", [(5, 21, 40), (8, 32, 64)], ids=["ragged", "aligned"])
 def test_conv3d_vs_torch_cpu(case, shape, precision):
@@ -185,7 +185,7 @@ def test_conv3d_vs_torch_cpu(case, shape, precision):
         assert abs(tot[1, 1].item() - (g1 ** 2).sum().item()) < 1e-4 * (g1 ** 2).sum().item()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16", "3xf16r"])
 def test_conv3d_is_bitwise_deterministic(precision):
     g = torch.Generator().manual_seed(5)
     D, H, W = 6, 24, 64
@@ -201,6 +201,45 @@ def test_conv3d_is_bitwise_deterministic(precision):
         outs.append(y.cpu())
         parts.append(p.cpu())
     assert torch.equal(outs[0], outs[1]) and torch.equal(parts[0], parts[1])
+
+
+@pytest.mark.parametrize("case", ["32to32", "36to32"])
+@pytest.mark.parametrize("shape", [(48, 64, 128), (13, 40, 70), (3, 120, 160), (1, 33, 65)],
+                         ids=["long_segments", "ragged", "three_planes", "one_plane"])
+def test_conv3d_ring_matches_exact_kernel(case, shape):
+    """The plane-ring schedule (conv3d_ring.cu) against the exact fp32 CUDA-core kernel on volumes large enough that a
+    CTA's range spans several planes and crosses column boundaries (partial first/last planes, ring wrap-around, the
+    hand-over of the last plane of a column), with residuals, two input segments and two output tensors."""
+    D, H, W = shape
+    g = torch.Generator().manual_seed(D * 1000 + H)
+    cin_seg = (8,) if case == "32to32" else (8, 1)
+    cin = 4 * sum(cin_seg)
+    x = torch.randn(sum(cin_seg), D, H, W, 4, generator=g).to(DEV)
+    w = torch.randn(32, cin, 3, 3, 3, generator=g) / (cin * 27) ** 0.5
+    scale = (torch.rand(32, generator=g) + 0.5).to(DEV)
+    shift = (torch.randn(32, generator=g) / 3).to(DEV)
+    pc = packing.attach_tc(ops.PackedConv(packing.pack_weight(w, list(range(cin)), list(range(32))).to(DEV), scale, shift,
+                                          sum(cin_seg), 32, 8, 16, "tanh", "relu"))
+    assert pc.weight_ring is not None
+    res0 = torch.randn(8, D, H, W, 4, generator=g).to(DEV)
+    ins = [x[:8].contiguous()] + ([x[8:].contiguous()] if len(cin_seg) > 1 else [])
+    got, want = {}, {}
+    for precision, store in (("fp32", want), ("3xf16r", got)):
+        o0 = torch.full((4, D, H, W, 4), float("nan"), device=DEV)
+        o1 = torch.full((4, D, H, W, 4), float("nan"), device=DEV)
+        n = ops.conv3d_num_ctas(pc, D, H, W, precision=precision)
+        part = torch.zeros(n, 2, 2, device=DEV, dtype=torch.float64)
+        ops.conv3d(pc, ins[0], o0, in1=ins[1] if len(ins) > 1 else None, out1=o1, res0=res0, post_scale=0.5,
+                   gn_partials=part, precision=precision)
+        store["y"], store["p"] = torch.cat([o0, o1], 0), part.sum(0)
+    assert torch.isfinite(got["y"]).all()
+    err = (got["y"] - want["y"]).abs().max().item()
+    print("conv3d ring %s %s: max |err| vs exact = %.3e" % (case, shape, err))
+    # 3 products x 54 (tap, k-step) pairs accumulate in ONE fp32 TMEM accumulator and the tensor core truncates on every
+    # accumulate: ~162 x 0.5 ulp of an O(1) sum (the output-stationary kernel keeps the small products apart: 4e-6)
+    assert err < 4e-5
+    assert torch.allclose(got["p"], want["p"], rtol=1e-5, atol=1e-3)
+    ops.check_status(torch.device(DEV))
 
 
 @pytest.mark.parametrize("j", [0, 2])

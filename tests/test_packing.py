@@ -80,3 +80,62 @@ def test_vol4_helpers_roundtrip():
     v = to_vol4(x)
     assert v.shape == (4, 2, 3, 5, 4) and v[1, 0, 0, 0, 2] == x[6, 0, 0, 0]
     assert torch.equal(from_vol4(v), x)
+
+
+def _simulate_ring(x, ring, k, nks, C, D, grid):
+    """Host model of conv3d_ring.cu's schedule for a 1-column volume: x [16*nks, D, H, W]; ring = pack_weight_ring output.
+    Walks the flat plane list in `grid` contiguous ranges exactly as the kernel does (segments, partial first/last
+    planes, slot masks and runs, hand-over after each plane, zeroing) and returns the [C, D, H, W] result."""
+    import torch.nn.functional as F
+    _, _, H, W = x.shape
+    w16 = ring.view(torch.float16).reshape(3, nks, 9, 2, 2, 3 * C, 8).to(torch.float64)
+    wsum = (w16[:, :, :, 0] + w16[:, :, :, 1]) * 2.0 ** -k            # hi + lo: [rot][ks][tap][kg][3C][8]
+    out = torch.full((C, D, H, W), float("nan"), dtype=torch.float64)
+    xs = x.to(torch.float64)
+    total = D
+    for b in range(grid):
+        f0, f1 = total * b // grid, total * (b + 1) // grid
+        if f1 <= f0:
+            continue
+        z0, z1 = f0, f1                                               # one column: the range is one segment
+        acc = torch.zeros(3, C, H, W, dtype=torch.float64)
+        for z in range(max(z0 - 1, 0), z1 + 1):
+            completes = (z - 1) >= z0
+            if z < D:
+                o_lo, o_hi = max(z - 1, z0), min(z + 1, z1 - 1)
+                mask = 0
+                for o in range(o_lo, o_hi + 1):
+                    mask |= 1 << (o % 3)
+                runs = [(0, 1), (2, 1)] if mask == 5 else [((0 if mask & 1 else 1 if mask & 2 else 2), bin(mask).count("1"))]
+                rot = z % 3
+                for first, cnt in runs:
+                    rows = slice(first * C, (first + cnt) * C)
+                    # [ks][tap][kg][rows][8] -> conv2d weight [rows, 16*nks, 3, 3]
+                    wt = wsum[rot][:, :, :, rows]                     # [ks][tap][kg][n][8]
+                    wt = wt.permute(3, 0, 2, 4, 1).reshape(cnt * C, 16 * nks, 3, 3)
+                    y = F.conv2d(xs[:, z].unsqueeze(0), wt, padding=1)[0]
+                    acc[first:first + cnt] += y.reshape(cnt, C, H, W)
+            if completes:
+                slot = (z - 1) % 3
+                out[:, z - 1] = acc[slot]
+                acc[slot] = 0
+        assert float(acc.abs().max()) == 0.0, "a ring slot was written but never handed over"
+    return out
+
+
+def test_ring_packing_and_schedule_reproduce_conv3d():
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    for cin, D, grids in ((32, 7, (1, 2, 3, 7)), (36, 4, (1, 4)), (32, 1, (1,)), (32, 2, (1, 2))):
+        w = torch.randn(32, cin, 3, 3, 3, generator=g) / 10
+        packed = packing.pack_weight(w, list(range(cin)), list(range(32)))
+        ring, k = packing.pack_weight_ring(packed, 32)
+        nks = (cin + 15) // 16
+        assert tuple(ring.shape) == (3, nks, 9, 2, 2, 96, 4)
+        x = torch.zeros(16 * nks, D, 5, 6)
+        x[:cin] = torch.randn(cin, D, 5, 6, generator=g)
+        want = F.conv3d(x[:cin].unsqueeze(0).double(), w.double(), padding=1)[0]
+        for grid in grids:
+            got = _simulate_ring(x, ring, k, nks, 32, D, grid)
+            assert torch.isfinite(got).all()
+            assert (got - want).abs().max().item() < 1e-5, (cin, D, grid)
