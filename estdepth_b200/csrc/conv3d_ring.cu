@@ -3,20 +3,25 @@
 // that the depth taps ride in the N dimension of the MMA.
 //
 // Why: with N = Cout = 32 the output-stationary kernel reads a 4 KB A operand from shared memory for every 32 accumulator
-// columns and is bound by shared-memory bandwidth (tensor pipe 35 % busy, profiles/README.md).  Here the INPUT plane is
-// stationary: one halo tile of input plane z is loaded and split once and multiplied against the weights of all three
-// depth taps at once, N = 3*Cout -- the three column blocks are the accumulators of output planes z+1, z, z-1.  Per
-// product that is one third of the A reads, one third of the TMA traffic and one third of the split work.
+// columns, and its back-to-back MMAs hit the same accumulator (profiles/README.md).  Here the INPUT plane is stationary:
+// one halo tile of input plane z is loaded and split once and multiplied against the weights of all three depth taps at
+// once, N = 3*Cout -- the three column blocks are the accumulators of output planes z-1, z, z+1.  Per product that is
+// one third of the A reads, one third of the TMA traffic and one third of the split work.
 //
-//   unit      a column of 16 x 32 voxels walked along depth; accumulators of the three output planes in flight live in a
-//             ring of 3 TMEM slots (slot = z mod 3) per M tile: 4 M tiles x 3 slots x Cout columns.
-//   weights   the slot <-> depth-tap assignment rotates with z mod 3, and B rows map 1:1 onto D columns, so the packed
-//             weights come in the 3 rotations; the stage of input plane z streams rotation z mod 3 (55 KB per 16 channels).
-//   MMA       per in-plane tap and M tile: A_hi x W_hi, A_hi x W_lo, A_lo x W_hi, each M = 128, N = 3*Cout, K = 16, all
-//             accumulating (slots are zeroed by the epilogue after it has read them, so there is no "first" MMA).
-//   epilogue  the column is two half tiles (M tiles 0,1 | 2,3).  After the MMAs of plane z, output plane z-1 is complete:
-//             the issuer commits half A, then issues half B; the 8 epilogue warps drain + zero half A's slot while the
-//             tensor core works on half B, and vice versa -- no second accumulator buffer needed.
+//   unit      a column of 16 x 32 voxels (4 M tiles) walked along depth.  The accumulators of the output planes in flight
+//             live in a ring of 4 TMEM slots per M tile (slot = z mod 4; 4 M tiles x 4 slots x Cout = 512 columns): three
+//             slots receive the current input plane, the fourth is being drained by the epilogue.
+//   weights   the slot <-> depth-tap assignment rotates with z mod 4, and B rows map 1:1 onto D columns, so the packed
+//             weights come in 4 rotations, each holding the rows of its 3 active slots in slot order; the stage of input
+//             plane z streams rotation z mod 4 (55 KB per 16 channels).  When the active slots wrap around the ring
+//             ({3,0,1}, {2,3,0}) the plane is issued as two runs of adjacent slots (N = 2*Cout and N = Cout).
+//   MMA       per in-plane tap and M tile: A_hi x W_hi, A_hi x W_lo, A_lo x W_hi, each M = 128, K = 16, all accumulating
+//             (slots are zeroed by the epilogue after it has read them, so there is no "first" MMA).  Issue order is
+//             tap > product > M tile, so consecutive MMAs hit 4 different accumulators (a dependent MMA waits for its
+//             predecessor's write-back: ~100 cycles for these 48-cycle instructions).
+//   epilogue  after the MMAs of plane z, output plane z-1 is complete; its slot is not written again before input plane
+//             z+2, so the 8 epilogue warps have a whole plane of MMA time to drain and zero it (two alternating pairs of
+//             full/empty barriers; the issuer only waits for the hand-over before last).
 //   balance   the flat list of (column, plane) pairs is cut into one contiguous range per CTA; a range that starts or
 //             ends inside a column pays one partial extra input plane (a single depth tap, N = Cout) on that side.
 #include <cuda.h>
@@ -42,13 +47,14 @@ struct Shape {
     static constexpr int HALO_H = TILE_H + 2, HALO_W = TILE_W + 2, HALO_VOX = HALO_H * HALO_W;
     static constexpr int KGROUP_BYTES = HALO_VOX * 16;            // one 16-byte K-group (8 x fp16) of the halo tile
     static constexpr int A_BYTES = 4 * KGROUP_BYTES;              // 16 channels: lands as 4 fp32 chunks, becomes hi|lo|hi|lo
-    static constexpr int N3 = 3 * COUT;                           // columns of one M tile: 3 ring slots
+    static constexpr int N3 = 3 * COUT;                           // weight rows of one rotation: the 3 active slots
+    static constexpr int SLOTS = 4, NACC = SLOTS * COUT;          // accumulator columns of one M tile: 4 ring slots
     static constexpr int W_PART_BYTES = 2 * N3 * 16;              // [2 K-groups][N3 rows][16 B] of w_hi (or w_lo)
     static constexpr int W_TAP_BYTES = 2 * W_PART_BYTES;          // w_hi block, then w_lo block
     static constexpr int W_BYTES = 9 * W_TAP_BYTES;
     static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES + 127) / 128 * 128;
     static constexpr int STAGES = 2;
-    static constexpr int COLS = MT * N3;
+    static constexpr int COLS = MT * NACC;
     static constexpr int TMEM_COLS = (COLS <= 128) ? 128 : (COLS <= 256) ? 256 : 512;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;
     static_assert(COLS <= 512, "ring accumulators must fit TMEM");
@@ -63,7 +69,7 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 struct Params {
-    const float* weight_ring;                   // [3 rotations][NKS][9 taps][hi,lo][2 K-groups][3*COUT rows][16 bytes]
+    const float* weight_ring;                   // [4 rotations][NKS][9 taps][hi,lo][2 K-groups][3*COUT rows][16 bytes]
     int* status;
     ConvEpilogue ep;
     int in0_chunks;
@@ -94,8 +100,8 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     uint64_t* full = bars;                  // [STAGES] TMA landed
     uint64_t* ready = bars + STAGES;        // [STAGES] split done
     uint64_t* empty = bars + 2 * STAGES;    // [STAGES] MMAs done reading
-    uint64_t* acc_full = bars + 3 * STAGES; // [2 halves] an output plane of this half tile is complete
-    uint64_t* acc_empty = acc_full + 2;     // [2 halves] its slot has been read and zeroed
+    uint64_t* acc_full = bars + 3 * STAGES; // [2] hand-over k uses pair k & 1: output plane complete in its slot
+    uint64_t* acc_empty = acc_full + 2;     // [2] ... and that slot has been read and zeroed
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
     __shared__ double s_red[EPI_WARPS][4];
 
@@ -136,10 +142,10 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                 const int h0 = (sg.col / p.tiles_w) * S::TILE_H, w0 = (sg.col % p.tiles_w) * S::TILE_W;
                 const int zin_hi = min(sg.z1, p.D - 1);
                 for (int z = max(sg.z0 - 1, 0); z <= zin_hi; ++z) {
-                    const int rot = z % 3;
+                    const int rot = z & 3;
                     for (int ks = 0; ks < NKS; ++ks, ++it) {
                         const int s = it % STAGES;
-                        if (it >= STAGES) mbar_wait(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
+                        if (it >= STAGES) mbar_wait_polls(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
                         unsigned char* stage = smem + (size_t)s * S::STAGE_BYTES;
                         mbar_arrive_expect_tx(&full[s], (uint32_t)(A_BYTES + S::W_BYTES));
                         const int chunk = 4 * ks;
@@ -154,74 +160,77 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
         // ===================== MMA issuer =====================
         const bool leader = elect_one();
         int it = 0, f = f_begin;
-        int n_full[2] = {0, 0};
+        int n_sig = 0;                                           // hand-overs issued so far
         Segment sg;
+        // hand-over j has been drained (its slot read and zeroed)
+        auto wait_drained = [&](int j) { mbar_wait_polls(&acc_empty[j & 1], (uint32_t)((j >> 1) & 1)); };
         while (next_segment(f, f_end, p.D, sg)) {
+            // a new column may start in any slot: everything handed over so far must be drained
+            if (n_sig >= 1) { wait_drained(n_sig - 1); tc_fence_after(); }
             for (int z = max(sg.z0 - 1, 0); z <= sg.z1; ++z) {
                 const bool real = z < p.D;                       // z == D: nothing to add, only the last plane to hand over
                 const bool completes = (z - 1) >= sg.z0;         // output plane z-1 is finished after this input plane
-                // active output planes and their ring slots
-                const int o_lo = max(z - 1, sg.z0), o_hi = min(z + 1, sg.z1 - 1);
-                uint32_t mask = 0;
-                for (int o = o_lo; o <= o_hi; ++o) mask |= 1u << (o % 3);
-                // maximal runs of adjacent slots: (first, count) x up to 2 (only slots {0,2} need two)
-                const int n_runs = (mask == 5u) ? 2 : 1;
-                const int run0_first = (mask & 1u) ? 0 : (mask & 2u) ? 1 : 2;
-                const int run0_n = (mask == 5u) ? 1 : __popc(mask);
+                // The slot of output plane z+1 was last used by plane z-3, handed over two hand-overs ago; it is also
+                // what keeps at most one hand-over pending per barrier pair.
+                if (n_sig >= 2) { wait_drained(n_sig - 2); tc_fence_after(); }
                 if (!real) {
-                    for (int half = 0; half < 2; ++half) {
-                        if (n_full[half] > 0) mbar_wait(&acc_empty[half], (uint32_t)((n_full[half] - 1) & 1));
-                        if (leader) umma_commit(&acc_full[half]);
-                        ++n_full[half];
-                    }
+                    if (leader) umma_commit(&acc_full[n_sig & 1]);
+                    ++n_sig;
                     __syncwarp();
                     continue;
                 }
+                // active output planes -> ring slots; runs of adjacent slots (at most 2); the weight rows of rotation
+                // z mod 4 hold its three slots {all but (z+2) mod 4} in slot order
+                const int o_lo = max(z - 1, sg.z0), o_hi = min(z + 1, sg.z1 - 1);
+                uint32_t mask = 0;
+                for (int o = o_lo; o <= o_hi; ++o) mask |= 1u << (o & 3);
+                const int idle = (z + 2) & 3;
+                int run_first0 = 0, run_n0 = 0, run_first1 = 0, run_n1 = 0;
+                for (int sl = 0; sl < 4; ++sl) {
+                    if (!((mask >> sl) & 1u)) continue;
+                    if (run_n0 == 0) { run_first0 = sl; run_n0 = 1; }
+                    else if (run_n1 == 0 && run_first0 + run_n0 == sl) ++run_n0;
+                    else if (run_n1 == 0) { run_first1 = sl; run_n1 = 1; }
+                    else ++run_n1;
+                }
+                const int n_runs = run_n1 > 0 ? 2 : 1;
                 for (int ks = 0; ks < NKS; ++ks, ++it) {
                     const int s = it % STAGES;
-                    mbar_wait(&ready[s], (uint32_t)((it / STAGES) & 1));
+                    mbar_wait_polls(&ready[s], (uint32_t)((it / STAGES) & 1));
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * S::STAGE_BYTES);
                     const uint64_t a_hi_desc = make_desc(a_hi, 2 * S::KGROUP_BYTES, HALO_W * 16);
                     const uint64_t a_lo_desc = make_desc(a_hi + S::KGROUP_BYTES, 2 * S::KGROUP_BYTES, HALO_W * 16);
                     const uint64_t w_hi_desc = make_desc(a_hi + A_BYTES, N3 * 16, 128);
                     const uint64_t w_lo_desc = make_desc(a_hi + A_BYTES + S::W_PART_BYTES, N3 * 16, 128);
+                    if (leader) {
 #pragma unroll 1
-                    for (int half = 0; half < 2; ++half) {
-                        if (ks == 0 && n_full[half] > 0) {
-                            // the slot that starts a new output plane now was handed to the epilogue one plane ago
-                            mbar_wait(&acc_empty[half], (uint32_t)((n_full[half] - 1) & 1));
-                            tc_fence_after();
-                        }
-                        if (leader) {
-#pragma unroll 1
-                            for (int r = 0; r < n_runs; ++r) {
-                                const int first = (r == 0) ? run0_first : 2, count = (r == 0) ? run0_n : 1;
-                                const uint32_t idesc = make_idesc(0u, count * COUT);
-                                const uint32_t acc0 = tmem_base + (uint32_t)(half * 2 * N3 + first * COUT);
-                                const uint64_t w_off = (uint64_t)(first * COUT);                 // rows = 16-byte units
-                                const uint64_t a_base = (uint64_t)(half * 16);                   // 2 M tiles x 8 voxels
+                        for (int r = 0; r < n_runs; ++r) {
+                            const int first = (r == 0) ? run_first0 : run_first1, count = (r == 0) ? run_n0 : run_n1;
+                            const int row0 = (first - (first > idle ? 1 : 0)) * COUT;       // rank of the slot among the stored three
+                            const uint32_t idesc = make_idesc(0u, count * COUT);
+                            const uint32_t acc0 = tmem_base + (uint32_t)(first * COUT);
+                            const uint64_t wh = w_hi_desc + (uint64_t)row0, wl = w_lo_desc + (uint64_t)row0;   // rows = 16-byte units
 #pragma unroll
-                                for (int tap = 0; tap < 9; ++tap) {
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint64_t b_off = (uint64_t)(tap * (S::W_TAP_BYTES >> 4));
 #pragma unroll
-                                    for (int m2 = 0; m2 < 2; ++m2) {
-                                        const uint64_t a_off = a_base + (uint64_t)((tap / 3) * HALO_W + 8 * m2 + (tap % 3));
-                                        const uint64_t b_off = w_off + (uint64_t)(tap * (S::W_TAP_BYTES >> 4));
-                                        const uint32_t acc = acc0 + (uint32_t)(m2 * N3);
-                                        umma<KIND_F16>(acc, a_hi_desc + a_off, w_hi_desc + b_off, idesc, 1u);
-                                        umma<KIND_F16>(acc, a_hi_desc + a_off, w_lo_desc + b_off, idesc, 1u);
-                                        umma<KIND_F16>(acc, a_lo_desc + a_off, w_hi_desc + b_off, idesc, 1u);
+                                for (int prod = 0; prod < 3; ++prod) {
+#pragma unroll
+                                    for (int mt = 0; mt < S::MT; ++mt) {
+                                        const uint64_t a_off = (uint64_t)((tap / 3) * HALO_W + 8 * mt + (tap % 3));
+                                        const uint32_t acc = acc0 + (uint32_t)(mt * S::NACC);
+                                        umma<KIND_F16>(acc, (prod == 2 ? a_lo_desc : a_hi_desc) + a_off, (prod == 1 ? wl : wh) + b_off, idesc, 1u);
                                     }
                                 }
                             }
-                            if (ks == NKS - 1 && completes) umma_commit(&acc_full[half]);
                         }
-                        if (ks == NKS - 1 && completes) ++n_full[half];
-                        __syncwarp();
+                        umma_commit(&empty[s]);                          // stage s may be refilled once these MMAs retire
+                        if (ks == NKS - 1 && completes) umma_commit(&acc_full[n_sig & 1]);
                     }
-                    if (leader) umma_commit(&empty[s]);
                     __syncwarp();
                 }
+                if (completes) ++n_sig;
             }
         }
     } else if (warp >= FIRST_SPLIT_WARP) {
@@ -234,7 +243,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
             const int n_planes = min(sg.z1, p.D - 1) - max(sg.z0 - 1, 0) + 1;
             for (int st = 0; st < n_planes * NKS; ++st, ++it) {
                 const int s = it % STAGES;
-                mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+                mbar_wait_polls(&full[s], (uint32_t)((it / STAGES) & 1));
                 unsigned char* area = smem + (size_t)s * S::STAGE_BYTES;
                 for (int i = t; i < 2 * HALO_VOX; i += SPLIT_THREADS) {
                     const int pair = i / HALO_VOX, v = i - pair * HALO_VOX;
@@ -262,28 +271,30 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
         if (bad && p.status) atomicOr(p.status, 1);
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int e = warp - 4, q = e & 3, m2 = e >> 2;          // TMEM lane quarter; which M tile of the half tile
+        const int e = warp - 4, q = e & 3, pair = e >> 2;        // TMEM lane quarter; M tiles 2*pair, 2*pair+1
         const int m = q * 32 + lane;                             // row of the M tile = voxel (h = m / 8, w = m % 8)
         const int mh = m >> 3, mw = m & 7;
         double gs[2] = {0.0, 0.0}, gq[2] = {0.0, 0.0};
         const size_t vox = (size_t)p.D * p.H * p.W;
         const ConvEpilogue& ep = p.ep;
-        int n_seen[2] = {0, 0};
+        const bool want_gn = ep.gn_partials != nullptr;
+        int n_seen = 0;
         int f = f_begin;
         Segment sg;
         while (next_segment(f, f_end, p.D, sg)) {
             const int h0 = (sg.col / p.tiles_w) * S::TILE_H, w0 = (sg.col % p.tiles_w) * S::TILE_W;
             const int h = h0 + mh;
-            for (int z = sg.z0; z < sg.z1; ++z) {
-                const int slot = z % 3;
+            for (int z = sg.z0; z < sg.z1; ++z, ++n_seen) {
+                const int slot = z & 3;
+                bool waited = false;
 #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    const int mt = 2 * half + m2;
+                for (int m2 = 0; m2 < 2; ++m2) {
+                    const int mt = 2 * pair + m2;
                     const int w = w0 + 8 * mt + mw;
                     const bool ok = (h < p.H) && (w < p.W);
                     const size_t pos = ((size_t)z * p.H + h) * p.W + w;
-                    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N3 + slot * COUT);
-                    // residuals of the first 16 channels are requested before the wait so that they are in flight meanwhile
+                    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * S::NACC + slot * COUT);
+                    // residuals of the next 16 channels are requested early so that they are in flight during the wait / the math
                     float4 r0[4], r1[4];
                     auto load_res = [&](int c0) {
 #pragma unroll
@@ -296,9 +307,11 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                         }
                     };
                     load_res(0);
-                    mbar_wait(&acc_full[half], (uint32_t)(n_seen[half] & 1));
-                    ++n_seen[half];
-                    tc_fence_after();
+                    if (!waited) {
+                        mbar_wait_polls(&acc_full[n_seen & 1], (uint32_t)((n_seen >> 1) & 1));
+                        tc_fence_after();
+                        waited = true;
+                    }
 #pragma unroll 1
                     for (int c0 = 0; c0 < COUT; c0 += 16) {
                         float a[16];
@@ -315,29 +328,39 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                             const int grp = (c < ep.act_split) ? 0 : 1;
                             const float4 sc = ldg4(ep.scale + c), sh = ldg4(ep.shift + c);
                             float v[4];
-                            v[0] = apply_act(fmaf(a[4 * j + 0], sc.x, sh.x), act) + r0[j].x;
-                            v[1] = apply_act(fmaf(a[4 * j + 1], sc.y, sh.y), act) + r0[j].y;
-                            v[2] = apply_act(fmaf(a[4 * j + 2], sc.z, sh.z), act) + r0[j].z;
-                            v[3] = apply_act(fmaf(a[4 * j + 3], sc.w, sh.w), act) + r0[j].w;
+                            v[0] = fmaf(a[4 * j + 0], sc.x, sh.x); v[1] = fmaf(a[4 * j + 1], sc.y, sh.y);
+                            v[2] = fmaf(a[4 * j + 2], sc.z, sh.z); v[3] = fmaf(a[4 * j + 3], sc.w, sh.w);
+                            if (act == ESTD_ACT_RELU) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) v[k] = fmaxf(v[k], 0.0f);
+                            } else if (act == ESTD_ACT_TANH) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) v[k] = tanhf(v[k]);
+                            }
+                            v[0] += r0[j].x; v[1] += r0[j].y; v[2] += r0[j].z; v[3] += r0[j].w;
                             v[0] += r1[j].x; v[1] += r1[j].y; v[2] += r1[j].z; v[3] += r1[j].w;
+                            float s4 = 0.f, q4 = 0.f;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 v[k] *= ep.post_scale;
-                                ts[grp] += v[k];
-                                tq[grp] = fmaf(v[k], v[k], tq[grp]);
+                                s4 += v[k];
+                                q4 = fmaf(v[k], v[k], q4);
                             }
+                            if (grp == 0) { ts[0] += s4; tq[0] += q4; } else { ts[1] += s4; tq[1] += q4; }
                             const size_t off = ((size_t)ch * vox + pos) * 4;
                             float* dst = (ch < ep.out0_chunks) ? ep.out0 + off : ep.out1 + (off - (size_t)ep.out0_chunks * vox * 4);
                             st4(dst, make_float4(v[0], v[1], v[2], v[3]));
                         }
-                        gs[0] += (double)ts[0]; gq[0] += (double)tq[0];
-                        gs[1] += (double)ts[1]; gq[1] += (double)tq[1];
+                        if (want_gn) {
+                            gs[0] += (double)ts[0]; gq[0] += (double)tq[0];
+                            gs[1] += (double)ts[1]; gq[1] += (double)tq[1];
+                        }
                         if (c0 + 16 < COUT) load_res(c0 + 16);
                     }
-                    tmem_st_wait();
-                    tc_fence_before();
-                    mbar_arrive(&acc_empty[half]);
                 }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&acc_empty[n_seen & 1]);
             }
         }
         if (ep.gn_partials) {
