@@ -33,12 +33,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
-// Same bound without reading the clock in the loop (the spinning roles of the ring kernel poll from 16 warps at once and
-// CS2R competes for the XU pipe): try_wait suspends for a hardware-chosen time slice, 2^27 slices is seconds.
+// Same bound without reading the clock in the loop, with a pause between polls: every poll is a shared-memory wavefront
+// and the ring kernel's waiting warps were taking a fifth of the shared-memory pipe from the tensor core's operand fetch
+// (profiles/README.md).  Roles with several warps let ONE warp poll and release the others through a named barrier.
 __device__ __forceinline__ void mbar_wait_polls(uint64_t* bar, uint32_t parity) {
     for (uint32_t i = 0; !mbar_try_wait(bar, parity); ++i) {
-        if (i > (1u << 27)) __trap();
+        __nanosleep(40);
+        if (i > (1u << 24)) __trap();
     }
+}
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(

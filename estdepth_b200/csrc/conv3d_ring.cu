@@ -3,25 +3,24 @@
 // that the depth taps ride in the N dimension of the MMA.
 //
 // Why: with N = Cout = 32 the output-stationary kernel reads a 4 KB A operand from shared memory for every 32 accumulator
-// columns, and its back-to-back MMAs hit the same accumulator (profiles/README.md).  Here the INPUT plane is stationary:
-// one halo tile of input plane z is loaded and split once and multiplied against the weights of all three depth taps at
-// once, N = 3*Cout -- the three column blocks are the accumulators of output planes z-1, z, z+1.  Per product that is
-// one third of the A reads, one third of the TMA traffic and one third of the split work.
+// columns: the tensor core waits for operands (profiles/README.md).  Here the INPUT plane is stationary: one halo tile
+// of input plane z is loaded and split once and multiplied against the weights of all three depth taps at once,
+// N = 3*Cout -- the three column blocks are the accumulators of output planes z-1, z, z+1.  Per product that is one
+// third of the A reads, one third of the TMA traffic and one third of the split work.  What remains is the operand
+// fetch of an M=128 x N=96 x K=16 MMA (4 KB of A + 3 KB of B = 56 shared-memory wavefronts against 48 cycles of math).
 //
-//   unit      a column of 16 x 32 voxels (4 M tiles) walked along depth.  The accumulators of the output planes in flight
-//             live in a ring of 4 TMEM slots per M tile (slot = z mod 4; 4 M tiles x 4 slots x Cout = 512 columns): three
-//             slots receive the current input plane, the fourth is being drained by the epilogue.
-//   weights   the slot <-> depth-tap assignment rotates with z mod 4, and B rows map 1:1 onto D columns, so the packed
-//             weights come in 4 rotations, each holding the rows of its 3 active slots in slot order; the stage of input
-//             plane z streams rotation z mod 4 (55 KB per 16 channels).  When the active slots wrap around the ring
-//             ({3,0,1}, {2,3,0}) the plane is issued as two runs of adjacent slots (N = 2*Cout and N = Cout).
-//   MMA       per in-plane tap and M tile: A_hi x W_hi, A_hi x W_lo, A_lo x W_hi, each M = 128, K = 16, all accumulating
-//             (slots are zeroed by the epilogue after it has read them, so there is no "first" MMA).  Issue order is
-//             tap > product > M tile, so consecutive MMAs hit 4 different accumulators (a dependent MMA waits for its
-//             predecessor's write-back: ~100 cycles for these 48-cycle instructions).
-//   epilogue  after the MMAs of plane z, output plane z-1 is complete; its slot is not written again before input plane
-//             z+2, so the 8 epilogue warps have a whole plane of MMA time to drain and zero it (two alternating pairs of
-//             full/empty barriers; the issuer only waits for the hand-over before last).
+//   unit      a column of 16 x 32 voxels (4 M tiles) walked along depth.  The accumulators of the three output planes
+//             in flight live in a ring of 3 TMEM slots per M tile (slot = z mod 3; 4 x 3 x Cout columns).
+//   weights   the slot <-> depth-tap assignment rotates with z mod 3, and B rows map 1:1 onto D columns, so the packed
+//             weights come in the 3 rotations; the stage of input plane z streams rotation z mod 3 (55 KB per 16 channels).
+//   MMA       per in-plane tap and M tile: A_hi x W_hi, A_hi x W_lo, A_lo x W_hi, each M = 128, N = 3*Cout, K = 16, all
+//             accumulating (slots are zeroed by the epilogue after it has read them, so there is no "first" MMA).
+//   epilogue  the column is two half tiles (M tiles 0,1 | 2,3).  After the MMAs of plane z, output plane z-1 is complete
+//             and its slot is needed again by plane z+1 (for z+2).  The issuer commits half A, then issues half B; the
+//             epilogue warps drain and zero half A's slot while the tensor core works on half B, and vice versa.
+//             Within a half the issue order is tap > product > M tile so that consecutive MMAs alternate accumulators.
+//             (A 4-slot ring gives the epilogue a whole plane of slack and 4-way interleaving, but two planes in four
+//             then wrap around the ring and must be issued as N = 64 + N = 32: measured 207 us against this schedule.)
 //   balance   the flat list of (column, plane) pairs is cut into one contiguous range per CTA; a range that starts or
 //             ends inside a column pays one partial extra input plane (a single depth tap, N = Cout) on that side.
 #include <cuda.h>
@@ -47,19 +46,18 @@ struct Shape {
     static constexpr int HALO_H = TILE_H + 2, HALO_W = TILE_W + 2, HALO_VOX = HALO_H * HALO_W;
     static constexpr int KGROUP_BYTES = HALO_VOX * 16;            // one 16-byte K-group (8 x fp16) of the halo tile
     static constexpr int A_BYTES = 4 * KGROUP_BYTES;              // 16 channels: lands as 4 fp32 chunks, becomes hi|lo|hi|lo
-    static constexpr int N3 = 3 * COUT;                           // weight rows of one rotation: the 3 active slots
-    static constexpr int SLOTS = 4, NACC = SLOTS * COUT;          // accumulator columns of one M tile: 4 ring slots
+    static constexpr int N3 = 3 * COUT;                           // weight rows of one rotation = accumulator columns of one M tile
     static constexpr int W_PART_BYTES = 2 * N3 * 16;              // [2 K-groups][N3 rows][16 B] of w_hi (or w_lo)
     static constexpr int W_TAP_BYTES = 2 * W_PART_BYTES;          // w_hi block, then w_lo block
     static constexpr int W_BYTES = 9 * W_TAP_BYTES;
     static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES + 127) / 128 * 128;
-    static constexpr int STAGES = 2;
-    static constexpr int COLS = MT * NACC;
+    static constexpr int STAGES = (3 * STAGE_BYTES + 2048 <= 227 * 1024) ? 3 : 2;
+    static constexpr int COLS = MT * N3;
     static constexpr int TMEM_COLS = (COLS <= 128) ? 128 : (COLS <= 256) ? 256 : 512;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;
     static_assert(COLS <= 512, "ring accumulators must fit TMEM");
-    static_assert(SMEM <= 227 * 1024, "stages must fit shared memory");
-    static_assert(COUT % 16 == 0 && N3 <= 256, "bad N");
+    static_assert(SMEM + 2048 <= 227 * 1024, "stages must fit shared memory");
+    static_assert(COUT % 16 == 0 && COUT <= 32 && N3 <= 256, "bad N");
 };
 
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
@@ -68,8 +66,18 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+#ifdef ESTD_RING_TIMING
+// experiment only (make EXTRA=-DESTD_RING_TIMING): cycles the MMA issuer spent waiting, per CTA: {ready, acc_empty, total, stages}
+__device__ long long g_ring_timing[148 * 4];
+#define RING_T0() const long long t_dbg0 = clock64()
+#define RING_T1(slot) t_dbg[slot] += clock64() - t_dbg0
+#else
+#define RING_T0()
+#define RING_T1(slot)
+#endif
+
 struct Params {
-    const float* weight_ring;                   // [4 rotations][NKS][9 taps][hi,lo][2 K-groups][3*COUT rows][16 bytes]
+    const float* weight_ring;                   // [3 rotations][NKS][9 taps][hi,lo][2 K-groups][3*COUT rows][16 bytes]
     int* status;
     ConvEpilogue ep;
     int in0_chunks;
@@ -100,10 +108,11 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     uint64_t* full = bars;                  // [STAGES] TMA landed
     uint64_t* ready = bars + STAGES;        // [STAGES] split done
     uint64_t* empty = bars + 2 * STAGES;    // [STAGES] MMAs done reading
-    uint64_t* acc_full = bars + 3 * STAGES; // [2] hand-over k uses pair k & 1: output plane complete in its slot
-    uint64_t* acc_empty = acc_full + 2;     // [2] ... and that slot has been read and zeroed
+    uint64_t* acc_full = bars + 3 * STAGES; // [2 halves] an output plane of this half tile is complete
+    uint64_t* acc_empty = acc_full + 2;     // [2 halves] its slot has been read and zeroed
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
     __shared__ double s_red[EPI_WARPS][4];
+    __shared__ __align__(16) float s_scale[COUT], s_shift[COUT];     // the epilogue reads them for every voxel
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -113,6 +122,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_base_smem, S::TMEM_COLS);
+    if (warp == 3 && lane < COUT) { s_scale[lane] = p.ep.scale[lane]; s_shift[lane] = p.ep.shift[lane]; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -120,8 +130,8 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
 
     // every ring slot starts at zero: all MMAs accumulate
     if (warp >= 4 && warp < FIRST_SPLIT_WARP) {
-        const int e = warp - 4, q = e & 3, half = e >> 2;
-        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (S::COLS / 2));
+        const int e = warp - 4, q = e & 3, part = e >> 2;
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * (S::COLS / 2));
 #pragma unroll
         for (int c = 0; c < S::COLS / 2; c += 16) tmem_st16_zero(t0 + (uint32_t)c);
         tmem_st_wait();
@@ -142,7 +152,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                 const int h0 = (sg.col / p.tiles_w) * S::TILE_H, w0 = (sg.col % p.tiles_w) * S::TILE_W;
                 const int zin_hi = min(sg.z1, p.D - 1);
                 for (int z = max(sg.z0 - 1, 0); z <= zin_hi; ++z) {
-                    const int rot = z & 3;
+                    const int rot = z % 3;
                     for (int ks = 0; ks < NKS; ++ks, ++it) {
                         const int s = it % STAGES;
                         if (it >= STAGES) mbar_wait_polls(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
@@ -160,79 +170,87 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
         // ===================== MMA issuer =====================
         const bool leader = elect_one();
         int it = 0, f = f_begin;
-        int n_sig = 0;                                           // hand-overs issued so far
+        int n_sig = 0;                                           // hand-overs issued so far (the same for both halves)
         Segment sg;
-        // hand-over j has been drained (its slot read and zeroed)
-        auto wait_drained = [&](int j) { mbar_wait_polls(&acc_empty[j & 1], (uint32_t)((j >> 1) & 1)); };
+#ifdef ESTD_RING_TIMING
+        long long t_dbg[2] = {0, 0};
+        const long long t_dbg_start = clock64();
+#endif
         while (next_segment(f, f_end, p.D, sg)) {
-            // a new column may start in any slot: everything handed over so far must be drained
-            if (n_sig >= 1) { wait_drained(n_sig - 1); tc_fence_after(); }
             for (int z = max(sg.z0 - 1, 0); z <= sg.z1; ++z) {
                 const bool real = z < p.D;                       // z == D: nothing to add, only the last plane to hand over
                 const bool completes = (z - 1) >= sg.z0;         // output plane z-1 is finished after this input plane
-                // The slot of output plane z+1 was last used by plane z-3, handed over two hand-overs ago; it is also
-                // what keeps at most one hand-over pending per barrier pair.
-                if (n_sig >= 2) { wait_drained(n_sig - 2); tc_fence_after(); }
+                const uint32_t drained = (uint32_t)((n_sig - 1) & 1);   // parity of the previous hand-over's drain
                 if (!real) {
-                    if (leader) umma_commit(&acc_full[n_sig & 1]);
+                    for (int half = 0; half < 2; ++half) {
+                        if (n_sig > 0) mbar_wait_polls(&acc_empty[half], drained);
+                        if (leader) umma_commit(&acc_full[half]);
+                    }
                     ++n_sig;
                     __syncwarp();
                     continue;
                 }
-                // active output planes -> ring slots; runs of adjacent slots (at most 2); the weight rows of rotation
-                // z mod 4 hold its three slots {all but (z+2) mod 4} in slot order
+                // active output planes -> ring slots -> runs of adjacent slots (only {0,2} needs two)
                 const int o_lo = max(z - 1, sg.z0), o_hi = min(z + 1, sg.z1 - 1);
                 uint32_t mask = 0;
-                for (int o = o_lo; o <= o_hi; ++o) mask |= 1u << (o & 3);
-                const int idle = (z + 2) & 3;
-                int run_first0 = 0, run_n0 = 0, run_first1 = 0, run_n1 = 0;
-                for (int sl = 0; sl < 4; ++sl) {
-                    if (!((mask >> sl) & 1u)) continue;
-                    if (run_n0 == 0) { run_first0 = sl; run_n0 = 1; }
-                    else if (run_n1 == 0 && run_first0 + run_n0 == sl) ++run_n0;
-                    else if (run_n1 == 0) { run_first1 = sl; run_n1 = 1; }
-                    else ++run_n1;
-                }
-                const int n_runs = run_n1 > 0 ? 2 : 1;
+                for (int o = o_lo; o <= o_hi; ++o) mask |= 1u << (o % 3);
+                const int n_runs = (mask == 5u) ? 2 : 1;
+                const int run0_first = (mask & 1u) ? 0 : (mask & 2u) ? 1 : 2;
+                const int run0_n = (mask == 5u) ? 1 : __popc(mask);
                 for (int ks = 0; ks < NKS; ++ks, ++it) {
                     const int s = it % STAGES;
-                    mbar_wait_polls(&ready[s], (uint32_t)((it / STAGES) & 1));
+                    { RING_T0(); mbar_wait_polls(&ready[s], (uint32_t)((it / STAGES) & 1)); RING_T1(0); }
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * S::STAGE_BYTES);
                     const uint64_t a_hi_desc = make_desc(a_hi, 2 * S::KGROUP_BYTES, HALO_W * 16);
                     const uint64_t a_lo_desc = make_desc(a_hi + S::KGROUP_BYTES, 2 * S::KGROUP_BYTES, HALO_W * 16);
                     const uint64_t w_hi_desc = make_desc(a_hi + A_BYTES, N3 * 16, 128);
                     const uint64_t w_lo_desc = make_desc(a_hi + A_BYTES + S::W_PART_BYTES, N3 * 16, 128);
-                    if (leader) {
 #pragma unroll 1
-                        for (int r = 0; r < n_runs; ++r) {
-                            const int first = (r == 0) ? run_first0 : run_first1, count = (r == 0) ? run_n0 : run_n1;
-                            const int row0 = (first - (first > idle ? 1 : 0)) * COUT;       // rank of the slot among the stored three
-                            const uint32_t idesc = make_idesc(0u, count * COUT);
-                            const uint32_t acc0 = tmem_base + (uint32_t)(first * COUT);
-                            const uint64_t wh = w_hi_desc + (uint64_t)row0, wl = w_lo_desc + (uint64_t)row0;   // rows = 16-byte units
+                    for (int half = 0; half < 2; ++half) {
+                        if (ks == 0 && n_sig > 0) {
+                            // the slot that starts a new output plane now was handed to the epilogue one plane ago
+                            { RING_T0(); mbar_wait_polls(&acc_empty[half], drained); RING_T1(1); }
+                            tc_fence_after();
+                        }
+                        if (leader) {
+#pragma unroll 1
+                            for (int r = 0; r < n_runs; ++r) {
+                                const int first = (r == 0) ? run0_first : 2, count = (r == 0) ? run0_n : 1;
+                                const uint32_t idesc = make_idesc(0u, count * COUT);
+                                const uint32_t acc0 = tmem_base + (uint32_t)(half * 2 * N3 + first * COUT);
+                                const uint64_t wh = w_hi_desc + (uint64_t)(first * COUT), wl = w_lo_desc + (uint64_t)(first * COUT);   // rows = 16-byte units
+                                const uint64_t a_base = (uint64_t)(half * 16);                   // 2 M tiles x 8 voxels
 #pragma unroll
-                            for (int tap = 0; tap < 9; ++tap) {
-                                const uint64_t b_off = (uint64_t)(tap * (S::W_TAP_BYTES >> 4));
+                                for (int tap = 0; tap < 9; ++tap) {
+                                    const uint64_t b_off = (uint64_t)(tap * (S::W_TAP_BYTES >> 4));
 #pragma unroll
-                                for (int prod = 0; prod < 3; ++prod) {
+                                    for (int prod = 0; prod < 3; ++prod) {
 #pragma unroll
-                                    for (int mt = 0; mt < S::MT; ++mt) {
-                                        const uint64_t a_off = (uint64_t)((tap / 3) * HALO_W + 8 * mt + (tap % 3));
-                                        const uint32_t acc = acc0 + (uint32_t)(mt * S::NACC);
-                                        umma<KIND_F16>(acc, (prod == 2 ? a_lo_desc : a_hi_desc) + a_off, (prod == 1 ? wl : wh) + b_off, idesc, 1u);
+                                        for (int m2 = 0; m2 < 2; ++m2) {
+                                            const uint64_t a_off = a_base + (uint64_t)((tap / 3) * HALO_W + 8 * m2 + (tap % 3));
+                                            const uint32_t acc = acc0 + (uint32_t)(m2 * N3);
+                                            umma<KIND_F16>(acc, (prod == 2 ? a_lo_desc : a_hi_desc) + a_off, (prod == 1 ? wl : wh) + b_off, idesc, 1u);
+                                        }
                                     }
                                 }
                             }
+                            if (ks == NKS - 1 && completes) umma_commit(&acc_full[half]);
                         }
-                        umma_commit(&empty[s]);                          // stage s may be refilled once these MMAs retire
-                        if (ks == NKS - 1 && completes) umma_commit(&acc_full[n_sig & 1]);
+                        __syncwarp();
                     }
+                    if (leader) umma_commit(&empty[s]);                  // stage s may be refilled once these MMAs retire
                     __syncwarp();
                 }
                 if (completes) ++n_sig;
             }
         }
+#ifdef ESTD_RING_TIMING
+        if (leader && blockIdx.x < 148) {
+            g_ring_timing[blockIdx.x * 4 + 0] = t_dbg[0]; g_ring_timing[blockIdx.x * 4 + 1] = t_dbg[1];
+            g_ring_timing[blockIdx.x * 4 + 2] = clock64() - t_dbg_start; g_ring_timing[blockIdx.x * 4 + 3] = it;
+        }
+#endif
     } else if (warp >= FIRST_SPLIT_WARP) {
         // ===================== hi/lo splitter =====================
         const int t = tid - FIRST_SPLIT_WARP * 32;
@@ -243,7 +261,8 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
             const int n_planes = min(sg.z1, p.D - 1) - max(sg.z0 - 1, 0) + 1;
             for (int st = 0; st < n_planes * NKS; ++st, ++it) {
                 const int s = it % STAGES;
-                mbar_wait_polls(&full[s], (uint32_t)((it / STAGES) & 1));
+                if (warp == FIRST_SPLIT_WARP) mbar_wait_polls(&full[s], (uint32_t)((it / STAGES) & 1));
+                named_barrier(2, SPLIT_THREADS);                 // one warp polls, the barrier releases the other seven
                 unsigned char* area = smem + (size_t)s * S::STAGE_BYTES;
                 for (int i = t; i < 2 * HALO_VOX; i += SPLIT_THREADS) {
                     const int pair = i / HALO_VOX, v = i - pair * HALO_VOX;
@@ -271,7 +290,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
         if (bad && p.status) atomicOr(p.status, 1);
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int e = warp - 4, q = e & 3, pair = e >> 2;        // TMEM lane quarter; M tiles 2*pair, 2*pair+1
+        const int e = warp - 4, q = e & 3, m2 = e >> 2;          // TMEM lane quarter; which M tile of each half tile
         const int m = q * 32 + lane;                             // row of the M tile = voxel (h = m / 8, w = m % 8)
         const int mh = m >> 3, mw = m & 7;
         double gs[2] = {0.0, 0.0}, gq[2] = {0.0, 0.0};
@@ -285,15 +304,14 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
             const int h0 = (sg.col / p.tiles_w) * S::TILE_H, w0 = (sg.col % p.tiles_w) * S::TILE_W;
             const int h = h0 + mh;
             for (int z = sg.z0; z < sg.z1; ++z, ++n_seen) {
-                const int slot = z & 3;
-                bool waited = false;
+                const int slot = z % 3;
 #pragma unroll 1
-                for (int m2 = 0; m2 < 2; ++m2) {
-                    const int mt = 2 * pair + m2;
+                for (int half = 0; half < 2; ++half) {
+                    const int mt = 2 * half + m2;
                     const int w = w0 + 8 * mt + mw;
                     const bool ok = (h < p.H) && (w < p.W);
                     const size_t pos = ((size_t)z * p.H + h) * p.W + w;
-                    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * S::NACC + slot * COUT);
+                    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N3 + slot * COUT);
                     // residuals of the next 16 channels are requested early so that they are in flight during the wait / the math
                     float4 r0[4], r1[4];
                     auto load_res = [&](int c0) {
@@ -307,11 +325,9 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                         }
                     };
                     load_res(0);
-                    if (!waited) {
-                        mbar_wait_polls(&acc_full[n_seen & 1], (uint32_t)((n_seen >> 1) & 1));
-                        tc_fence_after();
-                        waited = true;
-                    }
+                    if (e == 0) mbar_wait_polls(&acc_full[half], (uint32_t)(n_seen & 1));
+                    named_barrier(3, EPI_THREADS);
+                    tc_fence_after();
 #pragma unroll 1
                     for (int c0 = 0; c0 < COUT; c0 += 16) {
                         float a[16];
@@ -326,7 +342,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                             if (!ok || ch >= ep.out_chunks) continue;
                             const int act = (c < ep.act_split) ? ep.act_lo : ep.act_hi;
                             const int grp = (c < ep.act_split) ? 0 : 1;
-                            const float4 sc = ldg4(ep.scale + c), sh = ldg4(ep.shift + c);
+                            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c), sh = *reinterpret_cast<const float4*>(s_shift + c);
                             float v[4];
                             v[0] = fmaf(a[4 * j + 0], sc.x, sh.x); v[1] = fmaf(a[4 * j + 1], sc.y, sh.y);
                             v[2] = fmaf(a[4 * j + 2], sc.z, sh.z); v[3] = fmaf(a[4 * j + 3], sc.w, sh.w);
@@ -357,10 +373,10 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                         }
                         if (c0 + 16 < COUT) load_res(c0 + 16);
                     }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[half]);
                 }
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(&acc_empty[n_seen & 1]);
             }
         }
         if (ep.gn_partials) {
@@ -370,7 +386,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                 gs[1] += __shfl_xor_sync(0xffffffffu, gs[1], o); gq[1] += __shfl_xor_sync(0xffffffffu, gq[1], o);
             }
             if (lane == 0) { s_red[e][0] = gs[0]; s_red[e][1] = gq[0]; s_red[e][2] = gs[1]; s_red[e][3] = gq[1]; }
-            asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps only
+            named_barrier(1, EPI_THREADS);                            // the 8 epilogue warps only
             if (e == 0 && lane == 0) {
                 double* dst = ep.gn_partials + (size_t)blockIdx.x * 4;
                 for (int j = 0; j < 4; ++j) {
@@ -423,13 +439,19 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
 
 }  // namespace ring
 
+#ifdef ESTD_RING_TIMING
+extern "C" __attribute__((visibility("default"))) int estd_ring_timing(long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, ring::g_ring_timing, sizeof(long long) * 148 * 4) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 int dispatch_ring(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas) {
     using namespace ring;
     const int cin_chunks = d->in0_chunks + d->in1_chunks;
     const int nks = (cin_chunks + 3) / 4;                         // 16 channels per stage
     ESTD_REQUIRE(!d->planar && (d->dilation == 0 || d->dilation == 1), "estd_conv3d(ring): 3x3x3, dilation 1 only");
 #define ESTD_RING(NKS, COUT) if (nks == NKS && d->cout_pad == COUT) return launch<Shape<NKS, COUT>>(d, stream, count_only, n_ctas)
-    ESTD_RING(2, 32); ESTD_RING(3, 32);
+    ESTD_RING(2, 32); ESTD_RING(3, 32); ESTD_RING(1, 16); ESTD_RING(2, 16);
 #undef ESTD_RING
     return fail(ESTD_EUNSUPPORTED, "estd_conv3d(ring): no kernel for %d input chunks -> cout_pad %d", cin_chunks, d->cout_pad);
 }

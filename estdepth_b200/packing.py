@@ -109,18 +109,17 @@ def pack_weight_f16(packed, cout_pad_tc=None):
     return both.view(torch.float32), k
 
 
-RING_COUT = (32,)            # cout_pad values the plane-ring kernel (conv3d_ring.cu) is specialised for
-RING_NKS = (2, 3)
+RING_COUT = (16, 32)            # cout_pad values the plane-ring kernel (conv3d_ring.cu) is specialised for
+RING_NKS = (1, 2, 3)
 
 
 def pack_weight_ring(packed, cout_pad_tc=None):
     """SIMT packing [27][cin_pad][cout_pad] -> plane-ring packing of conv3d_ring.cu,
-    [4 rotations][nks][9 taps][hi,lo][2 K-groups][3*C rows][8 x fp16] (returned as a float32-typed byte buffer) + the
+    [3 rotations][nks][9 taps][hi,lo][2 K-groups][3*C rows][8 x fp16] (returned as a float32-typed byte buffer) + the
     power-of-two exponent of ``pack_weight_f16``.
 
-    While input plane z (rotation r = z mod 4) is stationary, ring slot s (s != (r+2) mod 4) accumulates the output
-    plane o == s (mod 4) among {z-1, z, z+1}, i.e. depth tap kd = z + 1 - o.  A rotation stores the rows of its three
-    active slots in ascending slot order (C rows each).
+    Row ``slot*C + c`` of rotation ``r`` holds depth tap ``kd = (r - slot + 1) mod 3``: while input plane z (r = z mod 3)
+    is stationary, ring slot ``j`` accumulates output plane ``z + 1 - kd`` == j (mod 3).
     """
     taps, cin_pad, cout_pad = packed.shape
     assert taps == 27
@@ -139,14 +138,9 @@ def pack_weight_ring(packed, cout_pad_tc=None):
 
     parts = torch.stack([arrange(hi), arrange(lo)], dim=3)                    # [kd][ks][tap9][prod][kg][C][e]
     rots = []
-    for r in range(4):
-        blocks = []
-        for s in range(4):
-            if s == (r + 2) % 4:
-                continue
-            d = (s - r + 1) % 4 - 1                                           # output plane = z + d
-            blocks.append(parts[1 - d])                                       # depth tap kd = 1 - d
-        rots.append(torch.cat(blocks, dim=4))                                 # [ks][tap9][prod][kg][3C][e]
+    for r in range(3):
+        slots = [parts[(r - j + 1) % 3] for j in range(3)]                    # each [ks][tap9][prod][kg][C][e]
+        rots.append(torch.cat(slots, dim=4))                                  # [ks][tap9][prod][kg][3C][e]
     return torch.stack(rots, dim=0).contiguous().view(torch.float32), k
 
 
@@ -160,7 +154,8 @@ def attach_tc(pc):
         if v.numel() < AFFINE_PAD:
             setattr(pc, name, torch.cat([v, torch.zeros(AFFINE_PAD - v.numel(), dtype=v.dtype, device=v.device)]).contiguous())
     pc.scale_f16 = (pc.scale * (2.0 ** -k)).contiguous()
-    if pc.weight.shape[0] == 27 and pc.cout_pad_tc in RING_COUT and (pc.weight.shape[1] + 15) // 16 in RING_NKS:
+    nks = (pc.weight.shape[1] + 15) // 16
+    if pc.weight.shape[0] == 27 and pc.cout_pad_tc in RING_COUT and nks in RING_NKS and (pc.cout_pad_tc, nks) != (16, 3):
         pc.weight_ring, k_ring = pack_weight_ring(pc.weight, pc.cout_pad_tc)
         assert k_ring == k
     return pc

@@ -50,8 +50,8 @@ extern "C" {
                                        activations must stay within the fp16 range (|x| <= 65504, reported through `status`) */
 #define ESTD_PREC_3XF16_RING 3      /* same arithmetic as ESTD_PREC_3XF16, plane-ring schedule (conv3d_ring.cu): the input plane is
                                        stationary and the three depth taps ride in the MMA's N dimension (N = 3*cout_pad);
-                                       `weight_tc` must hold the ring packing [4 rotations][nks][9][hi,lo][2][3*cout_pad rows][16 B];
-                                       3x3x3 only, cout_pad 32, 8 or 9 input chunks */
+                                       `weight_tc` must hold the ring packing [3 rotations][nks][9][hi,lo][2][3*cout_pad rows][16 B];
+                                       3x3x3 only; (input chunks, cout_pad) in {(8,32), (9,32), (4,16), (8,16)} */
 
 ESTD_API int estd_version(void);
 ESTD_API const char* estd_last_error(void);

@@ -85,11 +85,10 @@ def test_vol4_helpers_roundtrip():
 def _simulate_ring(x, ring, k, nks, C, D, grid):
     """Host model of conv3d_ring.cu's schedule for a 1-column volume: x [16*nks, D, H, W]; ring = pack_weight_ring output.
     Walks the flat plane list in `grid` contiguous ranges exactly as the kernel does (segments, partial first/last
-    planes, 4-slot ring, slot masks -> runs of adjacent slots, row offset = rank among the rotation's stored slots,
-    hand-over after each plane, zeroing, at most one undrained hand-over when a slot is reused) and returns [C, D, H, W]."""
+    planes, slot masks and runs, hand-over after each plane, zeroing) and returns the [C, D, H, W] result."""
     import torch.nn.functional as F
     _, _, H, W = x.shape
-    w16 = ring.view(torch.float16).reshape(4, nks, 9, 2, 2, 3 * C, 8).to(torch.float64)
+    w16 = ring.view(torch.float16).reshape(3, nks, 9, 2, 2, 3 * C, 8).to(torch.float64)
     wsum = (w16[:, :, :, 0] + w16[:, :, :, 1]) * 2.0 ** -k            # hi + lo: [rot][ks][tap][kg][3C][8]
     out = torch.full((C, D, H, W), float("nan"), dtype=torch.float64)
     xs = x.to(torch.float64)
@@ -99,44 +98,27 @@ def _simulate_ring(x, ring, k, nks, C, D, grid):
         if f1 <= f0:
             continue
         z0, z1 = f0, f1                                               # one column: the range is one segment
-        acc = torch.zeros(4, C, H, W, dtype=torch.float64)
-        pending = []                                                  # hand-overs not drained yet: (slot, z_out)
+        acc = torch.zeros(3, C, H, W, dtype=torch.float64)
         for z in range(max(z0 - 1, 0), z1 + 1):
             completes = (z - 1) >= z0
-            while len(pending) > 1:                                   # the issuer waits for the hand-over before last
-                slot, zo = pending.pop(0)
-                out[:, zo] = acc[slot]
-                acc[slot] = 0
             if z < D:
                 o_lo, o_hi = max(z - 1, z0), min(z + 1, z1 - 1)
                 mask = 0
                 for o in range(o_lo, o_hi + 1):
-                    mask |= 1 << (o % 4)
-                idle = (z + 2) % 4
-                assert not (mask >> idle) & 1
-                runs = []
-                for sl in range(4):
-                    if not (mask >> sl) & 1:
-                        continue
-                    if runs and runs[-1][0] + runs[-1][1] == sl:
-                        runs[-1][1] += 1
-                    else:
-                        runs.append([sl, 1])
-                assert len(runs) <= 2
-                rot = z % 4
+                    mask |= 1 << (o % 3)
+                runs = [(0, 1), (2, 1)] if mask == 5 else [((0 if mask & 1 else 1 if mask & 2 else 2), bin(mask).count("1"))]
+                rot = z % 3
                 for first, cnt in runs:
-                    assert all(s not in [pslot for pslot, _ in pending] for s in range(first, first + cnt)), "slot still pending"
-                    row0 = (first - (1 if first > idle else 0)) * C
-                    rows = slice(row0, row0 + cnt * C)
+                    rows = slice(first * C, (first + cnt) * C)
+                    # [ks][tap][kg][rows][8] -> conv2d weight [rows, 16*nks, 3, 3]
                     wt = wsum[rot][:, :, :, rows]                     # [ks][tap][kg][n][8]
                     wt = wt.permute(3, 0, 2, 4, 1).reshape(cnt * C, 16 * nks, 3, 3)
                     y = F.conv2d(xs[:, z].unsqueeze(0), wt, padding=1)[0]
                     acc[first:first + cnt] += y.reshape(cnt, C, H, W)
             if completes:
-                pending.append(((z - 1) % 4, z - 1))
-        for slot, zo in pending:
-            out[:, zo] = acc[slot]
-            acc[slot] = 0
+                slot = (z - 1) % 3
+                out[:, z - 1] = acc[slot]
+                acc[slot] = 0
         assert float(acc.abs().max()) == 0.0, "a ring slot was written but never handed over"
     return out
 
@@ -144,12 +126,12 @@ def _simulate_ring(x, ring, k, nks, C, D, grid):
 def test_ring_packing_and_schedule_reproduce_conv3d():
     import torch.nn.functional as F
     g = torch.Generator().manual_seed(3)
-    for cin, D, grids in ((32, 9, (1, 2, 3, 9)), (36, 5, (1, 5)), (32, 1, (1,)), (32, 2, (1, 2))):
+    for cin, D, grids in ((32, 7, (1, 2, 3, 7)), (36, 4, (1, 4)), (32, 1, (1,)), (32, 2, (1, 2))):
         w = torch.randn(32, cin, 3, 3, 3, generator=g) / 10
         packed = packing.pack_weight(w, list(range(cin)), list(range(32)))
         ring, k = packing.pack_weight_ring(packed, 32)
         nks = (cin + 15) // 16
-        assert tuple(ring.shape) == (4, nks, 9, 2, 2, 96, 4)
+        assert tuple(ring.shape) == (3, nks, 9, 2, 2, 96, 4)
         x = torch.zeros(16 * nks, D, 5, 6)
         x[:cin] = torch.randn(cin, D, 5, 6, generator=g)
         want = F.conv3d(x[:cin].unsqueeze(0).double(), w.double(), padding=1)[0]
