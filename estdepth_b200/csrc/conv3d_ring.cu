@@ -39,9 +39,11 @@ constexpr int EPI_THREADS = EPI_WARPS * 32, SPLIT_THREADS = SPLIT_WARPS * 32;
 constexpr int THREADS = 128 + EPI_THREADS + SPLIT_THREADS;       // warps 0-3 control, 4-11 epilogue, 12-19 splitters
 constexpr int FIRST_SPLIT_WARP = 4 + EPI_WARPS;
 
-template <int NKS_, int COUT_>
+// NKS k-steps of 16 input channels; COUT padded output channels (multiple of 16); MT M tiles (16 x 8 voxels each) per column:
+// 4 unless the 3*COUT*MT accumulator columns would not fit TMEM (COUT = 48 -> 2)
+template <int NKS_, int COUT_, int MT_>
 struct Shape {
-    static constexpr int NKS = NKS_, COUT = COUT_, MT = 4;
+    static constexpr int NKS = NKS_, COUT = COUT_, MT = MT_, MH = MT_ / 2;      // MH: M tiles per half tile
     static constexpr int TILE_H = 16, TILE_W = 8 * MT;
     static constexpr int HALO_H = TILE_H + 2, HALO_W = TILE_W + 2, HALO_VOX = HALO_H * HALO_W;
     static constexpr int KGROUP_BYTES = HALO_VOX * 16;            // one 16-byte K-group (8 x fp16) of the halo tile
@@ -57,7 +59,7 @@ struct Shape {
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;
     static_assert(COLS <= 512, "ring accumulators must fit TMEM");
     static_assert(SMEM + 2048 <= 227 * 1024, "stages must fit shared memory");
-    static_assert(COUT % 16 == 0 && COUT <= 32 && N3 <= 256, "bad N");
+    static_assert(COUT % 16 == 0 && COUT <= 48 && N3 <= 256 && (MT == 2 || MT == 4), "bad shape");
 };
 
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
@@ -118,11 +120,11 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], SPLIT_THREADS); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_THREADS); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128 * S::MH); }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_base_smem, S::TMEM_COLS);
-    if (warp == 3 && lane < COUT) { s_scale[lane] = p.ep.scale[lane]; s_shift[lane] = p.ep.shift[lane]; }
+    if (warp == 3) for (int i = lane; i < COUT; i += 32) { s_scale[i] = p.ep.scale[i]; s_shift[i] = p.ep.shift[i]; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -218,16 +220,16 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                             for (int r = 0; r < n_runs; ++r) {
                                 const int first = (r == 0) ? run0_first : 2, count = (r == 0) ? run0_n : 1;
                                 const uint32_t idesc = make_idesc(0u, count * COUT);
-                                const uint32_t acc0 = tmem_base + (uint32_t)(half * 2 * N3 + first * COUT);
+                                const uint32_t acc0 = tmem_base + (uint32_t)(half * S::MH * N3 + first * COUT);
                                 const uint64_t wh = w_hi_desc + (uint64_t)(first * COUT), wl = w_lo_desc + (uint64_t)(first * COUT);   // rows = 16-byte units
-                                const uint64_t a_base = (uint64_t)(half * 16);                   // 2 M tiles x 8 voxels
+                                const uint64_t a_base = (uint64_t)(half * S::MH * 8);            // MH M tiles x 8 voxels
 #pragma unroll
                                 for (int tap = 0; tap < 9; ++tap) {
                                     const uint64_t b_off = (uint64_t)(tap * (S::W_TAP_BYTES >> 4));
 #pragma unroll
                                     for (int prod = 0; prod < 3; ++prod) {
 #pragma unroll
-                                        for (int m2 = 0; m2 < 2; ++m2) {
+                                        for (int m2 = 0; m2 < S::MH; ++m2) {
                                             const uint64_t a_off = a_base + (uint64_t)((tap / 3) * HALO_W + 8 * m2 + (tap % 3));
                                             const uint32_t acc = acc0 + (uint32_t)(m2 * N3);
                                             umma<KIND_F16>(acc, (prod == 2 ? a_lo_desc : a_hi_desc) + a_off, (prod == 1 ? wl : wh) + b_off, idesc, 1u);
@@ -298,7 +300,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
         const ConvEpilogue& ep = p.ep;
         const bool want_gn = ep.gn_partials != nullptr;
         int n_seen = 0;
-        int f = f_begin;
+        int f = (m2 < S::MH) ? f_begin : f_end;                  // with 2 M tiles per column only the first 4 warps have work
         Segment sg;
         while (next_segment(f, f_end, p.D, sg)) {
             const int h0 = (sg.col / p.tiles_w) * S::TILE_H, w0 = (sg.col % p.tiles_w) * S::TILE_W;
@@ -307,7 +309,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                 const int slot = z % 3;
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
-                    const int mt = 2 * half + m2;
+                    const int mt = S::MH * half + m2;
                     const int w = w0 + 8 * mt + mw;
                     const bool ok = (h < p.H) && (w < p.W);
                     const size_t pos = ((size_t)z * p.H + h) * p.W + w;
@@ -326,7 +328,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                     };
                     load_res(0);
                     if (e == 0) mbar_wait_polls(&acc_full[half], (uint32_t)(n_seen & 1));
-                    named_barrier(3, EPI_THREADS);
+                    named_barrier(3, 128 * S::MH);
                     tc_fence_after();
 #pragma unroll 1
                     for (int c0 = 0; c0 < COUT; c0 += 16) {
@@ -450,8 +452,8 @@ int dispatch_ring(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
     const int cin_chunks = d->in0_chunks + d->in1_chunks;
     const int nks = (cin_chunks + 3) / 4;                         // 16 channels per stage
     ESTD_REQUIRE(!d->planar && (d->dilation == 0 || d->dilation == 1), "estd_conv3d(ring): 3x3x3, dilation 1 only");
-#define ESTD_RING(NKS, COUT) if (nks == NKS && d->cout_pad == COUT) return launch<Shape<NKS, COUT>>(d, stream, count_only, n_ctas)
-    ESTD_RING(2, 32); ESTD_RING(3, 32); ESTD_RING(1, 16); ESTD_RING(2, 16);
+#define ESTD_RING(NKS, COUT, MT) if (nks == NKS && d->cout_pad == COUT) return launch<Shape<NKS, COUT, MT>>(d, stream, count_only, n_ctas)
+    ESTD_RING(2, 32, 4); ESTD_RING(3, 32, 4); ESTD_RING(1, 16, 4); ESTD_RING(2, 16, 4); ESTD_RING(3, 48, 2);
 #undef ESTD_RING
     return fail(ESTD_EUNSUPPORTED, "estd_conv3d(ring): no kernel for %d input chunks -> cout_pad %d", cin_chunks, d->cout_pad);
 }

@@ -109,8 +109,8 @@ def pack_weight_f16(packed, cout_pad_tc=None):
     return both.view(torch.float32), k
 
 
-RING_COUT = (16, 32)            # cout_pad values the plane-ring kernel (conv3d_ring.cu) is specialised for
-RING_NKS = (1, 2, 3)
+# (16-channel k-steps, cout_pad) the plane-ring kernel (conv3d_ring.cu) is specialised for
+RING_SHAPES = ((2, 32), (3, 32), (1, 16), (2, 16), (3, 48))
 
 
 def pack_weight_ring(packed, cout_pad_tc=None):
@@ -155,7 +155,7 @@ def attach_tc(pc):
             setattr(pc, name, torch.cat([v, torch.zeros(AFFINE_PAD - v.numel(), dtype=v.dtype, device=v.device)]).contiguous())
     pc.scale_f16 = (pc.scale * (2.0 ** -k)).contiguous()
     nks = (pc.weight.shape[1] + 15) // 16
-    if pc.weight.shape[0] == 27 and pc.cout_pad_tc in RING_COUT and nks in RING_NKS and (pc.cout_pad_tc, nks) != (16, 3):
+    if pc.weight.shape[0] == 27 and (nks, pc.cout_pad_tc) in RING_SHAPES:
         pc.weight_ring, k_ring = pack_weight_ring(pc.weight, pc.cout_pad_tc)
         assert k_ring == k
     return pc

@@ -51,7 +51,7 @@ extern "C" {
 #define ESTD_PREC_3XF16_RING 3      /* same arithmetic as ESTD_PREC_3XF16, plane-ring schedule (conv3d_ring.cu): the input plane is
                                        stationary and the three depth taps ride in the MMA's N dimension (N = 3*cout_pad);
                                        `weight_tc` must hold the ring packing [3 rotations][nks][9][hi,lo][2][3*cout_pad rows][16 B];
-                                       3x3x3 only; (input chunks, cout_pad) in {(8,32), (9,32), (4,16), (8,16)} */
+                                       3x3x3 only; (input chunks, cout_pad) in {(8,32), (9,32), (4,16), (8,16), (9,48)} */
 
 ESTD_API int estd_version(void);
 ESTD_API const char* estd_last_error(void);

@@ -34,7 +34,7 @@ def timed(fn, n=20):
     return e0.elapsed_time(e1) / n * 1e3
 
 
-for name, cin_chunks, cout_pad, out_chunks in (("32to32", 8, 32, 8), ("36to32", 9, 32, 8), ("16to16", 4, 16, 4), ("32to16", 8, 16, 4)):
+for name, cin_chunks, cout_pad, out_chunks in (("32to32", 8, 32, 8), ("36to32", 9, 32, 8), ("16to16", 4, 16, 4), ("32to16", 8, 16, 4), ("36to40", 9, 40, 9)):
     pc = layer(cin_chunks, cout_pad, out_chunks)
     x = torch.randn(cin_chunks, D, H, W, 4, generator=g).to(dev)
     outs = [torch.empty(out_chunks, D, H, W, 4, device=dev) for _ in range(3)]

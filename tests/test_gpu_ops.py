@@ -203,7 +203,7 @@ def test_conv3d_is_bitwise_deterministic(precision):
     assert torch.equal(outs[0], outs[1]) and torch.equal(parts[0], parts[1])
 
 
-@pytest.mark.parametrize("case", ["32to32", "36to32", "16to16", "32to16"])
+@pytest.mark.parametrize("case", ["32to32", "36to32", "16to16", "32to16", "36to33"])
 @pytest.mark.parametrize("shape", [(48, 64, 128), (13, 40, 70), (3, 120, 160), (1, 33, 65)],
                          ids=["long_segments", "ragged", "three_planes", "one_plane"])
 def test_conv3d_ring_matches_exact_kernel(case, shape):
@@ -212,23 +212,29 @@ def test_conv3d_ring_matches_exact_kernel(case, shape):
     hand-over of the last plane of a column), with residuals, two input segments and two output tensors."""
     D, H, W = shape
     g = torch.Generator().manual_seed(D * 1000 + H)
-    cin_seg = {"32to32": (8,), "36to32": (8, 1), "16to16": (4,), "32to16": (4, 4)}[case]
-    cout = 16 if case.endswith("to16") else 32
+    cin_seg = {"32to32": (8,), "36to32": (8, 1), "16to16": (4,), "32to16": (4, 4), "36to33": (8, 1)}[case]
+    cout = {"16to16": 16, "32to16": 16, "36to33": 33}.get(case, 32)
+    cout_pad = 40 if cout == 33 else cout                 # 33 -> 40 for the exact kernel, 48 on the tensor cores (dres2)
     cin = 4 * sum(cin_seg)
     x = torch.randn(sum(cin_seg), D, H, W, 4, generator=g).to(DEV)
     w = torch.randn(cout, cin, 3, 3, 3, generator=g) / (cin * 27) ** 0.5
-    scale = (torch.rand(cout, generator=g) + 0.5).to(DEV)
-    shift = (torch.randn(cout, generator=g) / 3).to(DEV)
-    pc = packing.attach_tc(ops.PackedConv(packing.pack_weight(w, list(range(cin)), list(range(cout))).to(DEV), scale, shift,
-                                          sum(cin_seg), cout, cout // 4, cout // 2, "tanh", "relu"))
+    scale, shift = torch.zeros(cout_pad), torch.zeros(cout_pad)
+    scale[:cout] = torch.rand(cout, generator=g) + 0.5
+    shift[:cout] = torch.randn(cout, generator=g) / 3
+    order = list(range(cout)) + [-1] * (cout_pad - cout)
+    out_chunks = (cout + 3) // 4
+    oc = out_chunks // 2                                  # chunks of the first output tensor; the rest go to the second
+    pc = packing.attach_tc(ops.PackedConv(packing.pack_weight(w, list(range(cin)), order).to(DEV), scale.to(DEV), shift.to(DEV),
+                                          sum(cin_seg), cout_pad, out_chunks, 8 * (cout // 16), "tanh", "relu"))
     assert pc.weight_ring is not None
-    oc = cout // 8                                        # chunks per output tensor (two output tensors)
-    res0 = torch.randn(2 * oc, D, H, W, 4, generator=g).to(DEV)
+    res0 = torch.randn(out_chunks, D, H, W, 4, generator=g).to(DEV)
+    if cout % 4:                                          # pad channels of the residual must be zero to compare padded outputs
+        res0[-1, ..., cout % 4:] = 0
     ins = [x[:cin_seg[0]].contiguous()] + ([x[cin_seg[0]:].contiguous()] if len(cin_seg) > 1 else [])
     got, want = {}, {}
     for precision, store in (("fp32", want), ("3xf16r", got)):
         o0 = torch.full((oc, D, H, W, 4), float("nan"), device=DEV)
-        o1 = torch.full((oc, D, H, W, 4), float("nan"), device=DEV)
+        o1 = torch.full((out_chunks - oc, D, H, W, 4), float("nan"), device=DEV)
         n = ops.conv3d_num_ctas(pc, D, H, W, precision=precision)
         part = torch.zeros(n, 2, 2, device=DEV, dtype=torch.float64)
         ops.conv3d(pc, ins[0], o0, in1=ins[1] if len(ins) > 1 else None, out1=o1, res0=res0, post_scale=0.5,
