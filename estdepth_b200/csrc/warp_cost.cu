@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256, 4) warp_cost_kernel(const float* __restri
             o.y = r.y + fmaf(e[k].y, t.w_se, fmaf(c[k].y, t.w_sw, fmaf(b[k].y, t.w_ne, a[k].y * t.w_nw)));
             o.z = r.z + fmaf(e[k].z, t.w_se, fmaf(c[k].z, t.w_sw, fmaf(b[k].z, t.w_ne, a[k].z * t.w_nw)));
             o.w = r.w + fmaf(e[k].w, t.w_se, fmaf(c[k].w, t.w_sw, fmaf(b[k].w, t.w_ne, a[k].w * t.w_nw)));
-            st4(outp + j * out_chunk + (size_t)k * plane, o);
+            __stcs(reinterpret_cast<float4*>(outp + j * out_chunk + (size_t)k * plane), o);   // streamed: never re-read by this kernel
         }
     }
 }

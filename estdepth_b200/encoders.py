@@ -29,6 +29,7 @@ class _FoldedConv(object):
 
     def __init__(self):
         self.cache = {}
+        self.channels_last = False      # experiment switch (profiles/bench_feeders.py): NHWC weights for NHWC activations
 
     def params(self, conv, bn):
         ver = (conv.weight.data_ptr(), conv.weight._version, bn.weight._version, bn.bias._version,
@@ -45,6 +46,10 @@ class _FoldedConv(object):
 
     def __call__(self, x, conv, bn, relu=False, residual=None):
         w, b = self.params(conv, bn)
+        if self.channels_last:
+            w = w.contiguous(memory_format=torch.channels_last)
+            if residual is not None:
+                residual = residual.contiguous(memory_format=torch.channels_last)
         if x.is_cuda and relu and conv.groups == 1:
             if residual is not None:
                 return torch.cudnn_convolution_add_relu(x, w, residual, 1.0, b, conv.stride, conv.padding, conv.dilation, 1)
