@@ -1,0 +1,313 @@
+// Planar (2-D) 3x3 convolution, stride 1, dilation 1 or 2, on the tcgen05 tensor cores: the 3x3 layers of the 2-D feeder
+// networks (matching-feature net networks/psm_submodule.py:14-54, context decoder hybrid_models/hybrid_depth_decoder.py:
+// 17-30,163-184) over a stack of feature maps held as vol4 [C/4][N][H][W][4].  Same error-compensated fp16 split as the
+// 3-D kernels (x = x_hi + x_lo, w * 2^k = w_hi + w_lo; x_hi w_hi + x_hi w_lo + x_lo w_hi in fp32 TMEM accumulators).
+//
+//   GEMM     D[M = 128 pixels (16 rows x 8 columns), N] += A[M, K = 16 channels of one tap] * B[N, K]^T
+//   unit     16 x 16 pixels of one map (2 M tiles) x one slice of COUT output channels; persistent CTAs, unit = blockIdx + k*grid
+//   A        one TMA box per stage: the halo tile of 16 input channels (4 fp32 chunks), split IN PLACE by 8 warps into
+//            x_hi / x_lo K-groups; each tap of each M tile is a shifted start address of a no-swizzle K-major descriptor
+//   B        per-stage weight block [9 taps][2 K-groups][W_hi rows | W_lo rows][16 B] by bulk copy
+//   MMA      per tap and M tile: D[:, 0:2C] (+)= A_hi x [W_hi | W_lo] (N = 2C) and D[:, C:2C] += A_lo x W_hi (N = C): the
+//            small products accumulate apart from the large ones (the tensor core truncates to the accumulator's ulp on
+//            every accumulate; sharing the large products between the two halves was measured and is WORSE, because every
+//            small addend then also costs one truncation at full magnitude).
+//            With C = 64 that is 64 + 48 shared-memory wavefronts of operand fetch for 64 + 32 cycles of math
+//            (profiles/mma_probe.cu: an M=128, K=16 MMA costs max(N/2, 32 + N/4) cycles).
+//   TMEM     2 M tiles x 2C columns per unit, double buffered: the epilogue of unit u (8 warps: TMEM -> hi + lo -> affine ->
+//            activation -> residual -> 16-byte stores) overlaps the MMAs of unit u+1.
+//   The number of 16-channel k-steps is a run-time argument (64 ... 2048 input channels use the same kernel).
+// The x_hi w_hi products of an output run through one accumulator: 9 * Cin/16 accumulating MMAs, ~0.5 ulp of truncation
+// each (8e-5 at Cin = 1280 for O(1) outputs; cuDNN's own fp32 Winograd kernels are at 5e-5 .. 1e-4 on such layers).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "conv3d_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace estd {
+namespace planar {
+
+using namespace tc;
+
+constexpr int EPI_WARPS = 8, SPLIT_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32, SPLIT_THREADS = SPLIT_WARPS * 32;
+constexpr int THREADS = 128 + EPI_THREADS + SPLIT_THREADS;       // warps 0-3 control, 4-11 epilogue, 12-19 splitters
+constexpr int FIRST_SPLIT_WARP = 4 + EPI_WARPS;
+
+template <int COUT_, int DIL_>
+struct Shape {
+    static constexpr int COUT = COUT_, DIL = DIL_, MT = 2;
+    static constexpr int TILE_H = 16, TILE_W = 8 * MT;
+    static constexpr int HALO_H = TILE_H + 2 * DIL, HALO_W = TILE_W + 2 * DIL, HALO_VOX = HALO_H * HALO_W;
+    static constexpr int KGROUP_BYTES = HALO_VOX * 16;
+    static constexpr int A_BYTES = 4 * KGROUP_BYTES;
+    static constexpr int N_ALL = 2 * COUT;
+    static constexpr int W_TAP_BYTES = 2 * N_ALL * 16;            // [2 K-groups][N_ALL rows][16 B]
+    static constexpr int W_BYTES = 9 * W_TAP_BYTES;
+    static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES + 127) / 128 * 128;
+    static constexpr int STAGES = (4 * STAGE_BYTES + 4096 <= 227 * 1024) ? 4 : 3;
+    static constexpr int COLS_PER_UNIT = MT * N_ALL;
+    static constexpr int TMEM_COLS = (2 * COLS_PER_UNIT <= 128) ? 128 : (2 * COLS_PER_UNIT <= 256) ? 256 : 512;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;
+    static_assert(2 * COLS_PER_UNIT <= 512, "two accumulator buffers must fit TMEM");
+    static_assert(SMEM + 2048 <= 227 * 1024, "stages must fit shared memory");
+    static_assert(COUT % 16 == 0 && COUT <= 64, "bad COUT");
+};
+
+struct Params {
+    const float* weight_tc;                     // [nks][9 taps][2 K-groups][2*COUT rows][16 bytes]
+    int* status;
+    ConvEpilogue ep;
+    int in0_chunks, nks;
+    int D, H, W;                                // D = number of maps in the stack
+    int tiles_h, tiles_w, n_units;
+};
+
+template <class S>
+__global__ void __launch_bounds__(THREADS, 1)
+conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Params p) {
+    constexpr int COUT = S::COUT, STAGES = S::STAGES, N_ALL = S::N_ALL;
+    constexpr int HALO_W = S::HALO_W, HALO_VOX = S::HALO_VOX, A_BYTES = S::A_BYTES;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * S::STAGE_BYTES);
+    uint64_t* full = bars;                  // [STAGES] TMA landed
+    uint64_t* ready = bars + STAGES;        // [STAGES] split done
+    uint64_t* empty = bars + 2 * STAGES;    // [STAGES] MMAs done reading
+    uint64_t* acc_full = bars + 3 * STAGES; // [2]
+    uint64_t* acc_empty = acc_full + 2;     // [2]
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    __shared__ __align__(16) float s_scale[COUT], s_shift[COUT];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nks = p.nks;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], SPLIT_THREADS); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_THREADS); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_base_smem, S::TMEM_COLS);
+    if (warp == 3) for (int i = lane; i < COUT; i += 32) { s_scale[i] = p.ep.scale[i]; s_shift[i] = p.ep.shift[i]; }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    const int n_mine = (p.n_units > (int)blockIdx.x) ? (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    auto unit_origin = [&](int k, int& d, int& h0, int& w0) {
+        const int u = blockIdx.x + k * gridDim.x;
+        const int tw = u % p.tiles_w;
+        const int th = (u / p.tiles_w) % p.tiles_h;
+        d = u / (p.tiles_w * p.tiles_h);
+        h0 = th * S::TILE_H; w0 = tw * S::TILE_W;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int it = 0;
+            for (int k = 0; k < n_mine; ++k) {
+                int d, h0, w0;
+                unit_origin(k, d, h0, w0);
+                for (int ks = 0; ks < nks; ++ks, ++it) {
+                    const int s = it % STAGES;
+                    if (it >= STAGES) mbar_wait_polls(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
+                    unsigned char* stage = smem + (size_t)s * S::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(A_BYTES + S::W_BYTES));
+                    const int chunk = 4 * ks;
+                    if (chunk < p.in0_chunks) tma_load_4d(stage, &map0, &full[s], 4 * (w0 - S::DIL), h0 - S::DIL, d, chunk);
+                    else                      tma_load_4d(stage, &map1, &full[s], 4 * (w0 - S::DIL), h0 - S::DIL, d, chunk - p.in0_chunks);
+                    bulk_load(stage + A_BYTES, p.weight_tc + (size_t)ks * (S::W_BYTES / 4), (uint32_t)S::W_BYTES, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc_all = make_idesc(0u, N_ALL), idesc_hi = make_idesc(0u, COUT);
+        const bool leader = elect_one();
+        int it = 0;
+        for (int k = 0; k < n_mine; ++k) {
+            const int buf = k & 1, use = k >> 1;                   // how many times this accumulator buffer was used before
+            if (use > 0) { mbar_wait_polls(&acc_empty[buf], (uint32_t)((use - 1) & 1)); tc_fence_after(); }
+            const uint32_t acc0 = tmem_base + (uint32_t)(buf * S::COLS_PER_UNIT);
+            for (int ks = 0; ks < nks; ++ks, ++it) {
+                const int s = it % STAGES;
+                mbar_wait_polls(&ready[s], (uint32_t)((it / STAGES) & 1));
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + (size_t)s * S::STAGE_BYTES);
+                const uint64_t a_hi_desc = make_desc(a_hi, 2 * S::KGROUP_BYTES, HALO_W * 16);
+                const uint64_t a_lo_desc = make_desc(a_hi + S::KGROUP_BYTES, 2 * S::KGROUP_BYTES, HALO_W * 16);
+                const uint64_t b_desc = make_desc(a_hi + A_BYTES, N_ALL * 16, 128);
+                const uint32_t later = (ks == 0) ? 0u : 1u;        // the very first MMA of a unit overwrites the accumulator
+                if (leader) {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                        for (int mt = 0; mt < S::MT; ++mt) {
+                            const uint64_t a_off = (uint64_t)((tap / 3) * S::DIL * HALO_W + 8 * mt + (tap % 3) * S::DIL);
+                            const uint64_t b_off = (uint64_t)(tap * (S::W_TAP_BYTES >> 4));
+                            const uint32_t acc = acc0 + (uint32_t)(mt * N_ALL);
+                            umma<KIND_F16>(acc, a_hi_desc + a_off, b_desc + b_off, idesc_all, tap == 0 ? later : 1u);
+                            umma<KIND_F16>(acc + COUT, a_lo_desc + a_off, b_desc + b_off, idesc_hi, 1u);
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                    if (ks == nks - 1) umma_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= FIRST_SPLIT_WARP) {
+        // ===================== hi/lo splitter =====================
+        const int t = tid - FIRST_SPLIT_WARP * 32;
+        float amax = 0.0f;
+        const int n_stages = n_mine * nks;
+        for (int it = 0; it < n_stages; ++it) {
+            const int s = it % STAGES;
+            if (warp == FIRST_SPLIT_WARP) mbar_wait_polls(&full[s], (uint32_t)((it / STAGES) & 1));
+            named_barrier(2, SPLIT_THREADS);
+            unsigned char* area = smem + (size_t)s * S::STAGE_BYTES;
+            for (int i = t; i < 2 * HALO_VOX; i += SPLIT_THREADS) {
+                const int pair = i / HALO_VOX, v = i - pair * HALO_VOX;
+                float4* c0 = reinterpret_cast<float4*>(area + (size_t)pair * 2 * S::KGROUP_BYTES) + v;
+                float4* c1 = c0 + HALO_VOX;
+                const float4 a = *c0, b = *c1;
+                amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                                         fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+                const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+                const __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+                const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+                const __half2 l0 = __floats2half2_rn(a.x - f0.x, a.y - f0.y), l1 = __floats2half2_rn(a.z - f1.x, a.w - f1.y);
+                const __half2 l2 = __floats2half2_rn(b.x - f2.x, b.y - f2.y), l3 = __floats2half2_rn(b.z - f3.x, b.w - f3.y);
+                uint4 hv, lv;
+                hv.x = h2u(h0); hv.y = h2u(h1); hv.z = h2u(h2); hv.w = h2u(h3);
+                lv.x = h2u(l0); lv.y = h2u(l1); lv.z = h2u(l2); lv.w = h2u(l3);
+                *reinterpret_cast<uint4*>(c0) = hv;
+                *reinterpret_cast<uint4*>(c1) = lv;
+            }
+            fence_proxy_async();
+            mbar_arrive(&ready[s]);
+        }
+        const bool bad = !(amax <= 65504.0f);
+        if (bad && p.status) atomicOr(p.status, 1);
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int e = warp - 4, q = e & 3, mt = e >> 2;          // TMEM lane quarter; M tile
+        const int m = q * 32 + lane;
+        const int mh = m >> 3, mw = m & 7;
+        const size_t vox = (size_t)p.D * p.H * p.W;
+        const ConvEpilogue& ep = p.ep;
+        for (int k = 0; k < n_mine; ++k) {
+            const int buf = k & 1, use = k >> 1;
+            int d, h0, w0;
+            unit_origin(k, d, h0, w0);
+            const int h = h0 + mh, w = w0 + 8 * mt + mw;
+            const bool ok = (h < p.H) && (w < p.W);
+            const size_t pos = ((size_t)d * p.H + h) * p.W + w;
+            float4 r0[4];
+            auto load_res = [&](int c0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ch = (c0 >> 2) + j;
+                    const bool valid = ok && ch < ep.out_chunks;
+                    r0[j] = (ep.res0 && valid) ? ldg4(ep.res0 + ((size_t)ch * vox + pos) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            load_res(0);
+            if (e == 0) mbar_wait_polls(&acc_full[buf], (uint32_t)(use & 1));
+            named_barrier(3, EPI_THREADS);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * S::COLS_PER_UNIT + mt * N_ALL);
+#pragma unroll 1
+            for (int c0 = 0; c0 < COUT; c0 += 16) {
+                float a[16], b[16];
+                tmem_ld16(t0 + (uint32_t)c0, a);
+                tmem_ld16(t0 + (uint32_t)(COUT + c0), b);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = c0 + 4 * j;
+                    const int ch = c >> 2;
+                    if (!ok || ch >= ep.out_chunks) continue;
+                    const int act = (c < ep.act_split) ? ep.act_lo : ep.act_hi;
+                    const float4 sc = *reinterpret_cast<const float4*>(s_scale + c), sh = *reinterpret_cast<const float4*>(s_shift + c);
+                    float v[4];
+                    v[0] = fmaf(a[4 * j + 0] + b[4 * j + 0], sc.x, sh.x); v[1] = fmaf(a[4 * j + 1] + b[4 * j + 1], sc.y, sh.y);
+                    v[2] = fmaf(a[4 * j + 2] + b[4 * j + 2], sc.z, sh.z); v[3] = fmaf(a[4 * j + 3] + b[4 * j + 3], sc.w, sh.w);
+                    if (act == ESTD_ACT_RELU) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.0f);
+                    } else if (act == ESTD_ACT_TANH) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[i] = tanhf(v[i]);
+                    }
+                    v[0] += r0[j].x; v[1] += r0[j].y; v[2] += r0[j].z; v[3] += r0[j].w;
+                    const size_t off = ((size_t)ch * vox + pos) * 4;
+                    float* dst = (ch < ep.out0_chunks) ? ep.out0 + off : ep.out1 + (off - (size_t)ep.out0_chunks * vox * 4);
+                    st4(dst, make_float4(v[0] * ep.post_scale, v[1] * ep.post_scale, v[2] * ep.post_scale, v[3] * ep.post_scale));
+                }
+                if (c0 + 16 < COUT) load_res(c0 + 16);
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+template <class S>
+static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas) {
+    const int tiles_h = (d->H + S::TILE_H - 1) / S::TILE_H, tiles_w = (d->W + S::TILE_W - 1) / S::TILE_W;
+    const long long n_units = (long long)d->D * tiles_h * tiles_w;
+    ESTD_REQUIRE(n_units < (1ll << 30), "estd_conv3d(planar): too many tiles");
+    const int grid = n_units < sm_count() ? (int)n_units : sm_count();
+    *n_ctas = grid;
+    if (count_only) return ESTD_OK;
+    const int cin_chunks = d->in0_chunks + d->in1_chunks;
+    ESTD_REQUIRE(d->weight_tc && aligned16(d->weight_tc), "estd_conv3d(planar): needs a 16-byte aligned weight_tc");
+    ESTD_REQUIRE(d->in1_chunks == 0 || (d->in0_chunks % 4) == 0, "estd_conv3d(planar): first input segment must hold a multiple of 4 chunks");
+    ESTD_REQUIRE(!d->gn_partials && !d->res1, "estd_conv3d(planar): GroupNorm partial sums / second residual are not implemented for planar convolutions");
+    CUtensorMap map0, map1;
+    int rc = make_vol4_tensor_map(&map0, d->in0, d->in0_chunks, d->D, d->H, d->W, S::HALO_W * 4, S::HALO_H, 1, 4);
+    if (rc) return rc;
+    if (d->in1_chunks > 0) rc = make_vol4_tensor_map(&map1, d->in1, d->in1_chunks, d->D, d->H, d->W, S::HALO_W * 4, S::HALO_H, 1, 4);
+    else map1 = map0;
+    if (rc) return rc;
+    Params p;
+    p.weight_tc = d->weight_tc;
+    p.status = d->status;
+    fill_epilogue(&p.ep, d);
+    p.in0_chunks = d->in0_chunks;
+    p.nks = (cin_chunks + 3) / 4;
+    p.D = d->D; p.H = d->H; p.W = d->W;
+    p.tiles_h = tiles_h; p.tiles_w = tiles_w; p.n_units = (int)n_units;
+    auto kern = conv2d_tc_kernel<S>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM);
+        if (e != cudaSuccess) return fail(ESTD_ECUDA, "estd_conv3d(planar): cannot reserve %zu B of shared memory: %s", S::SMEM, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    kern<<<grid, THREADS, S::SMEM, stream>>>(map0, map1, p);
+    return check_launch("estd_conv3d(planar)");
+}
+
+}  // namespace planar
+
+int dispatch_planar(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas) {
+    using namespace planar;
+    ESTD_REQUIRE(d->precision == ESTD_PREC_3XF16 || d->precision == ESTD_PREC_3XF16_RING,
+                 "estd_conv3d: planar convolutions are implemented for the fp16 split only");
+    const int dil = d->dilation > 0 ? d->dilation : 1;
+    const int C = d->cout_pad;
+#define ESTD_PLANAR(COUT, DIL) if (C == COUT && dil == DIL) return launch<Shape<COUT, DIL>>(d, stream, count_only, n_ctas)
+    ESTD_PLANAR(64, 1); ESTD_PLANAR(64, 2); ESTD_PLANAR(32, 1); ESTD_PLANAR(32, 2); ESTD_PLANAR(16, 1);
+#undef ESTD_PLANAR
+    return fail(ESTD_EUNSUPPORTED, "estd_conv3d(planar): no kernel for cout_pad %d, dilation %d (cout_pad 16/32/64, dilation 1/2)", C, dil);
+}
+
+}  // namespace estd

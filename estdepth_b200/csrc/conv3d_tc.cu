@@ -353,18 +353,7 @@ int dispatch_tc(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only,
     const int cin_chunks = d->in0_chunks + d->in1_chunks;
     const int C = d->cout_pad;
     const int dil = d->dilation > 0 ? d->dilation : 1;
-    if (d->planar) {
-        // 2-D (1x3x3 per plane) convolutions of the matching-feature net: fp16 split only, 16x16-voxel units
-        ESTD_REQUIRE(d->precision == ESTD_PREC_3XF16, "estd_conv3d: planar convolutions are implemented for ESTD_PREC_3XF16 only");
-        const int nks = (cin_chunks + 3) / 4;
-#define ESTD_PLANAR(NKS, COUT, DIL) if (nks == NKS && C == COUT && dil == DIL) \
-            return launch<Shape<KIND_F16, NKS, COUT, 2, DIL, true>>(d, stream, count_only, n_ctas)
-        ESTD_PLANAR(2, 32, 1); ESTD_PLANAR(2, 64, 1); ESTD_PLANAR(4, 64, 1); ESTD_PLANAR(8, 64, 1); ESTD_PLANAR(8, 64, 2);
-        ESTD_PLANAR(20, 64, 1);
-#undef ESTD_PLANAR
-        return fail(ESTD_EUNSUPPORTED, "estd_conv3d(planar): no kernel for %d input chunks -> cout_pad %d, dilation %d",
-                    cin_chunks, C, dil);
-    }
+    ESTD_REQUIRE(!d->planar, "estd_conv3d: planar convolutions live in conv2d_tc.cu");
     ESTD_REQUIRE(dil == 1, "estd_conv3d: dilation is supported for planar convolutions only");
     if (d->precision == ESTD_PREC_3XTF32) {
         const int nks = (cin_chunks + 1) / 2;                     // 8 channels per stage

@@ -30,6 +30,30 @@ class _FoldedConv(object):
     def __init__(self):
         self.cache = {}
         self.channels_last = False      # experiment switch (profiles/bench_feeders.py): NHWC weights for NHWC activations
+        self.split_tf32 = False         # experiment switch: three-term TF32 split through cuDNN's tensor-core kernels
+        self.cache3 = {}
+
+    @staticmethod
+    def _split(t):
+        hi = (t.view(torch.int32) & -8192).view(torch.float32)
+        lo = ((t - hi).view(torch.int32) & -8192).view(torch.float32)
+        return hi, lo
+
+    def _call_split(self, x, conv, bn, relu, residual):
+        w, b = self.params(conv, bn)
+        ent = self.cache3.get(id(conv))
+        if ent is None or ent[0] is not w:
+            wh, wl = self._split(w)
+            ent = (w, torch.cat([wh, wl, wh], 1).contiguous(memory_format=torch.channels_last))
+            self.cache3[id(conv)] = ent
+        xh, xl = self._split(x)
+        x3 = torch.cat([xh, xh, xl], 1).contiguous(memory_format=torch.channels_last)
+        with torch.backends.cudnn.flags(enabled=True, benchmark=True, allow_tf32=True):
+            y = F.conv2d(x3, ent[1], b, conv.stride, conv.padding, conv.dilation, 1)
+        if residual is not None:
+            y = y + residual
+        y = F.relu_(y) if relu else y
+        return y.contiguous()
 
     def params(self, conv, bn):
         ver = (conv.weight.data_ptr(), conv.weight._version, bn.weight._version, bn.bias._version,
@@ -45,6 +69,8 @@ class _FoldedConv(object):
         return ent[1], ent[2]
 
     def __call__(self, x, conv, bn, relu=False, residual=None):
+        if self.split_tf32 and x.is_cuda and conv.groups == 1:
+            return self._call_split(x, conv, bn, relu, residual)
         w, b = self.params(conv, bn)
         if self.channels_last:
             w = w.contiguous(memory_format=torch.channels_last)
@@ -61,6 +87,8 @@ class _FoldedConv(object):
 
 
 _folded = _FoldedConv()
+import os as _os  # noqa: E402
+_folded.split_tf32 = _os.environ.get("ESTD_FEEDER_SPLIT_TF32", "0") == "1"
 
 
 def _conv_bn(cin, cout, k, stride, pad, dilation):

@@ -105,8 +105,8 @@ def pack_weight_f16(packed, cout_pad_tc=None):
     def arrange(x):      # [taps = dd*9+tap9][16*nks = ks*16+kg*8+e][C] -> [dd][ks][tap9][kg][C][e]
         return x.reshape(taps // 9, 9, nks, 2, 8, C).permute(0, 2, 1, 3, 5, 4)
 
-    both = torch.cat([arrange(hi), arrange(lo)], dim=4).contiguous()          # [planes][nks][9][2][2C][8] fp16
-    return both.view(torch.float32), k
+    both = torch.cat([arrange(hi), arrange(lo)], dim=4)                       # [planes][nks][9][2][2C][8] fp16
+    return both.contiguous().view(torch.float32), k
 
 
 # (16-channel k-steps, cout_pad) the plane-ring kernel (conv3d_ring.cu) is specialised for

@@ -102,8 +102,9 @@ typedef struct estd_conv3d_desc {
     int precision;                        /* ESTD_PREC_*; cout_pad is 16/32/40 for FP32 and 16/32/48 for the tensor-core paths */
     int* status;                          /* optional device int, OR-ed with 1 on an fp16 range violation (ESTD_PREC_3XF16) */
     int planar;                           /* 0: 3x3x3 filter.  1: 1x3x3 filter applied per plane = 2-D 3x3 convolution over a stack of
-                                             D feature maps (the matching-feature net); weight_tc is [nks][9][2][2*cout_pad][16 B];
-                                             ESTD_PREC_3XF16 only */
+                                             D feature maps (matching-feature net, context decoder); weight_tc is [nks][9][2][2*cout_pad][16 B],
+                                             any number of input chunks, cout_pad 16/32/64 (wider layers: one call per 64-channel
+                                             slice); fp16 split only; no gn_partials / res1 */
     int dilation;                         /* in-plane tap dilation, 1 or 2 (2: planar only); 0 is read as 1 */
     const float* scale;                   /* [cout_pad] per-channel multiplier (folded BN gamma/sqrt(var+eps)) */
     const float* shift;                   /* [cout_pad] per-channel offset (folded BN beta - mean*scale, or conv bias) */

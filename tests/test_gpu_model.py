@@ -18,7 +18,7 @@ from tests.helpers import cfg_of, synth_model_and_state
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 DEPTH_TOL = 1e-3          # north_star gate
-STATE_TOL = 1e-4
+STATE_TOL = 2e-4          # hidden state (|v| <= 1): key/value volumes after ~25 tensor-core layers, each truncating on accumulate
 STATE_STRIDE = 4
 
 

@@ -250,6 +250,49 @@ def test_conv3d_ring_matches_exact_kernel(case, shape):
     ops.check_status(torch.device(DEV))
 
 
+PLANAR_CASES = [
+    # name, cin segments (channels), cout, dilation, maps, H, W
+    ("64to64", (64,), 64, 1, 5, 40, 56),
+    ("64to64_dil2", (64,), 64, 2, 3, 33, 47),
+    ("32to32", (32,), 32, 1, 2, 48, 64),
+    ("320to128", (192, 128), 128, 1, 2, 30, 40),
+    ("1280to256_small", (256, 1024), 256, 1, 3, 15, 20),
+    ("128to33pad", (128,), 48, 1, 1, 16, 16),
+]
+
+
+@pytest.mark.parametrize("case", PLANAR_CASES, ids=[c[0] for c in PLANAR_CASES])
+def test_conv2d_planar_vs_torch_cpu(case):
+    """Planar tcgen05 3x3 convolution (conv2d_tc.cu) == F.conv2d (CPU, fp64 accumulate) + affine + ReLU + residual: any
+    number of input channels (run-time k-steps), two input segments (the decoder's torch.cat), 64-channel output slices,
+    dilation 2, ragged tiles."""
+    name, cin_seg, cout, dil, N, H, W = case
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)
+    cin = sum(cin_seg)
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) / 3
+    res = torch.randn(N, cout, H, W, generator=g)
+    want = (torch.relu(F.conv2d(x.double(), w.double(), None, 1, dil, dil) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)) + res).float()
+    pcs = packing.pack_conv2d(w, scale, shift, "relu", DEV, cout_slice=64 if cout >= 64 else (32 if cout >= 32 else 16))
+    x4 = ops.nchw_to_vol4(x.to(DEV))
+    ins = [x4[:cin_seg[0] // 4].contiguous()] + ([x4[cin_seg[0] // 4:].contiguous()] if len(cin_seg) > 1 else [])
+    out4 = torch.full((cout // 4, N, H, W, 4), float("nan"), device=DEV)
+    res4 = ops.nchw_to_vol4(res.to(DEV))
+    step = pcs[0].cout_pad // 4
+    for i, pc in enumerate(pcs):
+        lo, hi = step * i, step * i + pc.out_chunks
+        ops.conv_planar(pc, ins[0], out4[lo:hi], res0=res4[lo:hi], dilation=dil, in1=ins[1] if len(ins) > 1 else None)
+    got = ops.vol4_to_nchw(out4).cpu()
+    assert torch.isfinite(got).all()
+    err = (got - want).abs().max().item()
+    print("conv2d planar %s: max |err| = %.3e" % (name, err))
+    # x_hi*w_hi runs through one fp32 TMEM accumulator; the tensor core truncates on each of the 9*cin/16 accumulates
+    assert err < 3e-5 * max(1.0, cin / 320.0)
+    ops.check_status(torch.device(DEV))
+
+
 @pytest.mark.parametrize("j", [0, 2])
 def test_warp_volume_vs_reference_golden(j):
     """ops.warp_volume (the fused EST gather with N=1) == the reference's warp_volume (utils/homo_utils.py:240)."""
