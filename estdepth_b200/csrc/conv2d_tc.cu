@@ -16,7 +16,10 @@
 //            (profiles/mma_probe.cu: an M=128, K=16 MMA costs max(N/2, 32 + N/4) cycles).
 //   TMEM     2 M tiles x 2C columns per unit, double buffered: the epilogue of unit u (8 warps: TMEM -> hi + lo -> affine ->
 //            activation -> residual -> 16-byte stores) overlaps the MMAs of unit u+1.
-//   The number of 16-channel k-steps is a run-time argument (64 ... 2048 input channels use the same kernel).
+//   The number of 16-channel k-steps is a run-time argument (64 ... 2048 input channels use the same kernel), and layers
+//   wider than COUT run as cout_pad/COUT slices INSIDE one launch (unit = tile x slice, slices of a tile on adjacent CTAs so
+//   that the input tile is shared through L2): the small, deep maps of the context decoder (15x20 ... 30x40 pixels, 256
+//   output channels) would otherwise occupy a dozen SMs.
 // The x_hi w_hi products of an output run through one accumulator: 9 * Cin/16 accumulating MMAs, ~0.5 ulp of truncation
 // each (8e-5 at Cin = 1280 for O(1) outputs; cuDNN's own fp32 Winograd kernels are at 5e-5 .. 1e-4 on such layers).
 #include <cuda.h>
@@ -34,6 +37,7 @@ constexpr int EPI_WARPS = 8, SPLIT_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32, SPLIT_THREADS = SPLIT_WARPS * 32;
 constexpr int THREADS = 128 + EPI_THREADS + SPLIT_THREADS;       // warps 0-3 control, 4-11 epilogue, 12-19 splitters
 constexpr int FIRST_SPLIT_WARP = 4 + EPI_WARPS;
+constexpr int MAX_COUT_TOTAL = 512;
 
 template <int COUT_, int DIL_>
 struct Shape {
@@ -46,17 +50,18 @@ struct Shape {
     static constexpr int W_TAP_BYTES = 2 * N_ALL * 16;            // [2 K-groups][N_ALL rows][16 B]
     static constexpr int W_BYTES = 9 * W_TAP_BYTES;
     static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES + 127) / 128 * 128;
-    static constexpr int STAGES = (4 * STAGE_BYTES + 4096 <= 227 * 1024) ? 4 : 3;
+    static constexpr int STAGES = (4 * STAGE_BYTES + 8192 <= 227 * 1024) ? 4 : 3;
     static constexpr int COLS_PER_UNIT = MT * N_ALL;
     static constexpr int TMEM_COLS = (2 * COLS_PER_UNIT <= 128) ? 128 : (2 * COLS_PER_UNIT <= 256) ? 256 : 512;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;
     static_assert(2 * COLS_PER_UNIT <= 512, "two accumulator buffers must fit TMEM");
-    static_assert(SMEM + 2048 <= 227 * 1024, "stages must fit shared memory");
+    static_assert(SMEM + 6144 <= 227 * 1024, "stages must fit shared memory");
     static_assert(COUT % 16 == 0 && COUT <= 64, "bad COUT");
 };
 
 struct Params {
-    const float* weight_tc;                     // [nks][9 taps][2 K-groups][2*COUT rows][16 bytes]
+    const float* weight_tc;                     // [slices][nks][9 taps][2 K-groups][2*COUT rows][16 bytes]
+    int n_slices, cout_total;
     int* status;
     ConvEpilogue ep;
     int in0_chunks, nks;
@@ -77,7 +82,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     uint64_t* acc_full = bars + 3 * STAGES; // [2]
     uint64_t* acc_empty = acc_full + 2;     // [2]
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    __shared__ __align__(16) float s_scale[COUT], s_shift[COUT];
+    __shared__ __align__(16) float s_scale[MAX_COUT_TOTAL], s_shift[MAX_COUT_TOTAL];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nks = p.nks;
@@ -88,15 +93,17 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_base_smem, S::TMEM_COLS);
-    if (warp == 3) for (int i = lane; i < COUT; i += 32) { s_scale[i] = p.ep.scale[i]; s_shift[i] = p.ep.shift[i]; }
+    if (warp == 3) for (int i = lane; i < p.cout_total; i += 32) { s_scale[i] = p.ep.scale[i]; s_shift[i] = p.ep.shift[i]; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
     const int n_mine = (p.n_units > (int)blockIdx.x) ? (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    auto unit_origin = [&](int k, int& d, int& h0, int& w0) {
-        const int u = blockIdx.x + k * gridDim.x;
+    auto unit_origin = [&](int k, int& d, int& h0, int& w0, int& slice) {
+        const int uu = blockIdx.x + k * gridDim.x;
+        slice = uu % p.n_slices;
+        const int u = uu / p.n_slices;
         const int tw = u % p.tiles_w;
         const int th = (u / p.tiles_w) % p.tiles_h;
         d = u / (p.tiles_w * p.tiles_h);
@@ -108,8 +115,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         if (lane == 0) {
             int it = 0;
             for (int k = 0; k < n_mine; ++k) {
-                int d, h0, w0;
-                unit_origin(k, d, h0, w0);
+                int d, h0, w0, slice;
+                unit_origin(k, d, h0, w0, slice);
+                const float* wsl = p.weight_tc + (size_t)slice * nks * (S::W_BYTES / 4);
                 for (int ks = 0; ks < nks; ++ks, ++it) {
                     const int s = it % STAGES;
                     if (it >= STAGES) mbar_wait_polls(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
@@ -118,7 +126,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                     const int chunk = 4 * ks;
                     if (chunk < p.in0_chunks) tma_load_4d(stage, &map0, &full[s], 4 * (w0 - S::DIL), h0 - S::DIL, d, chunk);
                     else                      tma_load_4d(stage, &map1, &full[s], 4 * (w0 - S::DIL), h0 - S::DIL, d, chunk - p.in0_chunks);
-                    bulk_load(stage + A_BYTES, p.weight_tc + (size_t)ks * (S::W_BYTES / 4), (uint32_t)S::W_BYTES, &full[s]);
+                    bulk_load(stage + A_BYTES, wsl + (size_t)ks * (S::W_BYTES / 4), (uint32_t)S::W_BYTES, &full[s]);
                 }
             }
         }
@@ -200,8 +208,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         const ConvEpilogue& ep = p.ep;
         for (int k = 0; k < n_mine; ++k) {
             const int buf = k & 1, use = k >> 1;
-            int d, h0, w0;
-            unit_origin(k, d, h0, w0);
+            int d, h0, w0, slice;
+            unit_origin(k, d, h0, w0, slice);
+            const int cbase = slice * COUT;                        // first output channel of this slice
             const int h = h0 + mh, w = w0 + 8 * mt + mw;
             const bool ok = (h < p.H) && (w < p.W);
             const size_t pos = ((size_t)d * p.H + h) * p.W + w;
@@ -209,7 +218,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             auto load_res = [&](int c0) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int ch = (c0 >> 2) + j;
+                    const int ch = ((cbase + c0) >> 2) + j;
                     const bool valid = ok && ch < ep.out_chunks;
                     r0[j] = (ep.res0 && valid) ? ldg4(ep.res0 + ((size_t)ch * vox + pos) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -227,7 +236,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int c = c0 + 4 * j;
+                    const int c = cbase + c0 + 4 * j;
                     const int ch = c >> 2;
                     if (!ok || ch >= ep.out_chunks) continue;
                     const int act = (c < ep.act_split) ? ep.act_lo : ep.act_hi;
@@ -262,7 +271,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 template <class S>
 static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas) {
     const int tiles_h = (d->H + S::TILE_H - 1) / S::TILE_H, tiles_w = (d->W + S::TILE_W - 1) / S::TILE_W;
-    const long long n_units = (long long)d->D * tiles_h * tiles_w;
+    const int n_slices = d->cout_pad / S::COUT;
+    const long long n_units = (long long)d->D * tiles_h * tiles_w * n_slices;
     ESTD_REQUIRE(n_units < (1ll << 30), "estd_conv3d(planar): too many tiles");
     const int grid = n_units < sm_count() ? (int)n_units : sm_count();
     *n_ctas = grid;
@@ -279,6 +289,7 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
     if (rc) return rc;
     Params p;
     p.weight_tc = d->weight_tc;
+    p.n_slices = n_slices; p.cout_total = d->cout_pad;
     p.status = d->status;
     fill_epilogue(&p.ep, d);
     p.in0_chunks = d->in0_chunks;
@@ -304,10 +315,11 @@ int dispatch_planar(const estd_conv3d_desc* d, cudaStream_t stream, bool count_o
                  "estd_conv3d: planar convolutions are implemented for the fp16 split only");
     const int dil = d->dilation > 0 ? d->dilation : 1;
     const int C = d->cout_pad;
-#define ESTD_PLANAR(COUT, DIL) if (C == COUT && dil == DIL) return launch<Shape<COUT, DIL>>(d, stream, count_only, n_ctas)
+    ESTD_REQUIRE(C <= MAX_COUT_TOTAL, "estd_conv3d(planar): cout_pad %d exceeds %d", C, MAX_COUT_TOTAL);
+#define ESTD_PLANAR(COUT, DIL) if ((C == COUT || (COUT == 64 && C > 64 && C % 64 == 0)) && dil == DIL) return launch<Shape<COUT, DIL>>(d, stream, count_only, n_ctas)
     ESTD_PLANAR(64, 1); ESTD_PLANAR(64, 2); ESTD_PLANAR(32, 1); ESTD_PLANAR(32, 2); ESTD_PLANAR(16, 1);
 #undef ESTD_PLANAR
-    return fail(ESTD_EUNSUPPORTED, "estd_conv3d(planar): no kernel for cout_pad %d, dilation %d (cout_pad 16/32/64, dilation 1/2)", C, dil);
+    return fail(ESTD_EUNSUPPORTED, "estd_conv3d(planar): no kernel for cout_pad %d, dilation %d (cout_pad 16/32/64 or a multiple of 64, dilation 1/2)", C, dil);
 }
 
 }  // namespace estd

@@ -91,6 +91,39 @@ import os as _os  # noqa: E402
 _folded.split_tf32 = _os.environ.get("ESTD_FEEDER_SPLIT_TF32", "0") == "1"
 
 
+def _bn_affine(bn):
+    scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    shift = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+    return scale.float(), shift.float()
+
+
+def _pack3x3(conv, bn, act, device):
+    """conv(3x3, stride 1)+BN -> packed planar tensor-core layer (packing.pack_conv2d), or None when the shape is not one the
+    kernel takes (input channels must come in whole 16-channel k-steps)."""
+    from . import packing
+    w = conv.weight.detach()
+    if conv.kernel_size != (3, 3) or conv.stride != (1, 1) or conv.groups != 1 or w.shape[1] % 16 or conv.dilation not in ((1, 1), (2, 2)):
+        return None
+    s, b = _bn_affine(bn)
+    return packing.pack_conv2d(w, s, b, act, device, cout_slice=64 if w.shape[0] > 32 else 32)
+
+
+def _run3x3(pcs, x4, out4=None, res4=None, dilation=1, in1=None):
+    """One packed planar layer over vol4 maps [C/4, N, H, W, 4] (+ optional second input segment = torch.cat on channels)."""
+    from . import ops
+    pc = pcs[0]
+    if out4 is None:
+        out4 = torch.empty(pc.out_chunks, x4.shape[1], x4.shape[2], x4.shape[3], 4, device=x4.device, dtype=torch.float32)
+    ops.conv_planar(pc, x4, out4, res0=res4, dilation=dilation, in1=in1)
+    return out4
+
+
+def _up2_vol4(x4):
+    """nearest x2 upsampling of vol4 maps (hybrid_depth_decoder.py:11-14)."""
+    c, n, h, w, _ = x4.shape
+    return x4[:, :, :, None, :, None, :].expand(c, n, h, 2, w, 2, 4).reshape(c, n, 2 * h, 2 * w, 4)
+
+
 def _conv_bn(cin, cout, k, stride, pad, dilation):
     """conv(bias=False)+BN pair; padding rule of networks/layers_op.py:10-14 (pad = dilation if dilation>1)."""
     return nn.Sequential(
@@ -267,14 +300,31 @@ class ContextEncoder(nn.Module):
         if num_layers > 34:
             self.num_ch_enc[1:] *= 4
         self.encoder = ctor[num_layers](weights=None)
+        self.tensor_cores = False       # set by the owning model (feature_precision="3xf16")
+        self._tc_cache = {}
 
-    @staticmethod
-    def _block(blk, x):
-        """torchvision BasicBlock / Bottleneck in eval mode with folded BN and fused bias/residual/ReLU epilogues."""
+    def _packed3x3(self, blk, device):
+        """Bottleneck.conv2 (3x3, stride 1) packed for the planar tensor-core kernel; cached per block."""
+        key = (str(device), blk.conv2.weight.data_ptr(), blk.conv2.weight._version, blk.bn2.weight._version,
+               blk.bn2.running_var._version)
+        ent = self._tc_cache.get(id(blk))
+        if ent is None or ent[0] != key:
+            ent = (key, _pack3x3(blk.conv2, blk.bn2, "relu", device))
+            self._tc_cache[id(blk)] = ent
+        return ent[1]
+
+    def _block(self, blk, x):
+        """torchvision BasicBlock / Bottleneck in eval mode with folded BN and fused bias/residual/ReLU epilogues; with
+        ``tensor_cores`` the stride-1 3x3 convolution of a Bottleneck runs on the planar tcgen05 kernel."""
+        from . import ops
         identity = x if blk.downsample is None else _folded(x, blk.downsample[0], blk.downsample[1])
         y = _folded(x, blk.conv1, blk.bn1, relu=True)
         if hasattr(blk, "conv3"):
-            y = _folded(y, blk.conv2, blk.bn2, relu=True)
+            pcs = self._packed3x3(blk, x.device) if (self.tensor_cores and x.is_cuda) else None
+            if pcs is not None:
+                y = ops.vol4_to_nchw(_run3x3(pcs, ops.nchw_to_vol4(y)))
+            else:
+                y = _folded(y, blk.conv2, blk.bn2, relu=True)
             return _folded(y, blk.conv3, blk.bn3, relu=True, residual=identity)
         return _folded(y, blk.conv2, blk.bn2, relu=True, residual=identity)
 
@@ -338,7 +388,38 @@ class ContextDecoder2D(nn.Module):
         self.upconv_0_1 = _UpBlock(dec[0], dec[0])
         self.dispconv_0 = nn.Conv2d(dec[0], 1, 3, 1, 1, 1, bias=True)
 
+    tensor_cores = False                # set by the owning model (feature_precision="3xf16")
+
+    def _packed(self, device):
+        """The decoder's 3x3 conv+BN+ReLU layers packed for the planar tensor-core kernel (None entries: shapes it does not
+        take, e.g. a depth-plane count that is not a multiple of 16)."""
+        probe = self.upconv_4_0.conv[0].weight
+        key = (str(device), probe.data_ptr(), probe._version, self.upconv_2_1.conv[0].weight._version,
+               self.upconv_1_1.conv[1].running_var._version)
+        if getattr(self, "_tc_key", None) != key:
+            names = ("upconv_4_0", "upconv_4_1", "upconv_3_0", "upconv_3_1", "upconv_2_0", "upconv_2_1", "upconv_1_0", "upconv_1_1")
+            self._tc_packed = {n: _pack3x3(getattr(self, n).conv[0], getattr(self, n).conv[1], "relu", device) for n in names}
+            self._tc_key = key
+        return self._tc_packed
+
+    def _use_tc(self, x, names):
+        if not (self.tensor_cores and x.is_cuda and not self.training):
+            return None
+        P = self._packed(x.device)
+        return P if all(P[n] is not None for n in names) else None
+
     def context(self, maps):
+        from . import ops
+        P = self._use_tc(maps[4], ("upconv_4_0", "upconv_4_1", "upconv_3_0", "upconv_3_1", "upconv_2_0", "upconv_2_1"))
+        if P is not None and all(m.shape[1] % 16 == 0 for m in maps[1:]):
+            # same layers, planar tcgen05 kernel: torch.cat becomes a second input segment, activations stay in vol4
+            x = _run3x3(P["upconv_4_0"], ops.nchw_to_vol4(maps[4].contiguous()))
+            x = _run3x3(P["upconv_4_1"], _up2_vol4(x), in1=ops.nchw_to_vol4(maps[3].contiguous()))
+            x = _run3x3(P["upconv_3_0"], x)
+            x = _run3x3(P["upconv_3_1"], _up2_vol4(x), in1=ops.nchw_to_vol4(maps[2].contiguous()))
+            x = _run3x3(P["upconv_2_0"], x)
+            x = _run3x3(P["upconv_2_1"], _up2_vol4(x), in1=ops.nchw_to_vol4(maps[1].contiguous()))
+            return ops.vol4_to_nchw(x)
         x = self.upconv_4_0(maps[4])
         x = self.upconv_4_1(torch.cat([_up2(x), maps[3]], 1))
         x = self.upconv_3_0(x)
@@ -348,8 +429,14 @@ class ContextDecoder2D(nn.Module):
 
     def refine(self, semantic_vs, fused_logits, skip_half):
         """fused_logits: [B*T, D, H/4, W/4] raw logits of stereo_head1 (ReLU applied here, :268)."""
-        x = self.upconv_1_0(torch.cat([semantic_vs, F.relu(fused_logits)], dim=1))
-        x = self.upconv_1_1(torch.cat([_up2(x), skip_half], 1))
+        from . import ops
+        P = self._use_tc(semantic_vs, ("upconv_1_0", "upconv_1_1"))
+        if P is not None and semantic_vs.shape[1] % 16 == 0 and skip_half.shape[1] % 16 == 0:
+            x = _run3x3(P["upconv_1_0"], ops.nchw_to_vol4(semantic_vs.contiguous()), in1=ops.nchw_to_vol4(F.relu(fused_logits)))
+            x = ops.vol4_to_nchw(_run3x3(P["upconv_1_1"], _up2_vol4(x), in1=ops.nchw_to_vol4(skip_half.contiguous())))
+        else:
+            x = self.upconv_1_0(torch.cat([semantic_vs, F.relu(fused_logits)], dim=1))
+            x = self.upconv_1_1(torch.cat([_up2(x), skip_half], 1))
         depth_half = _up2(self.depth_max * torch.sigmoid(self.dispconv_1(x)))
         x = self.upconv_0_1(_up2(self.upconv_0_0(x)))
         depth_full = self.depth_max * torch.sigmoid(self.dispconv_0(x))

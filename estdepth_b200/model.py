@@ -118,6 +118,9 @@ class DepthNetHybrid(nn.Module):
         self.semanticFeature = ContextEncoder(resnet)
         self.CostRegNet = HybridDecoder(self.semanticFeature.num_ch_enc, self.ndepths, self.depth_max,
                                         self.IF_EST_transformer)
+        # the stride-1 3x3 convolutions of the context encoder's bottlenecks and of the 2-D decoder / refinement follow
+        # the same switch as the matching-feature net
+        self.semanticFeature.tensor_cores = self.CostRegNet.tensor_cores = (feature_precision == "3xf16")
         self.pre0 = _conv_bn3(64, 32, 1)
         self.pre1 = _conv_bn_act3(32, 32, nn.ReLU(inplace=True))
         self.pre2 = _conv_bn3(32, 32, 3)

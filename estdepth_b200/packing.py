@@ -162,9 +162,25 @@ def attach_tc(pc):
 
 
 def pack_conv2d(weight, scale, shift, act, device, cout_slice=64):
-    """2-D 3x3 conv [Cout,Cin,3,3] with folded per-channel affine -> list of PackedConv, one per ``cout_slice`` output
-    channels (the planar tensor-core kernel is specialised for 64 / 32 output channels; wider layers run as slices
-    writing adjacent chunk ranges of the output tensor)."""
+    """2-D 3x3 conv [Cout,Cin,3,3] with folded per-channel affine -> list with ONE PackedConv for conv2d_tc.cu.
+
+    The planar tensor-core kernel is specialised for 64 / 32 / 16 output channels per accumulator; wider layers are packed
+    as Cout/64 slices [slice][nks][9][2][128 rows][16 B] that the kernel runs as independent units of one launch
+    (cout_pad = 64 * slices).  (A list is returned for the callers that iterate over per-launch pieces.)"""
+    cout, cin = weight.shape[0], weight.shape[1]
+    if cout > cout_slice:
+        assert cout_slice == 64, "only 64-channel slices can be combined in one launch"
+        pieces = _pack_conv2d_slices(weight, scale, shift, act, device, 64)
+        total = 64 * len(pieces)
+        pc = PackedConv(None, torch.cat([q.scale for q in pieces]), torch.cat([q.shift for q in pieces]), (cin + 3) // 4, total,
+                        (cout + 3) // 4, total, act, act, cin=cin, cout=cout, cout_pad_tc=total)
+        pc.weight_f16 = torch.cat([q.weight_f16.reshape(-1) for q in pieces]).contiguous()
+        pc.scale_f16 = torch.cat([q.scale_f16 for q in pieces]).contiguous()
+        return [pc]
+    return _pack_conv2d_slices(weight, scale, shift, act, device, cout_slice)
+
+
+def _pack_conv2d_slices(weight, scale, shift, act, device, cout_slice):
     cout, cin = weight.shape[0], weight.shape[1]
     out = []
     for c0 in range(0, cout, cout_slice):

@@ -275,7 +275,7 @@ def test_conv2d_planar_vs_torch_cpu(case):
     shift = torch.randn(cout, generator=g) / 3
     res = torch.randn(N, cout, H, W, generator=g)
     want = (torch.relu(F.conv2d(x.double(), w.double(), None, 1, dil, dil) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)) + res).float()
-    pcs = packing.pack_conv2d(w, scale, shift, "relu", DEV, cout_slice=64 if cout >= 64 else (32 if cout >= 32 else 16))
+    pcs = packing.pack_conv2d(w, scale, shift, "relu", DEV, cout_slice=64 if cout > 32 else (32 if cout > 16 else 16))
     x4 = ops.nchw_to_vol4(x.to(DEV))
     ins = [x4[:cin_seg[0] // 4].contiguous()] + ([x4[cin_seg[0] // 4:].contiguous()] if len(cin_seg) > 1 else [])
     out4 = torch.full((cout // 4, N, H, W, 4), float("nan"), device=DEV)
