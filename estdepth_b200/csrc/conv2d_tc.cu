@@ -37,25 +37,30 @@ constexpr int EPI_WARPS = 8, SPLIT_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32, SPLIT_THREADS = SPLIT_WARPS * 32;
 constexpr int THREADS = 128 + EPI_THREADS + SPLIT_THREADS;       // warps 0-3 control, 4-11 epilogue, 12-19 splitters
 constexpr int FIRST_SPLIT_WARP = 4 + EPI_WARPS;
-constexpr int MAX_COUT_TOTAL = 512;
 
-template <int COUT_, int DIL_>
+// COUT output channels per accumulator (slice), DIL dilation of the taps, TAPS 9 (3x3) or 1 (1x1: the pointwise convolutions
+// of the ResNet bottlenecks -- same pipeline without a halo; with a single tap per 16 channels the stage is dominated by the
+// TMA fill and the hi/lo split rather than by the MMAs, still several times faster than the fp32 CUDA-core GEMM)
+template <int COUT_, int DIL_, int TAPS_>
 struct Shape {
-    static constexpr int COUT = COUT_, DIL = DIL_, MT = 2;
+    static constexpr int COUT = COUT_, DIL = DIL_, TAPS = TAPS_, MT = 2;
+    static constexpr int PAD = (TAPS == 9) ? DIL : 0;
     static constexpr int TILE_H = 16, TILE_W = 8 * MT;
-    static constexpr int HALO_H = TILE_H + 2 * DIL, HALO_W = TILE_W + 2 * DIL, HALO_VOX = HALO_H * HALO_W;
+    static constexpr int HALO_H = TILE_H + 2 * PAD, HALO_W = TILE_W + 2 * PAD, HALO_VOX = HALO_H * HALO_W;
+    static constexpr int MAX_COUT = (TAPS == 9) ? 512 : 2048;     // widest layer (all slices) one launch takes
     static constexpr int KGROUP_BYTES = HALO_VOX * 16;
     static constexpr int A_BYTES = 4 * KGROUP_BYTES;
     static constexpr int N_ALL = 2 * COUT;
     static constexpr int W_TAP_BYTES = 2 * N_ALL * 16;            // [2 K-groups][N_ALL rows][16 B]
-    static constexpr int W_BYTES = 9 * W_TAP_BYTES;
+    static constexpr int W_BYTES = TAPS * W_TAP_BYTES;
     static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES + 127) / 128 * 128;
-    static constexpr int STAGES = (4 * STAGE_BYTES + 8192 <= 227 * 1024) ? 4 : 3;
+    static constexpr int STAGES = (6 * STAGE_BYTES + 20480 <= 227 * 1024) ? 6 : (4 * STAGE_BYTES + 8192 <= 227 * 1024) ? 4 : 3;
     static constexpr int COLS_PER_UNIT = MT * N_ALL;
     static constexpr int TMEM_COLS = (2 * COLS_PER_UNIT <= 128) ? 128 : (2 * COLS_PER_UNIT <= 256) ? 256 : 512;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;
     static_assert(2 * COLS_PER_UNIT <= 512, "two accumulator buffers must fit TMEM");
-    static_assert(SMEM + 6144 <= 227 * 1024, "stages must fit shared memory");
+    static_assert(SMEM + 2 * 4 * MAX_COUT + 2048 <= 227 * 1024, "stages must fit shared memory");
+    static_assert(TAPS == 9 || TAPS == 1, "3x3 or 1x1");
     static_assert(COUT % 16 == 0 && COUT <= 64, "bad COUT");
 };
 
@@ -82,7 +87,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     uint64_t* acc_full = bars + 3 * STAGES; // [2]
     uint64_t* acc_empty = acc_full + 2;     // [2]
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    __shared__ __align__(16) float s_scale[MAX_COUT_TOTAL], s_shift[MAX_COUT_TOTAL];
+    __shared__ __align__(16) float s_scale[S::MAX_COUT], s_shift[S::MAX_COUT];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nks = p.nks;
@@ -124,8 +129,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                     unsigned char* stage = smem + (size_t)s * S::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full[s], (uint32_t)(A_BYTES + S::W_BYTES));
                     const int chunk = 4 * ks;
-                    if (chunk < p.in0_chunks) tma_load_4d(stage, &map0, &full[s], 4 * (w0 - S::DIL), h0 - S::DIL, d, chunk);
-                    else                      tma_load_4d(stage, &map1, &full[s], 4 * (w0 - S::DIL), h0 - S::DIL, d, chunk - p.in0_chunks);
+                    if (chunk < p.in0_chunks) tma_load_4d(stage, &map0, &full[s], 4 * (w0 - S::PAD), h0 - S::PAD, d, chunk);
+                    else                      tma_load_4d(stage, &map1, &full[s], 4 * (w0 - S::PAD), h0 - S::PAD, d, chunk - p.in0_chunks);
                     bulk_load(stage + A_BYTES, wsl + (size_t)ks * (S::W_BYTES / 4), (uint32_t)S::W_BYTES, &full[s]);
                 }
             }
@@ -150,10 +155,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                 const uint32_t later = (ks == 0) ? 0u : 1u;        // the very first MMA of a unit overwrites the accumulator
                 if (leader) {
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
+                    for (int tap = 0; tap < S::TAPS; ++tap) {
 #pragma unroll
                         for (int mt = 0; mt < S::MT; ++mt) {
-                            const uint64_t a_off = (uint64_t)((tap / 3) * S::DIL * HALO_W + 8 * mt + (tap % 3) * S::DIL);
+                            const uint64_t a_off = (uint64_t)((tap / 3) * S::DIL * HALO_W + 8 * mt + (tap % 3) * S::DIL);   // TAPS == 1: 8 * mt
                             const uint64_t b_off = (uint64_t)(tap * (S::W_TAP_BYTES >> 4));
                             const uint32_t acc = acc0 + (uint32_t)(mt * N_ALL);
                             umma<KIND_F16>(acc, a_hi_desc + a_off, b_desc + b_off, idesc_all, tap == 0 ? later : 1u);
@@ -252,6 +257,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                         for (int i = 0; i < 4; ++i) v[i] = tanhf(v[i]);
                     }
                     v[0] += r0[j].x; v[1] += r0[j].y; v[2] += r0[j].z; v[3] += r0[j].w;
+                    if (act == ESTD_ACT_ADD_RELU) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.0f);
+                    }
                     const size_t off = ((size_t)ch * vox + pos) * 4;
                     float* dst = (ch < ep.out0_chunks) ? ep.out0 + off : ep.out1 + (off - (size_t)ep.out0_chunks * vox * 4);
                     st4(dst, make_float4(v[0] * ep.post_scale, v[1] * ep.post_scale, v[2] * ep.post_scale, v[3] * ep.post_scale));
@@ -315,11 +324,14 @@ int dispatch_planar(const estd_conv3d_desc* d, cudaStream_t stream, bool count_o
                  "estd_conv3d: planar convolutions are implemented for the fp16 split only");
     const int dil = d->dilation > 0 ? d->dilation : 1;
     const int C = d->cout_pad;
-    ESTD_REQUIRE(C <= MAX_COUT_TOTAL, "estd_conv3d(planar): cout_pad %d exceeds %d", C, MAX_COUT_TOTAL);
-#define ESTD_PLANAR(COUT, DIL) if ((C == COUT || (COUT == 64 && C > 64 && C % 64 == 0)) && dil == DIL) return launch<Shape<COUT, DIL>>(d, stream, count_only, n_ctas)
-    ESTD_PLANAR(64, 1); ESTD_PLANAR(64, 2); ESTD_PLANAR(32, 1); ESTD_PLANAR(32, 2); ESTD_PLANAR(16, 1);
+    const int taps = d->planar == 2 ? 1 : 9;
+    ESTD_REQUIRE(C <= (taps == 9 ? 512 : 2048), "estd_conv3d(planar): cout_pad %d exceeds what one launch takes (%d)", C, taps == 9 ? 512 : 2048);
+#define ESTD_PLANAR(COUT, DIL, TAPS) if ((C == COUT || (COUT == 64 && C > 64 && C % 64 == 0)) && dil == DIL && taps == TAPS) \
+        return launch<Shape<COUT, DIL, TAPS>>(d, stream, count_only, n_ctas)
+    ESTD_PLANAR(64, 1, 9); ESTD_PLANAR(64, 2, 9); ESTD_PLANAR(32, 1, 9); ESTD_PLANAR(32, 2, 9); ESTD_PLANAR(16, 1, 9);
+    ESTD_PLANAR(64, 1, 1); ESTD_PLANAR(32, 1, 1);
 #undef ESTD_PLANAR
-    return fail(ESTD_EUNSUPPORTED, "estd_conv3d(planar): no kernel for cout_pad %d, dilation %d (cout_pad 16/32/64 or a multiple of 64, dilation 1/2)", C, dil);
+    return fail(ESTD_EUNSUPPORTED, "estd_conv3d(planar): no kernel for cout_pad %d, dilation %d, %d tap(s) (cout_pad 16/32/64 or a multiple of 64, dilation 1/2)", C, dil, taps);
 }
 
 }  // namespace estd

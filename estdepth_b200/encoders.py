@@ -98,24 +98,34 @@ def _bn_affine(bn):
 
 
 def _pack3x3(conv, bn, act, device):
-    """conv(3x3, stride 1)+BN -> packed planar tensor-core layer (packing.pack_conv2d), or None when the shape is not one the
-    kernel takes (input channels must come in whole 16-channel k-steps)."""
+    """conv(3x3 or 1x1, stride 1)+BN -> packed planar tensor-core layer (packing.pack_conv2d), or None when the shape is not
+    one the kernel takes (input channels must come in whole 16-channel k-steps)."""
     from . import packing
     w = conv.weight.detach()
-    if conv.kernel_size != (3, 3) or conv.stride != (1, 1) or conv.groups != 1 or w.shape[1] % 16 or conv.dilation not in ((1, 1), (2, 2)):
+    if conv.kernel_size not in ((3, 3), (1, 1)) or conv.stride != (1, 1) or conv.groups != 1 or w.shape[1] % 16 or w.shape[0] % 4 \
+            or conv.dilation not in ((1, 1), (2, 2)):
         return None
     s, b = _bn_affine(bn)
     return packing.pack_conv2d(w, s, b, act, device, cout_slice=64 if w.shape[0] > 32 else 32)
 
 
-def _run3x3(pcs, x4, out4=None, res4=None, dilation=1, in1=None):
+def _run3x3(pcs, x4, out4=None, res4=None, dilation=1, in1=None, taps=9):
     """One packed planar layer over vol4 maps [C/4, N, H, W, 4] (+ optional second input segment = torch.cat on channels)."""
     from . import ops
     pc = pcs[0]
     if out4 is None:
         out4 = torch.empty(pc.out_chunks, x4.shape[1], x4.shape[2], x4.shape[3], 4, device=x4.device, dtype=torch.float32)
-    ops.conv_planar(pc, x4, out4, res0=res4, dilation=dilation, in1=in1)
+    ops.conv_planar(pc, x4, out4, res0=res4, dilation=dilation, in1=in1, taps=taps)
     return out4
+
+
+def _as_vol4(t):
+    """NCHW feature map -> vol4, reusing the copy the encoder left on the tensor when there is one."""
+    from . import ops
+    cached = getattr(t, "_estd_vol4", None)
+    if cached is not None and cached.device == t.device and cached.shape[0] * 4 == t.shape[1]:
+        return cached
+    return ops.nchw_to_vol4(t.contiguous())
 
 
 def _up2_vol4(x4):
@@ -303,30 +313,57 @@ class ContextEncoder(nn.Module):
         self.tensor_cores = False       # set by the owning model (feature_precision="3xf16")
         self._tc_cache = {}
 
-    def _packed3x3(self, blk, device):
-        """Bottleneck.conv2 (3x3, stride 1) packed for the planar tensor-core kernel; cached per block."""
-        key = (str(device), blk.conv2.weight.data_ptr(), blk.conv2.weight._version, blk.bn2.weight._version,
-               blk.bn2.running_var._version)
+    def _packed_block(self, blk, device):
+        """Bottleneck layers packed for the planar tensor-core kernel (None where the shape is not taken: strided convs);
+        cached per block."""
+        key = (str(device), blk.conv2.weight.data_ptr(), blk.conv1.weight._version, blk.conv2.weight._version,
+               blk.conv3.weight._version, blk.bn2.running_var._version)
         ent = self._tc_cache.get(id(blk))
         if ent is None or ent[0] != key:
-            ent = (key, _pack3x3(blk.conv2, blk.bn2, "relu", device))
+            ent = (key, (_pack3x3(blk.conv1, blk.bn1, "relu", device), _pack3x3(blk.conv2, blk.bn2, "relu", device),
+                         _pack3x3(blk.conv3, blk.bn3, "add_relu", device)))
             self._tc_cache[id(blk)] = ent
         return ent[1]
 
-    def _block(self, blk, x):
-        """torchvision BasicBlock / Bottleneck in eval mode with folded BN and fused bias/residual/ReLU epilogues; with
-        ``tensor_cores`` the stride-1 3x3 convolution of a Bottleneck runs on the planar tcgen05 kernel."""
-        from . import ops
+    @staticmethod
+    def _block(blk, x):
+        """torchvision BasicBlock / Bottleneck in eval mode with folded BN and fused bias/residual/ReLU epilogues (cuDNN)."""
         identity = x if blk.downsample is None else _folded(x, blk.downsample[0], blk.downsample[1])
         y = _folded(x, blk.conv1, blk.bn1, relu=True)
         if hasattr(blk, "conv3"):
-            pcs = self._packed3x3(blk, x.device) if (self.tensor_cores and x.is_cuda) else None
-            if pcs is not None:
-                y = ops.vol4_to_nchw(_run3x3(pcs, ops.nchw_to_vol4(y)))
-            else:
-                y = _folded(y, blk.conv2, blk.bn2, relu=True)
+            y = _folded(y, blk.conv2, blk.bn2, relu=True)
             return _folded(y, blk.conv3, blk.bn3, relu=True, residual=identity)
         return _folded(y, blk.conv2, blk.bn2, relu=True, residual=identity)
+
+    def _stage_tc(self, stage, x):
+        """One ResNet stage of Bottlenecks with the 1x1 and the stride-1 3x3 convolutions on the planar tcgen05 kernel;
+        activations stay in vol4 inside the stage, only strided convolutions (conv2 / downsample of the first block) go
+        through cuDNN.  x: NCHW in; returns (NCHW out, vol4 out)."""
+        from . import ops
+        x4 = None
+        for blk in stage:
+            p1, p2, p3 = self._packed_block(blk, x.device if x is not None else x4.device)
+            if p1 is None or p3 is None:                               # not a shape the kernel takes: whole block on cuDNN
+                x = self._block(blk, x if x is not None else ops.vol4_to_nchw(x4))
+                x4 = None
+                continue
+            if x4 is None:
+                x4 = ops.nchw_to_vol4(x.contiguous())
+            if blk.downsample is None:
+                identity4 = x4
+            else:
+                xin = x if x is not None else ops.vol4_to_nchw(x4)
+                identity4 = ops.nchw_to_vol4(_folded(xin, blk.downsample[0], blk.downsample[1]))
+            y4 = _run3x3(p1, x4, taps=1)
+            if p2 is not None:
+                y4 = _run3x3(p2, y4)
+            else:
+                y4 = ops.nchw_to_vol4(_folded(ops.vol4_to_nchw(y4), blk.conv2, blk.bn2, relu=True))
+            x4 = _run3x3(p3, y4, res4=identity4, taps=1)
+            x = None
+        if x is None:
+            x = ops.vol4_to_nchw(x4)
+        return x, x4
 
     def forward(self, x):
         e = self.encoder
@@ -339,8 +376,13 @@ class ContextEncoder(nn.Module):
         maps = [_folded(x, e.conv1, e.bn1, relu=True)]
         x = e.maxpool(maps[-1])
         for stage in (e.layer1, e.layer2, e.layer3, e.layer4):
-            for blk in stage:
-                x = self._block(blk, x)
+            if self.tensor_cores and x.is_cuda and hasattr(stage[0], "conv3"):
+                x, x4 = self._stage_tc(stage, x)
+                if x4 is not None:
+                    x._estd_vol4 = x4          # the decoder takes the vol4 copy directly (saves a layout pass per map)
+            else:
+                for blk in stage:
+                    x = self._block(blk, x)
             maps.append(x)
         return maps
 
@@ -413,12 +455,12 @@ class ContextDecoder2D(nn.Module):
         P = self._use_tc(maps[4], ("upconv_4_0", "upconv_4_1", "upconv_3_0", "upconv_3_1", "upconv_2_0", "upconv_2_1"))
         if P is not None and all(m.shape[1] % 16 == 0 for m in maps[1:]):
             # same layers, planar tcgen05 kernel: torch.cat becomes a second input segment, activations stay in vol4
-            x = _run3x3(P["upconv_4_0"], ops.nchw_to_vol4(maps[4].contiguous()))
-            x = _run3x3(P["upconv_4_1"], _up2_vol4(x), in1=ops.nchw_to_vol4(maps[3].contiguous()))
+            x = _run3x3(P["upconv_4_0"], _as_vol4(maps[4]))
+            x = _run3x3(P["upconv_4_1"], _up2_vol4(x), in1=_as_vol4(maps[3]))
             x = _run3x3(P["upconv_3_0"], x)
-            x = _run3x3(P["upconv_3_1"], _up2_vol4(x), in1=ops.nchw_to_vol4(maps[2].contiguous()))
+            x = _run3x3(P["upconv_3_1"], _up2_vol4(x), in1=_as_vol4(maps[2]))
             x = _run3x3(P["upconv_2_0"], x)
-            x = _run3x3(P["upconv_2_1"], _up2_vol4(x), in1=ops.nchw_to_vol4(maps[1].contiguous()))
+            x = _run3x3(P["upconv_2_1"], _up2_vol4(x), in1=_as_vol4(maps[1]))
             return ops.vol4_to_nchw(x)
         x = self.upconv_4_0(maps[4])
         x = self.upconv_4_1(torch.cat([_up2(x), maps[3]], 1))

@@ -102,8 +102,10 @@ def pack_weight_f16(packed, cout_pad_tc=None):
     hi = ws.to(torch.float16)
     lo = (ws - hi.to(torch.float32)).to(torch.float16)
 
+    tpp = 9 if taps % 9 == 0 else taps                 # taps per plane (a 1x1 convolution has one)
+
     def arrange(x):      # [taps = dd*9+tap9][16*nks = ks*16+kg*8+e][C] -> [dd][ks][tap9][kg][C][e]
-        return x.reshape(taps // 9, 9, nks, 2, 8, C).permute(0, 2, 1, 3, 5, 4)
+        return x.reshape(taps // tpp, tpp, nks, 2, 8, C).permute(0, 2, 1, 3, 5, 4)
 
     both = torch.cat([arrange(hi), arrange(lo)], dim=4)                       # [planes][nks][9][2][2C][8] fp16
     return both.contiguous().view(torch.float32), k
@@ -185,7 +187,8 @@ def _pack_conv2d_slices(weight, scale, shift, act, device, cout_slice):
     out = []
     for c0 in range(0, cout, cout_slice):
         n = min(cout_slice, cout - c0)
-        w = weight[c0:c0 + n].reshape(n, cin, 9).permute(2, 1, 0).to(device=device, dtype=torch.float32).contiguous()   # [9][Cin][n]
+        taps = weight.shape[2] * weight.shape[3]           # 9 (3x3) or 1 (1x1)
+        w = weight[c0:c0 + n].reshape(n, cin, taps).permute(2, 1, 0).to(device=device, dtype=torch.float32).contiguous()   # [taps][Cin][n]
         wf16, k = pack_weight_f16(w, cout_slice)
         s = torch.zeros(cout_slice, dtype=torch.float32, device=device)
         b = torch.zeros(cout_slice, dtype=torch.float32, device=device)

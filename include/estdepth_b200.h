@@ -41,6 +41,7 @@ extern "C" {
 #define ESTD_ACT_NONE 0
 #define ESTD_ACT_RELU 1
 #define ESTD_ACT_TANH 2
+#define ESTD_ACT_ADD_RELU 3          /* ReLU applied AFTER the residual add (ResNet blocks); planar convolutions only */
 
 #define ESTD_MAX_SOURCES 8          /* max N of the EST attention */
 
@@ -101,7 +102,8 @@ typedef struct estd_conv3d_desc {
     const float* weight_tc;               /* tensor-core packing [3][nks][9][2][2*cout_pad rows][16 bytes] (hi|lo split), else NULL */
     int precision;                        /* ESTD_PREC_*; cout_pad is 16/32/40 for FP32 and 16/32/48 for the tensor-core paths */
     int* status;                          /* optional device int, OR-ed with 1 on an fp16 range violation (ESTD_PREC_3XF16) */
-    int planar;                           /* 0: 3x3x3 filter.  1: 1x3x3 filter applied per plane = 2-D 3x3 convolution over a stack of
+    int planar;                           /* 0: 3x3x3 filter.  2: 1x1 (pointwise) 2-D convolution, same packing with a single tap.
+                                             1: 1x3x3 filter applied per plane = 2-D 3x3 convolution over a stack of
                                              D feature maps (matching-feature net, context decoder); weight_tc is [nks][9][2][2*cout_pad][16 B],
                                              any number of input chunks, cout_pad 16/32/64 (wider layers: one call per 64-channel
                                              slice); fp16 split only; no gn_partials / res1 */

@@ -258,6 +258,9 @@ PLANAR_CASES = [
     ("320to128", (192, 128), 128, 1, 2, 30, 40),
     ("1280to256_small", (256, 1024), 256, 1, 3, 15, 20),
     ("128to33pad", (128,), 48, 1, 1, 16, 16),
+    ("1x1_256to64", (256,), 64, 0, 3, 40, 56),
+    ("1x1_64to256", (64,), 256, 0, 3, 33, 47),
+    ("1x1_512to2048_small", (512,), 2048, 0, 3, 15, 20),
 ]
 
 
@@ -269,13 +272,17 @@ def test_conv2d_planar_vs_torch_cpu(case):
     name, cin_seg, cout, dil, N, H, W = case
     g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)
     cin = sum(cin_seg)
+    k = 3 if dil > 0 else 1                                # dilation 0 marks the 1x1 (pointwise) cases
     x = torch.randn(N, cin, H, W, generator=g)
-    w = torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+    w = torch.randn(cout, cin, k, k, generator=g) / (k * k * cin) ** 0.5
     scale = torch.rand(cout, generator=g) + 0.5
     shift = torch.randn(cout, generator=g) / 3
     res = torch.randn(N, cout, H, W, generator=g)
-    want = (torch.relu(F.conv2d(x.double(), w.double(), None, 1, dil, dil) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)) + res).float()
-    pcs = packing.pack_conv2d(w, scale, shift, "relu", DEV, cout_slice=64 if cout > 32 else (32 if cout > 16 else 16))
+    y = F.conv2d(x.double(), w.double(), None, 1, dil, max(dil, 1)) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    # 3x3 layers: ReLU then residual (PSM blocks, quirk Q12); 1x1 layers: residual then ReLU (ResNet bottleneck)
+    want = (torch.relu(y) + res).float() if k == 3 else torch.relu(y + res).float()
+    pcs = packing.pack_conv2d(w, scale, shift, "relu" if k == 3 else "add_relu", DEV,
+                              cout_slice=64 if cout > 32 else (32 if cout > 16 else 16))
     x4 = ops.nchw_to_vol4(x.to(DEV))
     ins = [x4[:cin_seg[0] // 4].contiguous()] + ([x4[cin_seg[0] // 4:].contiguous()] if len(cin_seg) > 1 else [])
     out4 = torch.full((cout // 4, N, H, W, 4), float("nan"), device=DEV)
@@ -283,7 +290,8 @@ def test_conv2d_planar_vs_torch_cpu(case):
     step = pcs[0].cout_pad // 4
     for i, pc in enumerate(pcs):
         lo, hi = step * i, step * i + pc.out_chunks
-        ops.conv_planar(pc, ins[0], out4[lo:hi], res0=res4[lo:hi], dilation=dil, in1=ins[1] if len(ins) > 1 else None)
+        ops.conv_planar(pc, ins[0], out4[lo:hi], res0=res4[lo:hi], dilation=max(dil, 1), in1=ins[1] if len(ins) > 1 else None,
+                        taps=k * k)
     got = ops.vol4_to_nchw(out4).cpu()
     assert torch.isfinite(got).all()
     err = (got - want).abs().max().item()
