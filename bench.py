@@ -318,14 +318,22 @@ def run_ours(args):
     conv_name = "conv3d_" + model.precision
     conv = kernels.get(conv_name, dom[1])
     mma_per_flop = {"fp32": 0.0, "3xtf32": 3.0, "3xf16": 3.0, "3xf16r": 3.0}[model.precision]
-    roofline = {"kernel": "estd conv3d_tc_kernel (3x3x3 implicit GEMM, %s)" % model.precision if conv_name in kernels else dom[0], "bound": "tensor",
+    # dram__bytes_read.sum + dram__bytes_write.sum of one 32->32 launch at cfg2 size from the committed ncu --set full capture
+    # (profiles/kernels_r01_final.txt): 256.9 + 119.0 MB against 314.6 MB algorithmic = the 18x34 / 16x32 halo re-read
+    traffic = 375.8e6 if (args.workload == "cfg2" and model.precision == "3xf16r") else None
+    kname = {"3xf16r": "estd::ring::conv3d_ring_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule, fp16 two-term split)"}.get(
+        model.precision, "estd conv3d kernel (%s)" % model.precision)
+    roofline = {"kernel": kname if conv_name in kernels else dom[0], "bound": "tensor",
                 "achieved": conv.get("TFLOPps"), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": (conv.get("TFLOPps") or 0.0) / peaks["bf16_sustained"], "traffic": None,
+                "frac": (conv.get("TFLOPps") or 0.0) / peaks["bf16_sustained"], "traffic": traffic,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "note": "achieved = ALGORITHMIC fp32 conv flops (54*Cin*Cout*Vx) / CUDA-event time, averaged over the step's launches; "
-                        "the error-compensated split issues %.0fx that many tensor-core flops; peak = dense bf16 (cuBLAS). "
+                        "the error-compensated split issues %.0fx that many tensor-core flops (tensor_flops_issued_TFLOPps / peak = the "
+                        "tensor-pipe fraction); peak = dense bf16 (cuBLAS).  The kernel is bound by the shared-memory pipe that feeds the "
+                        "tensor core (an M=128 N=96 K=16 MMA needs 56 wavefronts of operands for 48 cycles of math, profiles/README.md). "
                         "share of step = %.1f%%" % (mma_per_flop, 100.0 * conv["share_ms_per_step"] / sum(k["share_ms_per_step"] for k in kernels.values())),
-                "tensor_flops_issued_TFLOPps": (conv.get("TFLOPps") or 0.0) * mma_per_flop}
+                "tensor_flops_issued_TFLOPps": (conv.get("TFLOPps") or 0.0) * mma_per_flop,
+                "tensor_pipe_frac_issued": (conv.get("TFLOPps") or 0.0) * mma_per_flop / peaks["bf16_sustained"]}
     cpu_base, _ = (None, None)
     if not args.no_cpu_baseline:
         cpu_base, _ = oracle_sample(args.workload, 1, 1, budget_s=60.0)
