@@ -255,6 +255,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                     } else if (act == ESTD_ACT_TANH) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) v[i] = tanhf(v[i]);
+                    } else if (act == ESTD_ACT_SIGMOID) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[i] = sigmoidf_acc(v[i]);
                     }
                     v[0] += r0[j].x; v[1] += r0[j].y; v[2] += r0[j].z; v[3] += r0[j].w;
                     if (act == ESTD_ACT_ADD_RELU) {

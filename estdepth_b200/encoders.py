@@ -98,24 +98,29 @@ def _bn_affine(bn):
 
 
 def _pack3x3(conv, bn, act, device):
-    """conv(3x3 or 1x1, stride 1)+BN -> packed planar tensor-core layer (packing.pack_conv2d), or None when the shape is not
-    one the kernel takes (input channels must come in whole 16-channel k-steps)."""
+    """conv(3x3 or 1x1, stride 1)+BN (bn=None: conv with bias) -> packed planar tensor-core layer (packing.pack_conv2d), or
+    None when the shape is not one the kernel takes (input channels must come in whole 16-channel k-steps)."""
     from . import packing
     w = conv.weight.detach()
-    if conv.kernel_size not in ((3, 3), (1, 1)) or conv.stride != (1, 1) or conv.groups != 1 or w.shape[1] % 16 or w.shape[0] % 4 \
+    if conv.kernel_size not in ((3, 3), (1, 1)) or conv.stride != (1, 1) or conv.groups != 1 or w.shape[1] % 16 \
             or conv.dilation not in ((1, 1), (2, 2)):
         return None
-    s, b = _bn_affine(bn)
-    return packing.pack_conv2d(w, s, b, act, device, cout_slice=64 if w.shape[0] > 32 else 32)
+    if bn is not None:
+        s, b = _bn_affine(bn)
+    else:
+        s = torch.ones(w.shape[0])
+        b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0])
+    cout = w.shape[0]
+    return packing.pack_conv2d(w, s, b, act, device, cout_slice=64 if cout > 32 else 32 if cout > 16 else 16)
 
 
-def _run3x3(pcs, x4, out4=None, res4=None, dilation=1, in1=None, taps=9):
+def _run3x3(pcs, x4, out4=None, res4=None, dilation=1, in1=None, taps=9, post_scale=1.0):
     """One packed planar layer over vol4 maps [C/4, N, H, W, 4] (+ optional second input segment = torch.cat on channels)."""
     from . import ops
     pc = pcs[0]
     if out4 is None:
         out4 = torch.empty(pc.out_chunks, x4.shape[1], x4.shape[2], x4.shape[3], 4, device=x4.device, dtype=torch.float32)
-    ops.conv_planar(pc, x4, out4, res0=res4, dilation=dilation, in1=in1, taps=taps)
+    ops.conv_planar(pc, x4, out4, res0=res4, dilation=dilation, in1=in1, taps=taps, post_scale=post_scale)
     return out4
 
 
@@ -439,8 +444,11 @@ class ContextDecoder2D(nn.Module):
         key = (str(device), probe.data_ptr(), probe._version, self.upconv_2_1.conv[0].weight._version,
                self.upconv_1_1.conv[1].running_var._version)
         if getattr(self, "_tc_key", None) != key:
-            names = ("upconv_4_0", "upconv_4_1", "upconv_3_0", "upconv_3_1", "upconv_2_0", "upconv_2_1", "upconv_1_0", "upconv_1_1")
+            names = ("upconv_4_0", "upconv_4_1", "upconv_3_0", "upconv_3_1", "upconv_2_0", "upconv_2_1", "upconv_1_0", "upconv_1_1",
+                     "upconv_0_0", "upconv_0_1")
             self._tc_packed = {n: _pack3x3(getattr(self, n).conv[0], getattr(self, n).conv[1], "relu", device) for n in names}
+            for n in ("dispconv_1", "dispconv_0"):          # 3x3 conv + bias -> sigmoid, x depth_max in the epilogue
+                self._tc_packed[n] = _pack3x3(getattr(self, n), None, "sigmoid", device)
             self._tc_key = key
         return self._tc_packed
 
@@ -472,13 +480,18 @@ class ContextDecoder2D(nn.Module):
     def refine(self, semantic_vs, fused_logits, skip_half):
         """fused_logits: [B*T, D, H/4, W/4] raw logits of stereo_head1 (ReLU applied here, :268)."""
         from . import ops
-        P = self._use_tc(semantic_vs, ("upconv_1_0", "upconv_1_1"))
+        P = self._use_tc(semantic_vs, ("upconv_1_0", "upconv_1_1", "upconv_0_0", "upconv_0_1", "dispconv_1", "dispconv_0"))
         if P is not None and semantic_vs.shape[1] % 16 == 0 and skip_half.shape[1] % 16 == 0:
+            # whole refinement on the planar tcgen05 kernel: cat -> second input segment, sigmoid * depth_max in the epilogue
             x = _run3x3(P["upconv_1_0"], ops.nchw_to_vol4(semantic_vs.contiguous()), in1=ops.nchw_to_vol4(F.relu(fused_logits)))
-            x = ops.vol4_to_nchw(_run3x3(P["upconv_1_1"], _up2_vol4(x), in1=ops.nchw_to_vol4(skip_half.contiguous())))
-        else:
-            x = self.upconv_1_0(torch.cat([semantic_vs, F.relu(fused_logits)], dim=1))
-            x = self.upconv_1_1(torch.cat([_up2(x), skip_half], 1))
+            x = _run3x3(P["upconv_1_1"], _up2_vol4(x), in1=ops.nchw_to_vol4(skip_half.contiguous()))
+            d1 = _run3x3(P["dispconv_1"], x, post_scale=self.depth_max)                  # [1 chunk, N, H/2, W/2, 4]
+            depth_half = _up2(d1[0, ..., 0].unsqueeze(1))
+            x = _run3x3(P["upconv_0_1"], _up2_vol4(_run3x3(P["upconv_0_0"], x)))
+            depth_full = _run3x3(P["dispconv_0"], x, post_scale=self.depth_max)[0, ..., 0].unsqueeze(1).contiguous()
+            return depth_half, depth_full
+        x = self.upconv_1_0(torch.cat([semantic_vs, F.relu(fused_logits)], dim=1))
+        x = self.upconv_1_1(torch.cat([_up2(x), skip_half], 1))
         depth_half = _up2(self.depth_max * torch.sigmoid(self.dispconv_1(x)))
         x = self.upconv_0_1(_up2(self.upconv_0_0(x)))
         depth_full = self.depth_max * torch.sigmoid(self.dispconv_0(x))

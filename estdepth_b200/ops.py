@@ -18,7 +18,7 @@ import torch
 from . import _lib
 from ._lib import ConvDesc, check
 
-ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2, "add_relu": 3}
+ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2, "add_relu": 3, "sigmoid": 4}
 PRECISION = {"fp32": 0, "3xtf32": 1, "3xf16": 2, "3xf16r": 3}
 MAX_SOURCES = 8
 # default arithmetic of conv3d: "fp32" = exact CUDA-core kernel, "3xtf32" / "3xf16" = error-compensated splits on tcgen05,
@@ -241,10 +241,10 @@ def conv3d(pc, in0, out0, in1=None, out1=None, res0=None, res1=None, post_scale=
     return out0
 
 
-def conv_planar(pc, in0, out0, res0=None, dilation=1, in1=None, taps=9):
+def conv_planar(pc, in0, out0, res0=None, dilation=1, in1=None, taps=9, post_scale=1.0):
     """2-D 3x3 (taps=9; stride 1, padding = dilation) or 1x1 (taps=1) convolution over a stack of N maps held as vol4
     [C/4,N,H,W,4], with folded affine + activation (+ residual), on the tensor cores (fp16 two-term split).  Returns out0."""
-    d = _conv_desc(pc, in0, in1, out0, None, res0, None, 1.0, None, "3xf16", planar=1 if taps == 9 else 2, dilation=dilation)
+    d = _conv_desc(pc, in0, in1, out0, None, res0, None, post_scale, None, "3xf16", planar=1 if taps == 9 else 2, dilation=dilation)
     t = _pb()
     check(_lib.get().estd_conv3d(ctypes.byref(d), _stream()), "estd_conv3d(planar)")
     vox = float(d.D) * d.H * d.W

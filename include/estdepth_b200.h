@@ -41,6 +41,7 @@ extern "C" {
 #define ESTD_ACT_NONE 0
 #define ESTD_ACT_RELU 1
 #define ESTD_ACT_TANH 2
+#define ESTD_ACT_SIGMOID 4           /* 1/(1+exp(-x)) (the dispconv heads, hybrid_depth_decoder.py:279,290); planar convolutions only */
 #define ESTD_ACT_ADD_RELU 3          /* ReLU applied AFTER the residual add (ResNet blocks); planar convolutions only */
 
 #define ESTD_MAX_SOURCES 8          /* max N of the EST attention */
