@@ -97,12 +97,15 @@ def _bn_affine(bn):
     return scale.float(), shift.float()
 
 
-def _pack3x3(conv, bn, act, device):
+def _pack3x3(conv, bn, act, device, any_stride=False):
     """conv(3x3 or 1x1, stride 1)+BN (bn=None: conv with bias) -> packed planar tensor-core layer (packing.pack_conv2d), or
-    None when the shape is not one the kernel takes (input channels must come in whole 16-channel k-steps)."""
+    None when the shape is not one the kernel takes (input channels must come in whole 16-channel k-steps).
+    any_stride: also pack stride-2 layers -- the caller runs them at stride 1 / on a subsampled input and keeps every other
+    row and column (a stride-2 convolution with this padding IS the stride-1 result at the even positions)."""
     from . import packing
     w = conv.weight.detach()
-    if conv.kernel_size not in ((3, 3), (1, 1)) or conv.stride != (1, 1) or conv.groups != 1 or w.shape[1] % 16 \
+    if conv.kernel_size not in ((3, 3), (1, 1)) or (conv.stride != (1, 1) and not (any_stride and conv.stride == (2, 2))) \
+            or conv.padding != ((conv.kernel_size[0] // 2) * conv.dilation[0],) * 2 or conv.groups != 1 or w.shape[1] % 16 \
             or conv.dilation not in ((1, 1), (2, 2)):
         return None
     if bn is not None:
@@ -216,20 +219,21 @@ class MatchingFeatureNet(nn.Module):
                 P[("layer1", i, 1)], P[("layer1", i, 2)] = pack(blk.conv1[0], "relu"), pack(blk.conv2, "none")
             for name in ("layer2", "layer3", "layer4"):
                 for i, blk in enumerate(getattr(self, name)):
-                    if blk.conv1[0][0].stride == (1, 1):
-                        P[(name, i, 1)] = pack(blk.conv1[0], "relu")
+                    P[(name, i, 1)] = pack(blk.conv1[0], "relu")        # layer2 block 0 is stride 2: run at stride 1, subsampled
                     P[(name, i, 2)] = pack(blk.conv2, "none")
+                    if blk.downsample is not None:
+                        P[(name, i, "down")] = pack(blk.downsample, "none")      # 1x1 (+BN) projection shortcut
             P["fuse"] = pack(self.lastconv[0], "relu")
+            last = self.lastconv[2].weight.detach()                              # final 1x1, no BN / bias / activation
+            P["last"] = packing.pack_conv2d(last, torch.ones(last.shape[0]), torch.zeros(last.shape[0]), "none", device, cout_slice=32)
             self._tc_packed, self._tc_key = P, key
         return self._tc_packed
 
     @staticmethod
-    def _conv_tc(pcs, x4, out4, res4=None, dilation=1):
-        """Runs a (possibly output-sliced) packed 3x3 layer: slice i writes chunks [16i, 16i+16) of out4."""
+    def _conv_tc(pcs, x4, out4, res4=None, dilation=1, taps=9):
+        """Runs a packed planar layer (3x3, or 1x1 with taps=1) from vol4 maps into out4."""
         from . import ops
-        for i, pc in enumerate(pcs):
-            lo, hi = 16 * i, 16 * i + pc.out_chunks                 # (single-slice layers: i == 0)
-            ops.conv_planar(pc, x4, out4[lo:hi], res0=None if res4 is None else res4[lo:hi], dilation=dilation)
+        ops.conv_planar(pcs[0], x4, out4, res0=res4, dilation=dilation, taps=taps)
         return out4
 
     def forward_tc(self, x):
@@ -246,17 +250,19 @@ class MatchingFeatureNet(nn.Module):
         for i in range(len(self.layer1)):
             self._conv_tc(P[("layer1", i, 1)], cur, tmp)
             cur = self._conv_tc(P[("layer1", i, 2)], tmp, half(), cur)
-        x = ops.vol4_to_nchw(cur)
         blk = self.layer2[0]
-        y = _folded(x, blk.conv1[0][0], blk.conv1[0][1], relu=True)  # stride-2 conv: cuDNN
-        H, W = y.shape[-2:]
+        H, W = (Hh + 1) // 2, (Wh + 1) // 2
         dev = x.device
 
         def vol(chunks):
             return torch.empty(chunks, N, H, W, 4, device=dev, dtype=torch.float32)
 
         cat = vol(80)                                               # [raw 64 | skip 128 | branch4..1 32 each]
-        cur = self._conv_tc(P[("layer2", 0, 2)], ops.nchw_to_vol4(y), vol(16), ops.nchw_to_vol4(_folded(x, blk.downsample[0], blk.downsample[1])))
+        # layer2 block 0: the stride-2 3x3 runs at stride 1 and keeps the even rows / columns; the stride-2 1x1 shortcut
+        # runs on the subsampled input
+        y = self._conv_tc(P[("layer2", 0, 1)], cur, torch.empty(16, N, Hh, Wh, 4, device=dev))[:, :, ::2, ::2, :].contiguous()
+        shortcut = self._conv_tc(P[("layer2", 0, "down")], cur[:, :, ::2, ::2, :].contiguous(), vol(16), taps=1)
+        cur = self._conv_tc(P[("layer2", 0, 2)], y, vol(16), shortcut)
         tmp = vol(16)
         n2 = len(self.layer2)
         for i in range(1, n2):
@@ -266,7 +272,7 @@ class MatchingFeatureNet(nn.Module):
         raw = cur
         # layer3: block 0 changes the width (64 -> 128) and projects the shortcut with a 1x1 conv (cuDNN)
         blk = self.layer3[0]
-        shortcut = ops.nchw_to_vol4(_folded(ops.vol4_to_nchw(raw), blk.downsample[0], blk.downsample[1]))
+        shortcut = self._conv_tc(P[("layer3", 0, "down")], raw, vol(32), taps=1)
         tmp = self._conv_tc(P[("layer3", 0, 1)], raw, vol(32))
         cur = self._conv_tc(P[("layer3", 0, 2)], tmp, vol(32), shortcut)
         stages = [("layer3", i, 1) for i in range(1, len(self.layer3))] + [("layer4", i, 2) for i in range(len(self.layer4))]
@@ -283,7 +289,7 @@ class MatchingFeatureNet(nn.Module):
             b = F.interpolate(_folded(pooled, br[1][0], br[1][1], relu=True), size=(H, W), mode="bilinear", align_corners=False)
             ops.nchw_to_vol4(b.contiguous(), cat[48 + 8 * slot:56 + 8 * slot])
         fused = self._conv_tc(P["fuse"], cat, vol(32))
-        return self.lastconv[2](ops.vol4_to_nchw(fused))
+        return ops.vol4_to_nchw(self._conv_tc(P["last"], fused, vol(8), taps=1))
 
     def forward(self, x):
         if x.is_cuda and getattr(self, "tensor_cores", False):
@@ -319,14 +325,14 @@ class ContextEncoder(nn.Module):
         self._tc_cache = {}
 
     def _packed_block(self, blk, device):
-        """Bottleneck layers packed for the planar tensor-core kernel (None where the shape is not taken: strided convs);
-        cached per block."""
+        """Bottleneck layers (conv1, conv2, conv3, downsample) packed for the planar tensor-core kernel; cached per block."""
         key = (str(device), blk.conv2.weight.data_ptr(), blk.conv1.weight._version, blk.conv2.weight._version,
                blk.conv3.weight._version, blk.bn2.running_var._version)
         ent = self._tc_cache.get(id(blk))
         if ent is None or ent[0] != key:
-            ent = (key, (_pack3x3(blk.conv1, blk.bn1, "relu", device), _pack3x3(blk.conv2, blk.bn2, "relu", device),
-                         _pack3x3(blk.conv3, blk.bn3, "add_relu", device)))
+            pd = None if blk.downsample is None else _pack3x3(blk.downsample[0], blk.downsample[1], "none", device, any_stride=True)
+            ent = (key, (_pack3x3(blk.conv1, blk.bn1, "relu", device), _pack3x3(blk.conv2, blk.bn2, "relu", device, any_stride=True),
+                         _pack3x3(blk.conv3, blk.bn3, "add_relu", device), pd))
             self._tc_cache[id(blk)] = ent
         return ent[1]
 
@@ -341,15 +347,16 @@ class ContextEncoder(nn.Module):
         return _folded(y, blk.conv2, blk.bn2, relu=True, residual=identity)
 
     def _stage_tc(self, stage, x):
-        """One ResNet stage of Bottlenecks with the 1x1 and the stride-1 3x3 convolutions on the planar tcgen05 kernel;
-        activations stay in vol4 inside the stage, only strided convolutions (conv2 / downsample of the first block) go
-        through cuDNN.  x: NCHW in; returns (NCHW out, vol4 out)."""
+        """One ResNet stage of Bottlenecks on the planar tcgen05 kernel; activations stay in vol4 inside the stage.  The
+        stride-2 3x3 of a stage's first block runs at stride 1 and keeps the even rows / columns (4x the flops of a
+        strided kernel, still several times faster than the fp32 CUDA-core one); its stride-2 1x1 shortcut runs on the
+        subsampled input.  x: NCHW in; returns (NCHW out, vol4 out)."""
         from . import ops
         x4 = None
         for blk in stage:
-            p1, p2, p3 = self._packed_block(blk, x.device if x is not None else x4.device)
-            if p1 is None or p3 is None:                               # not a shape the kernel takes: whole block on cuDNN
-                x = self._block(blk, x if x is not None else ops.vol4_to_nchw(x4))
+            p1, p2, p3, pd = self._packed_block(blk, x.device if x is not None else x4.device)
+            if p1 is None or p2 is None or p3 is None or (blk.downsample is not None and pd is None):
+                x = self._block(blk, x if x is not None else ops.vol4_to_nchw(x4))     # not a shape the kernel takes: cuDNN
                 x4 = None
                 continue
             if x4 is None:
@@ -357,13 +364,11 @@ class ContextEncoder(nn.Module):
             if blk.downsample is None:
                 identity4 = x4
             else:
-                xin = x if x is not None else ops.vol4_to_nchw(x4)
-                identity4 = ops.nchw_to_vol4(_folded(xin, blk.downsample[0], blk.downsample[1]))
-            y4 = _run3x3(p1, x4, taps=1)
-            if p2 is not None:
-                y4 = _run3x3(p2, y4)
-            else:
-                y4 = ops.nchw_to_vol4(_folded(ops.vol4_to_nchw(y4), blk.conv2, blk.bn2, relu=True))
+                xs = x4 if blk.downsample[0].stride == (1, 1) else x4[:, :, ::2, ::2, :].contiguous()
+                identity4 = _run3x3(pd, xs, taps=1)
+            y4 = _run3x3(p2, _run3x3(p1, x4, taps=1))
+            if blk.conv2.stride != (1, 1):
+                y4 = y4[:, :, ::2, ::2, :].contiguous()
             x4 = _run3x3(p3, y4, res4=identity4, taps=1)
             x = None
         if x is None:
