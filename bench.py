@@ -317,11 +317,13 @@ def run_ours(args):
     dom = max(kernels.items(), key=lambda kv: kv[1]["share_ms_per_step"])
     conv_name = "conv3d_" + model.precision
     conv = kernels.get(conv_name, dom[1])
-    mma_per_flop = {"fp32": 0.0, "3xtf32": 3.0, "3xf16": 3.0, "3xf16r": 3.0}[model.precision]
+    mma_per_flop = {"fp32": 0.0, "3xtf32": 3.0, "3xf16": 3.0, "3xf16r": 3.0, "3xf16r2": 3.0}[model.precision]
     # dram__bytes_read.sum + dram__bytes_write.sum of one 32->32 launch at cfg2 size from the committed ncu --set full capture
     # (profiles/kernels_r01_final.txt): 256.9 + 119.0 MB against 314.6 MB algorithmic = the 18x34 / 16x32 halo re-read
-    traffic = 375.8e6 if (args.workload == "cfg2" and model.precision == "3xf16r") else None
-    kname = {"3xf16r": "estd::ring::conv3d_ring_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule, fp16 two-term split)"}.get(
+    traffic = 375.8e6 if (args.workload == "cfg2" and model.precision in ("3xf16r", "3xf16r2")) else None
+    kname = {"3xf16r": "estd::ring::conv3d_ring_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule, fp16 two-term split)",
+             "3xf16r2": "estd::ring2::conv3d_ring2_kernel / ring::conv3d_ring_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule, "
+                        "CTA pairs where specialised, fp16 two-term split)"}.get(
         model.precision, "estd conv3d kernel (%s)" % model.precision)
     roofline = {"kernel": kname if conv_name in kernels else dom[0], "bound": "tensor",
                 "achieved": conv.get("TFLOPps"), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
@@ -359,7 +361,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=None, choices=["fp32", "3xtf32", "3xf16", "3xf16r"], help="conv3d arithmetic (default: the model's)")
+    ap.add_argument("--precision", default=None, choices=["fp32", "3xtf32", "3xf16", "3xf16r", "3xf16r2"], help="conv3d arithmetic (default: the model's)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~1 min oracle timing on the host cores")
     args = ap.parse_args()
     if args.impl == "reference":

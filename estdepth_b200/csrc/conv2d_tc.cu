@@ -229,12 +229,17 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                 }
             };
             load_res(0);
+            const float mult = s_scale[cbase];                     // uniform within a slice: the per-channel multiplier is folded into the weights
             if (e == 0) mbar_wait_polls(&acc_full[buf], (uint32_t)(use & 1));
             named_barrier(3, EPI_THREADS);
             tc_fence_after();
             const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * S::COLS_PER_UNIT + mt * N_ALL);
 #pragma unroll 1
             for (int c0 = 0; c0 < COUT; c0 += 16) {
+                // the 16 offsets of this block in one batch (a shared-memory load queues behind the tensor core's operand fetches)
+                float4 sh[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sh[j] = *reinterpret_cast<const float4*>(s_shift + cbase + c0 + 4 * j);
                 float a[16], b[16];
                 tmem_ld16(t0 + (uint32_t)c0, a);
                 tmem_ld16(t0 + (uint32_t)(COUT + c0), b);
@@ -245,10 +250,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                     const int ch = c >> 2;
                     if (!ok || ch >= ep.out_chunks) continue;
                     const int act = (c < ep.act_split) ? ep.act_lo : ep.act_hi;
-                    const float4 sc = *reinterpret_cast<const float4*>(s_scale + c), sh = *reinterpret_cast<const float4*>(s_shift + c);
                     float v[4];
-                    v[0] = fmaf(a[4 * j + 0] + b[4 * j + 0], sc.x, sh.x); v[1] = fmaf(a[4 * j + 1] + b[4 * j + 1], sc.y, sh.y);
-                    v[2] = fmaf(a[4 * j + 2] + b[4 * j + 2], sc.z, sh.z); v[3] = fmaf(a[4 * j + 3] + b[4 * j + 3], sc.w, sh.w);
+                    v[0] = fmaf(a[4 * j + 0] + b[4 * j + 0], mult, sh[j].x); v[1] = fmaf(a[4 * j + 1] + b[4 * j + 1], mult, sh[j].y);
+                    v[2] = fmaf(a[4 * j + 2] + b[4 * j + 2], mult, sh[j].z); v[3] = fmaf(a[4 * j + 3] + b[4 * j + 3], mult, sh[j].w);
                     if (act == ESTD_ACT_RELU) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.0f);

@@ -295,6 +295,7 @@ static int dispatch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_o
         ESTD_REQUIRE((d->W * 16) % 16 == 0 && d->W * 4 <= (1 << 30), "estd_conv3d: W too large");
     }
     if (d->planar) return dispatch_planar(d, stream, count_only, n_ctas);
+    if (d->precision == ESTD_PREC_3XF16_RING2) return dispatch_ring2(d, stream, count_only, n_ctas);
     if (d->precision == ESTD_PREC_3XF16_RING) return dispatch_ring(d, stream, count_only, n_ctas);
     if (d->precision == ESTD_PREC_3XTF32 || d->precision == ESTD_PREC_3XF16) return dispatch_tc(d, stream, count_only, n_ctas);
     ESTD_REQUIRE(d->precision == ESTD_PREC_FP32, "estd_conv3d: unknown precision %d", d->precision);

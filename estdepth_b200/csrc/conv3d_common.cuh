@@ -150,6 +150,8 @@ inline int sm_count() {
 
 // implemented in conv3d_tc.cu
 int dispatch_tc(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas);
+// implemented in conv3d_ring2.cu
+int dispatch_ring2(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas);
 // implemented in conv2d_tc.cu
 int dispatch_planar(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas);
 // implemented in conv3d_ring.cu

@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "conv3d_common.cuh"
 #include "tc_ptx.cuh"
+#include "ring_epilogue.cuh"
 
 namespace estd {
 namespace ring {
@@ -62,11 +63,6 @@ struct Shape {
     static_assert(COUT % 16 == 0 && COUT <= 48 && N3 <= 256 && (MT == 2 || MT == 4), "bad shape");
 };
 
-__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
-                 ::"r"(taddr), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 #ifdef ESTD_RING_TIMING
 // experiment only (make EXTRA=-DESTD_RING_TIMING): cycles the MMA issuer spent waiting, per CTA: {ready, acc_empty, total, stages}
@@ -114,7 +110,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     uint64_t* acc_empty = acc_full + 2;     // [2 halves] its slot has been read and zeroed
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
     __shared__ double s_red[EPI_WARPS][4];
-    __shared__ __align__(16) float s_scale[COUT], s_shift[COUT];     // the epilogue reads them for every voxel
+    __shared__ __align__(16) float s_shift[COUT];                    // per-channel offset; the per-channel multiplier is folded into the weights
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -124,7 +120,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_base_smem, S::TMEM_COLS);
-    if (warp == 3) for (int i = lane; i < COUT; i += 32) { s_scale[i] = p.ep.scale[i]; s_shift[i] = p.ep.shift[i]; }
+    if (warp == 3) for (int i = lane; i < COUT; i += 32) s_shift[i] = p.ep.shift[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -266,6 +262,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                 if (warp == FIRST_SPLIT_WARP) mbar_wait_polls(&full[s], (uint32_t)((it / STAGES) & 1));
                 named_barrier(2, SPLIT_THREADS);                 // one warp polls, the barrier releases the other seven
                 unsigned char* area = smem + (size_t)s * S::STAGE_BYTES;
+#ifndef ESTD_EXP_NOSPLIT      // timing experiment only: skip the hi/lo split (operands are garbage)
                 for (int i = t; i < 2 * HALO_VOX; i += SPLIT_THREADS) {
                     const int pair = i / HALO_VOX, v = i - pair * HALO_VOX;
                     float4* c0 = reinterpret_cast<float4*>(area + (size_t)pair * 2 * S::KGROUP_BYTES) + v;   // channels 8p..8p+3
@@ -284,6 +281,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                     *reinterpret_cast<uint4*>(c0) = hv;          // x_hi K-group of this pair
                     *reinterpret_cast<uint4*>(c1) = lv;          // x_lo K-group of this pair
                 }
+#endif
                 fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async proxy
                 mbar_arrive(&ready[s]);
             }
@@ -299,6 +297,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
         const size_t vox = (size_t)p.D * p.H * p.W;
         const ConvEpilogue& ep = p.ep;
         const bool want_gn = ep.gn_partials != nullptr;
+        const float mult = __ldg(ep.scale);                      // uniform: 2^-k of the fp16 weight scaling (pack_weight_ring)
         int n_seen = 0;
         int f = (m2 < S::MH) ? f_begin : f_end;                  // with 2 M tiles per column only the first 4 warps have work
         Segment sg;
@@ -314,70 +313,10 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                     const bool ok = (h < p.H) && (w < p.W);
                     const size_t pos = ((size_t)z * p.H + h) * p.W + w;
                     const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N3 + slot * COUT);
-                    // residuals of the next 16 channels are requested early so that they are in flight during the wait / the math
-                    float4 r0[4], r1[4];
-                    auto load_res = [&](int c0) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int ch = (c0 >> 2) + j;
-                            const bool valid = ok && ch < ep.out_chunks;
-                            const size_t off = ((size_t)ch * vox + pos) * 4;
-                            r0[j] = (ep.res0 && valid) ? ldg4(ep.res0 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            r1[j] = (ep.res1 && valid) ? ldg4(ep.res1 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    };
-                    load_res(0);
                     if (e == 0) mbar_wait_polls(&acc_full[half], (uint32_t)(n_seen & 1));
                     named_barrier(3, 128 * S::MH);
                     tc_fence_after();
-#pragma unroll 1
-                    for (int c0 = 0; c0 < COUT; c0 += 16) {
-                        float a[16];
-                        tmem_ld16(t0 + (uint32_t)c0, a);
-                        tmem_ld_wait();
-                        tmem_st16_zero(t0 + (uint32_t)c0);
-                        float ts[2] = {0.f, 0.f}, tq[2] = {0.f, 0.f};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int c = c0 + 4 * j;
-                            const int ch = c >> 2;
-                            if (!ok || ch >= ep.out_chunks) continue;
-                            const int act = (c < ep.act_split) ? ep.act_lo : ep.act_hi;
-                            const int grp = (c < ep.act_split) ? 0 : 1;
-                            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c), sh = *reinterpret_cast<const float4*>(s_shift + c);
-                            float v[4];
-                            v[0] = fmaf(a[4 * j + 0], sc.x, sh.x); v[1] = fmaf(a[4 * j + 1], sc.y, sh.y);
-                            v[2] = fmaf(a[4 * j + 2], sc.z, sh.z); v[3] = fmaf(a[4 * j + 3], sc.w, sh.w);
-                            if (act == ESTD_ACT_RELU) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) v[k] = fmaxf(v[k], 0.0f);
-                            } else if (act == ESTD_ACT_TANH) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) v[k] = tanhf(v[k]);
-                            }
-                            v[0] += r0[j].x; v[1] += r0[j].y; v[2] += r0[j].z; v[3] += r0[j].w;
-                            v[0] += r1[j].x; v[1] += r1[j].y; v[2] += r1[j].z; v[3] += r1[j].w;
-                            float s4 = 0.f, q4 = 0.f;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                v[k] *= ep.post_scale;
-                                s4 += v[k];
-                                q4 = fmaf(v[k], v[k], q4);
-                            }
-                            if (grp == 0) { ts[0] += s4; tq[0] += q4; } else { ts[1] += s4; tq[1] += q4; }
-                            const size_t off = ((size_t)ch * vox + pos) * 4;
-                            float* dst = (ch < ep.out0_chunks) ? ep.out0 + off : ep.out1 + (off - (size_t)ep.out0_chunks * vox * 4);
-                            st4(dst, make_float4(v[0], v[1], v[2], v[3]));
-                        }
-                        if (want_gn) {
-                            gs[0] += (double)ts[0]; gq[0] += (double)tq[0];
-                            gs[1] += (double)ts[1]; gq[1] += (double)tq[1];
-                        }
-                        if (c0 + 16 < COUT) load_res(c0 + 16);
-                    }
-                    tmem_st_wait();
-                    tc_fence_before();
-                    mbar_arrive(&acc_empty[half]);
+                    ring_drain_slot<COUT>(ep, s_shift, mult, t0, ok, pos, vox, want_gn, gs, gq, [&]() { mbar_arrive(&acc_empty[half]); });
                 }
             }
         }

@@ -1,0 +1,106 @@
+// Epilogue of the plane-ring kernels (conv3d_ring.cu, conv3d_ring2.cu): drain one ring slot of one M tile.
+#pragma once
+#include "common.cuh"
+#include "conv3d_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace estd {
+namespace tc {
+
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+                 ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// The accumulator slot at TMEM address t0 (COUT columns, this thread's lane = its voxel) is complete.
+//   1. TMEM -> registers, zero the slot, hand it back to the MMA issuer (hand_back());
+//   2. only then: * mult + shift -> activation -> residuals -> post_scale -> GroupNorm partial sums -> 16-byte stores.
+// The order matters: the issuer needs the slot back within the time the tensor core spends on the other half tile, and every
+// load/store of step 2 queues behind the tensor core's operand fetches on the saturated l1tex data pipe (measured: ~1900
+// cycles per 16 channels, profiles/README.md) -- with the stores on the critical path the issuer waited a third of the time.
+template <int COUT, class HandBack>
+__device__ __forceinline__ void ring_drain_slot(const ConvEpilogue& ep, const float* s_shift, float mult, uint32_t t0, bool ok,
+                                                size_t pos, size_t vox, bool want_gn, double (&gs)[2], double (&gq)[2],
+                                                HandBack&& hand_back) {
+    constexpr int NB = COUT / 16;
+    float acc[NB][16];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) tmem_ld16(t0 + (uint32_t)(16 * b), acc[b]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int b = 0; b < NB; ++b) tmem_st16_zero(t0 + (uint32_t)(16 * b));
+    tmem_st_wait();
+    tc_fence_before();
+    hand_back();
+
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int c0 = 16 * b;
+        float (&v)[16] = acc[b];                                   // finished in place: the kernel is at the register limit of its 640 threads
+        // what the block needs from memory is requested in batches (offsets + first residual, then the second residual)
+        float4 sh[4], r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sh[j] = *reinterpret_cast<const float4*>(s_shift + c0 + 4 * j);
+        if (ep.res0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ch = (c0 >> 2) + j;
+                r[j] = (ok && ch < ep.out_chunks) ? ldg4(ep.res0 + ((size_t)ch * vox + pos) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + 4 * j;
+            const int act = (c < ep.act_split) ? ep.act_lo : ep.act_hi;
+            v[4 * j + 0] = fmaf(v[4 * j + 0], mult, sh[j].x); v[4 * j + 1] = fmaf(v[4 * j + 1], mult, sh[j].y);
+            v[4 * j + 2] = fmaf(v[4 * j + 2], mult, sh[j].z); v[4 * j + 3] = fmaf(v[4 * j + 3], mult, sh[j].w);
+            if (act == ESTD_ACT_RELU) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[4 * j + k] = fmaxf(v[4 * j + k], 0.0f);
+            } else if (act == ESTD_ACT_TANH) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[4 * j + k] = tanhf(v[4 * j + k]);
+            }
+            v[4 * j + 0] += r[j].x; v[4 * j + 1] += r[j].y; v[4 * j + 2] += r[j].z; v[4 * j + 3] += r[j].w;
+        }
+        if (ep.res1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ch = (c0 >> 2) + j;
+                r[j] = (ok && ch < ep.out_chunks) ? ldg4(ep.res1 + ((size_t)ch * vox + pos) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { v[4 * j + 0] += r[j].x; v[4 * j + 1] += r[j].y; v[4 * j + 2] += r[j].z; v[4 * j + 3] += r[j].w; }
+        }
+        float ts[2] = {0.f, 0.f}, tq[2] = {0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + 4 * j;
+            const int ch = c >> 2;
+            if (!ok || ch >= ep.out_chunks) continue;
+            const int grp = (c < ep.act_split) ? 0 : 1;
+            float s4 = 0.f, q4 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[4 * j + k] *= ep.post_scale;
+                s4 += v[4 * j + k];
+                q4 = fmaf(v[4 * j + k], v[4 * j + k], q4);
+            }
+            if (grp == 0) { ts[0] += s4; tq[0] += q4; } else { ts[1] += s4; tq[1] += q4; }
+            const size_t off = ((size_t)ch * vox + pos) * 4;
+            float* dst = (ch < ep.out0_chunks) ? ep.out0 + off : ep.out1 + (off - (size_t)ep.out0_chunks * vox * 4);
+            st4(dst, make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        }
+        if (want_gn) {
+            gs[0] += (double)ts[0]; gq[0] += (double)tq[0];
+            gs[1] += (double)ts[1]; gq[1] += (double)tq[1];
+        }
+    }
+}
+
+}  // namespace tc
+}  // namespace estd

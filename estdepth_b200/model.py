@@ -82,7 +82,7 @@ class _Workspace(object):
 
 class DepthNetHybrid(nn.Module):
     def __init__(self, ndepths=64, depth_min=0.01, depth_max=10.0, resnet=50, IF_EST_transformer=True,
-                 align_corners=False, fix_stale_pose=False, precision="3xf16r", feature_precision="3xf16"):
+                 align_corners=False, fix_stale_pose=False, precision="3xf16r2", feature_precision="3xf16"):
         """First five arguments: hybrid_models/model_hybrid.py:15-16.  Extra, keyword-only in practice:
 
         align_corners   grid_sample semantics of the warps: False = torch >= 1.3 (what the reference computes when run
@@ -90,8 +90,9 @@ class DepthNetHybrid(nn.Module):
         fix_stale_pose  opt-in fix of quirk Q4 (return the current target's pose with the hidden state).
         precision       arithmetic of the 3-D convolutions: "3xf16" / "3xtf32" = error-compensated two-term splits on the
                         tcgen05 tensor cores (fp32-class accuracy; "3xf16" moves half the operand bytes and needs
-                        |activation| <= 65504, which is checked), "3xf16r" (default) = the 3xf16 arithmetic on the
-                        plane-ring schedule for the 32-output-channel layers, "fp32" = exact fp32 on the CUDA cores.
+                        |activation| <= 65504, which is checked), "3xf16r" = the 3xf16 arithmetic on the plane-ring
+                        schedule, "3xf16r2" (default) = the same on CTA pairs (cta_group::2) where specialised,
+                        "fp32" = exact fp32 on the CUDA cores.
         """
         super().__init__()
         self.ndepths = int(ndepths)
@@ -248,7 +249,7 @@ class DepthNetHybrid(nn.Module):
             raise NotImplementedError("estdepth_b200 implements the inference path (mode='val'); got mode=%r" % (mode,))
         if not imgs.is_cuda:
             raise RuntimeError("estdepth_b200.DepthNetHybrid runs on CUDA only (no CPU fallback); imgs is on %s" % imgs.device)
-        if self.precision in ("3xf16", "3xf16r"):
+        if self.precision in ("3xf16", "3xf16r", "3xf16r2"):
             ops.check_status(imgs.device)       # range flag of the previous call (its work has been consumed by now)
         with torch.no_grad():
             return self._forward_val(imgs, cam_poses, cam_intr, pre_costs, pre_cam_poses)

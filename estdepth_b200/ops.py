@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import ConvDesc, check
 
 ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2, "add_relu": 3, "sigmoid": 4}
-PRECISION = {"fp32": 0, "3xtf32": 1, "3xf16": 2, "3xf16r": 3}
+PRECISION = {"fp32": 0, "3xtf32": 1, "3xf16": 2, "3xf16r": 3, "3xf16r2": 4}
 MAX_SOURCES = 8
 # default arithmetic of conv3d: "fp32" = exact CUDA-core kernel, "3xtf32" / "3xf16" = error-compensated splits on tcgen05,
 # "3xf16r" = the 3xf16 arithmetic on the plane-ring schedule (conv3d_ring.cu) for the layers it is specialised for, the
@@ -141,7 +141,7 @@ def warp_cost(ref_mix, src_mix, homo12, depth_values, out=None, align_corners=Fa
 class PackedConv(object):
     """Folded, packed parameters of one 3x3x3 layer (see packing.pack_conv3d)."""
     __slots__ = ("weight", "scale", "shift", "cin_chunks", "cout_pad", "out_chunks", "act_split", "act_lo", "act_hi",
-                 "cin", "cout", "weight_tc", "cout_pad_tc", "weight_f16", "scale_f16", "weight_ring")
+                 "cin", "cout", "weight_tc", "cout_pad_tc", "weight_f16", "scale_f16", "weight_ring", "weight_ring2", "scale_ring")
 
     def __init__(self, weight, scale, shift, cin_chunks, cout_pad, out_chunks, act_split, act_lo, act_hi,
                  cin=None, cout=None, weight_tc=None, cout_pad_tc=None):
@@ -149,6 +149,8 @@ class PackedConv(object):
         self.weight_tc, self.cout_pad_tc = weight_tc, cout_pad_tc      # tcgen05 packings (packing.attach_tc)
         self.weight_f16, self.scale_f16 = None, None
         self.weight_ring = None                                        # plane-ring packing (packing.pack_weight_ring)
+        self.weight_ring2 = None                                       # CTA-pair plane-ring packing (packing.pack_weight_ring2)
+        self.scale_ring = None                                         # uniform 2^-k multiplier of the ring packings
         self.cin = cin if cin is not None else 4 * cin_chunks          # real (un-padded) channel counts, for flop accounting
         self.cout = cout if cout is not None else min(cout_pad, 4 * out_chunks)
         self.cin_chunks, self.cout_pad, self.out_chunks = cin_chunks, cout_pad, out_chunks
@@ -159,6 +161,8 @@ def _precision(pc, precision):
     precision = DEFAULT_PRECISION if precision is None else precision
     if precision not in PRECISION:
         raise RuntimeError("conv3d: unknown precision %r" % (precision,))
+    if precision == "3xf16r2" and pc.weight_ring2 is None:
+        precision = "3xf16r"           # same arithmetic and schedule on single CTAs: no CTA-pair specialisation for this shape
     if precision == "3xf16r" and pc.weight_ring is None:
         precision = "3xf16"            # same arithmetic, output-stationary schedule: no ring specialisation for this shape
     if (precision == "3xtf32" and pc.weight_tc is None) or (precision == "3xf16" and pc.weight_f16 is None):
@@ -197,9 +201,11 @@ def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, pr
         raise RuntimeError("conv3d: layer packed for %d input chunks, got %d" % (pc.cin_chunks, d.in0_chunks + d.in1_chunks))
     tc = precision != "fp32"
     d.weight = _ptr(pc.weight)
-    f16 = precision in ("3xf16", "3xf16r")
-    d.weight_tc = _ptr(pc.weight_ring if precision == "3xf16r" else pc.weight_f16 if precision == "3xf16" else pc.weight_tc)
-    d.scale, d.shift = _ptr(pc.scale_f16 if f16 else pc.scale), _ptr(pc.shift)
+    f16 = precision in ("3xf16", "3xf16r", "3xf16r2")
+    d.weight_tc = _ptr(pc.weight_ring2 if precision == "3xf16r2" else pc.weight_ring if precision == "3xf16r"
+                       else pc.weight_f16 if precision == "3xf16" else pc.weight_tc)
+    ring = precision in ("3xf16r", "3xf16r2")
+    d.scale, d.shift = _ptr(pc.scale_ring if ring else pc.scale_f16 if f16 else pc.scale), _ptr(pc.shift)
     d.cout_pad = pc.cout_pad_tc if tc else pc.cout_pad
     d.status = _ptr(status_flag(in0.device), torch.int32) if f16 else None
     d.act_split, d.act_lo, d.act_hi = pc.act_split, pc.act_lo, pc.act_hi

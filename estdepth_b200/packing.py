@@ -115,7 +115,7 @@ def pack_weight_f16(packed, cout_pad_tc=None):
 RING_SHAPES = ((2, 32), (3, 32), (1, 16), (2, 16), (3, 48))
 
 
-def pack_weight_ring(packed, cout_pad_tc=None):
+def pack_weight_ring(packed, cout_pad_tc=None, scale=None):
     """SIMT packing [27][cin_pad][cout_pad] -> plane-ring packing of conv3d_ring.cu,
     [3 rotations][nks][9 taps][hi,lo][2 K-groups][3*C rows][8 x fp16] (returned as a float32-typed byte buffer) + the
     power-of-two exponent of ``pack_weight_f16``.
@@ -129,6 +129,10 @@ def pack_weight_ring(packed, cout_pad_tc=None):
     nks = (cin_pad + 15) // 16
     w = torch.zeros(27, 16 * nks, C, dtype=torch.float32, device=packed.device)
     w[:, :cin_pad, :cout_pad] = packed
+    if scale is not None:
+        # the per-channel multiplier (folded BN scale) goes into the weights: the ring kernels' epilogue applies one
+        # uniform factor 2^-k and the per-channel offset only
+        w[:, :, :cout_pad] = w[:, :, :cout_pad] * scale[:cout_pad].to(device=w.device, dtype=torch.float32).view(1, 1, -1)
     wmax = float(w.abs().max())
     k = 0 if wmax == 0.0 else max(-14, min(24, int(torch.floor(torch.log2(torch.tensor(1023.0 / wmax))))))
     ws = w * (2.0 ** k)
@@ -146,6 +150,52 @@ def pack_weight_ring(packed, cout_pad_tc=None):
     return torch.stack(rots, dim=0).contiguous().view(torch.float32), k
 
 
+RING2_SHAPES = ((2, 32), (3, 32))
+
+
+def pack_weight_ring2(packed, cout_pad_tc=None, scale=None):
+    """SIMT packing [27][cin_pad][cout_pad] -> CTA-pair ring packing of conv3d_ring2.cu,
+    [7 live-tap masks][3 rotations][nks][2 CTAs][9 taps][hi,lo][2 K-groups][3*C/2 rows][8 x fp16] (float32-typed bytes)
+    + the power-of-two exponent of ``pack_weight_f16``.
+
+    Rotation r orders the rows by ring slot exactly like ``pack_weight_ring`` (slot j <- depth tap (r - j + 1) mod 3);
+    variant ``mask - 1`` zeroes the taps whose bit is clear in ``mask`` (bit kd: output plane z + 1 - kd belongs to the
+    CTA pair's range), so that partial first / last planes issue the same full-N MMA; CTA 0 of the pair holds rows
+    [0, 3C/2), CTA 1 rows [3C/2, 3C)."""
+    taps, cin_pad, cout_pad = packed.shape
+    assert taps == 27
+    C = tc_cout_pad(cout_pad) if cout_pad_tc is None else cout_pad_tc
+    nks = (cin_pad + 15) // 16
+    w = torch.zeros(27, 16 * nks, C, dtype=torch.float32, device=packed.device)
+    w[:, :cin_pad, :cout_pad] = packed
+    if scale is not None:
+        # the per-channel multiplier (folded BN scale) goes into the weights: the ring kernels' epilogue applies one
+        # uniform factor 2^-k and the per-channel offset only
+        w[:, :, :cout_pad] = w[:, :, :cout_pad] * scale[:cout_pad].to(device=w.device, dtype=torch.float32).view(1, 1, -1)
+    wmax = float(w.abs().max())
+    k = 0 if wmax == 0.0 else max(-14, min(24, int(torch.floor(torch.log2(torch.tensor(1023.0 / wmax))))))
+    ws = w * (2.0 ** k)
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.to(torch.float32)).to(torch.float16)
+
+    def arrange(x):      # [kd*9+tap9][ks*16+kg*8+e][C] -> [kd][ks][tap9][kg][C][e]
+        return x.reshape(3, 9, nks, 2, 8, C).permute(0, 2, 1, 3, 5, 4)
+
+    parts = torch.stack([arrange(hi), arrange(lo)], dim=3)                    # [kd][ks][tap9][prod][kg][C][e]
+    zero = torch.zeros_like(parts[0])
+    NH = 3 * C // 2
+    variants = []
+    for mask in range(1, 8):
+        rots = []
+        for r in range(3):
+            slots = [parts[(r - j + 1) % 3] if (mask >> ((r - j + 1) % 3)) & 1 else zero for j in range(3)]
+            full = torch.cat(slots, dim=4)                                    # [ks][tap9][prod][kg][3C][e]
+            halves = full.reshape(nks, 9, 2, 2, 2, NH, 8).permute(0, 4, 1, 2, 3, 5, 6)      # [ks][half][tap9][prod][kg][NH][e]
+            rots.append(halves)
+        variants.append(torch.stack(rots, dim=0))
+    return torch.stack(variants, dim=0).contiguous().view(torch.float32), k
+
+
 def attach_tc(pc):
     """Adds the tensor-core packings (3xTF32 and fp16-split) to a PackedConv and pads its affine arrays."""
     pc.cout_pad_tc = tc_cout_pad(pc.cout_pad)
@@ -157,9 +207,13 @@ def attach_tc(pc):
             setattr(pc, name, torch.cat([v, torch.zeros(AFFINE_PAD - v.numel(), dtype=v.dtype, device=v.device)]).contiguous())
     pc.scale_f16 = (pc.scale * (2.0 ** -k)).contiguous()
     nks = (pc.weight.shape[1] + 15) // 16
+    if pc.weight.shape[0] == 27 and (nks, pc.cout_pad_tc) in RING2_SHAPES:
+        pc.weight_ring2, k_ring2 = pack_weight_ring2(pc.weight, pc.cout_pad_tc, pc.scale)
     if pc.weight.shape[0] == 27 and (nks, pc.cout_pad_tc) in RING_SHAPES:
-        pc.weight_ring, k_ring = pack_weight_ring(pc.weight, pc.cout_pad_tc)
-        assert k_ring == k
+        pc.weight_ring, k_ring = pack_weight_ring(pc.weight, pc.cout_pad_tc, pc.scale)
+        assert pc.weight_ring2 is None or k_ring2 == k_ring
+        # uniform multiplier of the ring kernels (read as scale[0]): undoes the power-of-two weight scaling
+        pc.scale_ring = torch.full((AFFINE_PAD,), 2.0 ** -k_ring, dtype=torch.float32, device=pc.weight.device)
     return pc
 
 
@@ -189,14 +243,15 @@ def _pack_conv2d_slices(weight, scale, shift, act, device, cout_slice):
         n = min(cout_slice, cout - c0)
         taps = weight.shape[2] * weight.shape[3]           # 9 (3x3) or 1 (1x1)
         w = weight[c0:c0 + n].reshape(n, cin, taps).permute(2, 1, 0).to(device=device, dtype=torch.float32).contiguous()   # [taps][Cin][n]
+        # the per-channel multiplier is folded into the weights: the kernel applies one factor per slice (2^-k) + the offsets
+        w = w * scale[c0:c0 + n].to(device=device, dtype=torch.float32).view(1, 1, -1)
         wf16, k = pack_weight_f16(w, cout_slice)
-        s = torch.zeros(cout_slice, dtype=torch.float32, device=device)
+        s = torch.full((cout_slice,), 2.0 ** -k, dtype=torch.float32, device=device)
         b = torch.zeros(cout_slice, dtype=torch.float32, device=device)
-        s[:n] = scale[c0:c0 + n].to(device)
         b[:n] = shift[c0:c0 + n].to(device)
         pc = PackedConv(None, s, b, (cin + 3) // 4, cout_slice, (n + 3) // 4, cout_slice, act, act, cin=cin, cout=n,
                         cout_pad_tc=cout_slice)
-        pc.weight_f16, pc.scale_f16 = wf16, (s * (2.0 ** -k)).contiguous()
+        pc.weight_f16, pc.scale_f16 = wf16, s
         out.append(pc)
     return out
 

@@ -53,7 +53,13 @@ extern "C" {
 #define ESTD_PREC_3XF16_RING 3      /* same arithmetic as ESTD_PREC_3XF16, plane-ring schedule (conv3d_ring.cu): the input plane is
                                        stationary and the three depth taps ride in the MMA's N dimension (N = 3*cout_pad);
                                        `weight_tc` must hold the ring packing [3 rotations][nks][9][hi,lo][2][3*cout_pad rows][16 B];
+                                       the per-channel multiplier must be FOLDED INTO THE WEIGHTS: the kernel applies scale[0] to every
+                                       channel (the 2^-k of the fp16 weight scaling) and shift[c] per channel;
                                        3x3x3 only; (input chunks, cout_pad) in {(8,32), (9,32), (4,16), (8,16), (9,48)} */
+
+#define ESTD_PREC_3XF16_RING2 4     /* ESTD_PREC_3XF16_RING on CTA pairs (tcgen05 cta_group::2, conv3d_ring2.cu): M = 256 per MMA, each CTA of
+                                       the cluster holds half of the weight rows; `weight_tc` = packing [7 masks][3 rotations][nks][2 CTAs]
+                                       [9][hi,lo][2][3*cout_pad/2 rows][16 B]; cout_pad 32, 8 or 9 input chunks */
 
 ESTD_API int estd_version(void);
 ESTD_API const char* estd_last_error(void);
@@ -107,7 +113,8 @@ typedef struct estd_conv3d_desc {
                                              1: 1x3x3 filter applied per plane = 2-D 3x3 convolution over a stack of
                                              D feature maps (matching-feature net, context decoder); weight_tc is [nks][9][2][2*cout_pad][16 B],
                                              any number of input chunks, cout_pad 16/32/64 (wider layers: one call per 64-channel
-                                             slice); fp16 split only; no gn_partials / res1 */
+                                             slice); fp16 split only; no gn_partials / res1; the per-channel multiplier must be folded
+                                             into the weights: scale[64*s] is applied to every channel of slice s */
     int dilation;                         /* in-plane tap dilation, 1 or 2 (2: planar only); 0 is read as 1 */
     const float* scale;                   /* [cout_pad] per-channel multiplier (folded BN gamma/sqrt(var+eps)) */
     const float* shift;                   /* [cout_pad] per-channel offset (folded BN beta - mean*scale, or conv bias) */

@@ -66,9 +66,80 @@ __global__ void __launch_bounds__(256, 1) probe(int N, int layout, int n_mma, in
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// The exact MMA stream of one conv3d_ring.cu stage (2 halves x 9 taps x 3 products x 2 M tiles, N = 96, accumulators at
+// columns (2*half + m2) * 96, A_hi / A_lo halo views, W_hi / W_lo blocks of 9 taps) with nothing else running on the SM.
+__global__ void __launch_bounds__(256, 1) probe_ring(int n_stage, long long* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 190 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    if (warp == 0) {
+        const bool leader = elect_one();
+        constexpr int HALO_W = 34, KG = 612 * 16, A_BYTES = 4 * KG, N3 = 96, W_PART = 2 * N3 * 16, W_TAP = 2 * W_PART, STAGE = 94464;
+        const uint32_t idesc = make_idesc(0u, N3);
+        long long t0 = 0, t1 = 0;
+        if (leader) {
+            for (int rep = 0; rep < 2; ++rep) {
+                t0 = clock64();
+                for (int st = 0; st < n_stage; ++st) {
+                    const uint32_t a_hi = smem_u32(smem) + (uint32_t)((st & 1) * STAGE);
+                    const uint64_t a_hi_desc = make_desc(a_hi, 2 * KG, HALO_W * 16);
+                    const uint64_t a_lo_desc = make_desc(a_hi + KG, 2 * KG, HALO_W * 16);
+                    const uint64_t w_hi_desc = make_desc(a_hi + A_BYTES, N3 * 16, 128);
+                    const uint64_t w_lo_desc = make_desc(a_hi + A_BYTES + W_PART, N3 * 16, 128);
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t acc0 = tmem_base + (uint32_t)(half * 2 * N3);
+                        const uint64_t a_base = (uint64_t)(half * 16);
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint64_t b_off = (uint64_t)(tap * (W_TAP >> 4));
+#pragma unroll
+                            for (int prod = 0; prod < 3; ++prod) {
+#pragma unroll
+                                for (int m2 = 0; m2 < 2; ++m2) {
+                                    const uint64_t a_off = a_base + (uint64_t)((tap / 3) * HALO_W + 8 * m2 + (tap % 3));
+                                    umma<KIND_F16>(acc0 + (uint32_t)(m2 * N3), (prod == 2 ? a_lo_desc : a_hi_desc) + a_off,
+                                                   (prod == 1 ? w_lo_desc : w_hi_desc) + b_off, idesc, 1u);
+                                }
+                            }
+                        }
+                    }
+                }
+                umma_commit(&bar);
+                mbar_wait(&bar, (uint32_t)(rep & 1));
+                t1 = clock64();
+            }
+            out[blockIdx.x] = t1 - t0;
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 int main() {
     long long* out;
     cudaMallocManaged(&out, 2048 * sizeof(long long));
+    cudaFuncSetAttribute(probe_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    {
+        const int n_stage = 40;
+        probe_ring<<<148, 256, 200 * 1024>>>(n_stage, out);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+        long long mx = 0;
+        for (int i = 0; i < 148; ++i) mx = out[i] > mx ? out[i] : mx;
+        printf("ring stage pattern: %.1f clk/MMA (%.0f clk per 108-MMA stage)\n", (double)mx / (n_stage * 108), (double)mx / n_stage);
+    }
     cudaFuncSetAttribute(probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(probe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int n_mma = 36 * 128;

@@ -36,7 +36,7 @@ def _run_joint(model, height, width, starts=(0, 3)):
     return results
 
 
-@pytest.mark.parametrize("precision", ["3xf16r", "3xf16", "3xtf32", "fp32"])
+@pytest.mark.parametrize("precision", ["3xf16r2", "3xf16r", "3xf16", "3xtf32", "fp32"])
 @pytest.mark.parametrize("resnet,ndepths,height,width,name", [
     (18, 32, 128, 160, "joint_r18_d32_128x160.npz"),
     (50, 64, 128, 128, "joint_r50_d64_128x128.npz"),

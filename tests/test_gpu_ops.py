@@ -127,7 +127,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16", "3xf16r"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16", "3xf16r", "3xf16r2"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 @pytest.mark.parametrize("shape", [(5, 21, 40), (8, 32, 64)], ids=["ragged", "aligned"])
 def test_conv3d_vs_torch_cpu(case, shape, precision):
@@ -185,7 +185,7 @@ def test_conv3d_vs_torch_cpu(case, shape, precision):
         assert abs(tot[1, 1].item() - (g1 ** 2).sum().item()) < 1e-4 * (g1 ** 2).sum().item()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16", "3xf16r"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16", "3xf16r", "3xf16r2"])
 def test_conv3d_is_bitwise_deterministic(precision):
     g = torch.Generator().manual_seed(5)
     D, H, W = 6, 24, 64
@@ -203,10 +203,11 @@ def test_conv3d_is_bitwise_deterministic(precision):
     assert torch.equal(outs[0], outs[1]) and torch.equal(parts[0], parts[1])
 
 
+@pytest.mark.parametrize("ring", ["3xf16r", "3xf16r2"])
 @pytest.mark.parametrize("case", ["32to32", "36to32", "16to16", "32to16", "36to33"])
 @pytest.mark.parametrize("shape", [(48, 64, 128), (13, 40, 70), (3, 120, 160), (1, 33, 65)],
                          ids=["long_segments", "ragged", "three_planes", "one_plane"])
-def test_conv3d_ring_matches_exact_kernel(case, shape):
+def test_conv3d_ring_matches_exact_kernel(case, shape, ring):
     """The plane-ring schedule (conv3d_ring.cu) against the exact fp32 CUDA-core kernel on volumes large enough that a
     CTA's range spans several planes and crosses column boundaries (partial first/last planes, ring wrap-around, the
     hand-over of the last plane of a column), with residuals, two input segments and two output tensors."""
@@ -232,7 +233,9 @@ def test_conv3d_ring_matches_exact_kernel(case, shape):
         res0[-1, ..., cout % 4:] = 0
     ins = [x[:cin_seg[0]].contiguous()] + ([x[cin_seg[0]:].contiguous()] if len(cin_seg) > 1 else [])
     got, want = {}, {}
-    for precision, store in (("fp32", want), ("3xf16r", got)):
+    if ring == "3xf16r2" and pc.weight_ring2 is None:
+        pytest.skip("no CTA-pair specialisation for this shape (runs the single-CTA ring kernel)")
+    for precision, store in (("fp32", want), (ring, got)):
         o0 = torch.full((oc, D, H, W, 4), float("nan"), device=DEV)
         o1 = torch.full((out_chunks - oc, D, H, W, 4), float("nan"), device=DEV)
         n = ops.conv3d_num_ctas(pc, D, H, W, precision=precision)

@@ -139,3 +139,23 @@ def test_ring_packing_and_schedule_reproduce_conv3d():
             got = _simulate_ring(x, ring, k, nks, 32, D, grid)
             assert torch.isfinite(got).all()
             assert (got - want).abs().max().item() < 1e-5, (cin, D, grid)
+
+
+def test_ring2_packing_is_the_ring_packing_split_over_the_cta_pair():
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(32, 36, 3, 3, 3, generator=g) / 10
+    packed = packing.pack_weight(w, list(range(36)), list(range(32)))
+    ring, k = packing.pack_weight_ring(packed, 32)
+    ring2, k2 = packing.pack_weight_ring2(packed, 32)
+    assert k == k2 and tuple(ring2.shape) == (7, 3, 3, 2, 9, 2, 2, 48, 4)
+    full = ring2[6].permute(0, 1, 3, 4, 5, 2, 6, 7).reshape(3, 3, 9, 2, 2, 96, 4)         # all taps live: [rot][ks][tap][prod][kg][96][4]
+    assert torch.equal(full, ring)
+    # mask 1 (only depth tap 0 live): for rotation r the rows of the slots holding taps 1 and 2 are zero
+    only0 = ring2[0].permute(0, 1, 3, 4, 5, 2, 6, 7).reshape(3, 3, 9, 2, 2, 96, 4)
+    for r in range(3):
+        for slot in range(3):
+            blk = only0[r][..., 32 * slot:32 * slot + 32, :]
+            if (r - slot + 1) % 3 == 0:
+                assert torch.equal(blk, ring[r][..., 32 * slot:32 * slot + 32, :])
+            else:
+                assert float(blk.view(torch.int32).abs().max()) == 0.0
