@@ -114,6 +114,60 @@ def volume_warp_setup(pose_i, pose_j, cam_intr, out=None):
     return out
 
 
+_INV_MIN_BATCH = 8
+
+
+def _inv(m):
+    """torch.inverse without blocking the host.  ``torch.inverse`` checks its result (one synchronisation per call), and
+    even ``linalg.inv_ex`` synchronises when it is given a SINGLE 4x4 matrix (looped cuSOLVER path; measured in
+    profiles/inv_sync.py) -- the batched path does not, and gives the same bits per matrix (profiles/inv_bits.py).  So the
+    batch is padded with identities to at least 8 matrices."""
+    n = m.shape[0]
+    if n < _INV_MIN_BATCH:
+        pad = torch.eye(m.shape[-1], device=m.device, dtype=m.dtype).expand(_INV_MIN_BATCH - n, -1, -1)
+        return torch.linalg.inv_ex(torch.cat([m, pad], 0))[0][:n]
+    return torch.linalg.inv_ex(m)[0]
+
+
+def homography_table_torch(poses, K4, pairs):
+    """The [rot | trans] of every (reference view, source view) pair computed with the REFERENCE'S OWN fp32 torch ops, in its
+    order (model_hybrid.py:74-88, homo_utils.py:469-471): ext = inverse(pose); proj[:3,:4] = K ext[:3,:4];
+    M = src_proj inverse(ref_proj).  poses [V,4,4], K4 [3,3], pairs = [(ref, src), ...] -> [len(pairs), 12].
+
+    Why not the fp64 kernel (estd_homography_setup): a sampling coordinate within an ulp of the [-1, 1] range flips between
+    'sampled' and 'zero-filled' (quirk Q10) when the matrices differ in the last bit; with the reference's matrices the
+    kernels' coordinate arithmetic reproduces the reference's bit for bit (tests/run_fullsize_parity.py)."""
+    V = poses.shape[0]
+    ext = _inv(poses)                                                    # [V,4,4]
+    proj = []
+    for v in range(V):
+        p = ext[v:v + 1].clone()
+        p[:, :3, :4] = K4.unsqueeze(0) @ ext[v:v + 1, :3, :4]            # batch-1 bmm, as the reference issues it
+        proj.append(p)
+    refs = sorted(set(r for r, _ in pairs))
+    ref_inv = _inv(torch.cat([proj[r] for r in refs], 0))
+    rows = []
+    for r, s_ in pairs:
+        m = torch.matmul(proj[s_], ref_inv[refs.index(r):refs.index(r) + 1])[0]
+        rows.append(torch.cat([m[:3, :3].reshape(9), m[:3, 3]]))
+    return torch.stack(rows).contiguous()
+
+
+def volume_warp_tables_torch(all_poses, n_targets, K4):
+    """[Kinv | Minv (3x4) | K] for every (target i < n_targets, source j != i) pair of ``all_poses`` with the reference's fp32
+    torch ops (hybrid_depth_decoder.py:235: rel = P_j inverse(P_i); homo_utils.py:51,258: inverse(K), inverse(rel)).
+    all_poses: list of [4,4]; K4 [3,3] -> list (per target) of [len(all_poses) - 1, 30], sources in list order."""
+    n = len(all_poses)
+    inv_t = _inv(torch.stack(all_poses[:n_targets]))                     # one batched LU: same bits as one at a time
+    rel = torch.cat([all_poses[j].unsqueeze(0) @ inv_t[i:i + 1]          # batch-1 matmuls, as the reference issues them
+                     for i in range(n_targets) for j in range(n) if j != i], 0)
+    m = n_targets * (n - 1)
+    minv = _inv(rel)[:, :3, :4].reshape(m, 12)
+    kinv = _inv(K4.unsqueeze(0)).reshape(1, 9).expand(m, 9)
+    table = torch.cat([kinv, minv, K4.reshape(1, 9).expand(m, 9)], 1).contiguous()
+    return [table[i * (n - 1):(i + 1) * (n - 1)] for i in range(n_targets)]
+
+
 def premix(fea_chw, weight, bias=None, out=None):
     """fea [Cin,H,W], weight [Cout,Cin], bias [Cout]|None -> map4 [Cout/4,H,W,4]."""
     cin, H, W = fea_chw.shape
@@ -182,12 +236,40 @@ def status_flag(device):
 
 
 def check_status(device):
-    """Raises if any 3xf16 convolution saw |x| > 65504 since the last check (one 4-byte D2H read)."""
+    """Raises if any 3xf16 convolution saw |x| > 65504 since the last check (one 4-byte D2H read; synchronises)."""
     flag = _STATUS.get(str(device))
     if flag is not None and int(flag.item()) != 0:
         flag.zero_()
         raise RuntimeError("estdepth_b200: an activation exceeded the fp16 range in a 3xf16 convolution; "
                            "results are invalid -- use precision='3xtf32' or 'fp32' for this model")
+
+
+_STATUS_ASYNC = {}
+
+
+def check_status_async(device):
+    """The same check WITHOUT blocking the host: the flag is copied to pinned memory behind the work already enqueued, and
+    the copy of an EARLIER call is examined once its event has completed.  A violation is therefore reported one or two
+    calls late -- but a model's forward no longer drains the GPU before it starts issuing (the blocking check cost the
+    whole issue latency of the first kernels of every step)."""
+    key = str(device)
+    flag = _STATUS.get(key)
+    if flag is None:
+        return
+    ent = _STATUS_ASYNC.get(key)
+    if ent is not None and ent[1].query():
+        if int(ent[0][0]) != 0:
+            flag.zero_()
+            _STATUS_ASYNC.pop(key, None)
+            raise RuntimeError("estdepth_b200: an activation exceeded the fp16 range in a 3xf16 convolution of an earlier "
+                               "call; its results are invalid -- use precision='3xtf32' or 'fp32' for this model")
+        ent = None
+    if ent is None:
+        host = torch.empty(1, dtype=torch.int32).pin_memory()
+        host.copy_(flag, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(flag.device))
+        _STATUS_ASYNC[key] = (host, ev)
 
 
 def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision, planar=0, dilation=1):

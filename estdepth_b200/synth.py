@@ -8,8 +8,8 @@ not in the image, so the benchmark, the smoke test and the parity fixtures all u
     depth logits spread over several units (default torch init gives logits with sigma ~ 1e-3, i.e. a
     uniform softmax and depth == 5.05 everywhere whatever the kernels do -- SURVEY.md section 7);
   * ``synth_inputs``: the synthetic 7-Scenes-like window of SURVEY.md section 8(d): low-passed random
-    images, intrinsics of data/general_eval.py:168-176 scaled to the image size, a slow translate+yaw
-    camera track that keeps every projected depth positive.
+    images, intrinsics of data/general_eval.py:168-176 scaled to the image size, a slow camera track
+    (translation + yaw / pitch / roll) that keeps every projected depth positive.
 
 Both are bit-reproducible on any machine with the same torch build (CPU generators only).
 """
@@ -81,16 +81,26 @@ def synth_state_dict(reference_state, seed=0, head_gain=HEAD_GAIN):
 
 
 def camera_track(num_views, start=0, dtype=torch.float32):
-    """cam->world poses [V,4,4]: translation (0.05 v, 0, 0.01 v) m and yaw 0.02 v rad."""
+    """cam->world poses [V,4,4]: translation (0.05 v, 0.013 v, 0.01 v) m, yaw 0.02 v, pitch 0.011 v and roll 0.007 v rad.
+
+    SURVEY.md 8d proposed translate-in-x/z + yaw only.  That track keeps every image ROW on itself wherever the depth of a
+    point is the same in both views, so the warps of the first / last row land exactly on the +-1 cut of the reference's
+    sampling range (quirk Q10) and fp32 round-off decides, voxel by voxel, between 'sampled' and 'zero-filled' -- a property
+    of the synthetic geometry, not of real sequences.  A little vertical motion, pitch and roll makes the cut generic again.
+    """
     poses = torch.zeros(num_views, 4, 4, dtype=torch.float64)
     for i in range(num_views):
         v = start + i
-        a = 0.02 * v
-        c, s = math.cos(a), math.sin(a)
-        poses[i] = torch.tensor([[c, 0.0, s, 0.05 * v],
-                                 [0.0, 1.0, 0.0, 0.0],
-                                 [-s, 0.0, c, 0.01 * v],
-                                 [0.0, 0.0, 0.0, 1.0]], dtype=torch.float64)
+        yaw, pitch, roll = 0.02 * v, 0.011 * v, 0.007 * v
+        cy, sy = math.cos(yaw), math.sin(yaw)
+        cp, sp = math.cos(pitch), math.sin(pitch)
+        cr, sr = math.cos(roll), math.sin(roll)
+        Ry = torch.tensor([[cy, 0.0, sy], [0.0, 1.0, 0.0], [-sy, 0.0, cy]], dtype=torch.float64)
+        Rx = torch.tensor([[1.0, 0.0, 0.0], [0.0, cp, -sp], [0.0, sp, cp]], dtype=torch.float64)
+        Rz = torch.tensor([[cr, -sr, 0.0], [sr, cr, 0.0], [0.0, 0.0, 1.0]], dtype=torch.float64)
+        poses[i, :3, :3] = Ry @ Rx @ Rz
+        poses[i, :3, 3] = torch.tensor([0.05 * v, 0.013 * v, 0.01 * v], dtype=torch.float64)
+        poses[i, 3, 3] = 1.0
     return poses.to(dtype)
 
 
