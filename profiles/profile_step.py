@@ -22,8 +22,9 @@ model = DepthNetHybrid(ndepths=D, depth_min=0.1, depth_max=10.0, resnet=resnet, 
 model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=0))
 model.eval().to(dev)
 w1 = synth.synth_inputs(V, H, W, seed=0, start=0)
-w2 = [t.to(dev) for t in synth.synth_inputs(V, H, W, seed=0, start=V - 2)[:3]]
-_, state, pstate = model(w1[0].to(dev), w1[1].to(dev), w1[2].to(dev), None, mode="val")
+w2 = list(synth.synth_inputs(V, H, W, seed=0, start=V - 2)[:3])
+w2[0] = w2[0].to(dev)                       # images resident, camera parameters on the host (as bench.py)
+_, state, pstate = model(w1[0].to(dev), w1[1], w1[2], None, mode="val")
 for _ in range(2):
     model(w2[0], w2[1], w2[2], None, state, pstate, mode="val")
 torch.cuda.synchronize()
