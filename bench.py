@@ -323,8 +323,10 @@ def run_ours(args):
     conv = kernels.get(conv_name, dom[1])
     mma_per_flop = {"fp32": 0.0, "3xtf32": 3.0, "3xf16": 3.0, "3xf16r": 3.0, "3xf16r2": 3.0}[model.precision]
     # dram__bytes_read.sum + dram__bytes_write.sum of one 32->32 launch at cfg2 size from the committed ncu --set full capture
-    # (profiles/kernels_r01_final.txt): 256.9 + 119.0 MB against 314.6 MB algorithmic = the 18x34 / 16x32 halo re-read
-    traffic = 375.8e6 if (args.workload == "cfg2" and model.precision in ("3xf16r", "3xf16r2")) else None
+    # (profiles/kernels_r01_final.txt): CTA-pair kernel 217.5 + 115.2 MB, single-CTA ring kernel 256.9 + 119.0 MB, against
+    # 314.6 MB algorithmic (157.3 MB read + 157.3 MB written; the reads carry the 18x34 / 16x32 halo, part of the output is
+    # still in L2 when the kernel ends)
+    traffic = {"3xf16r2": 332.6e6, "3xf16r": 375.8e6}.get(model.precision) if args.workload == "cfg2" else None
     kname = {"3xf16r": "estd::ring::conv3d_ring_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule, fp16 two-term split)",
              "3xf16r2": "estd::ring2::conv3d_ring2_kernel / ring::conv3d_ring_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule, "
                         "CTA pairs where specialised, fp16 two-term split)"}.get(
@@ -335,9 +337,9 @@ def run_ours(args):
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "note": "achieved = ALGORITHMIC fp32 conv flops (54*Cin*Cout*Vx) / CUDA-event time, averaged over the step's launches; "
                         "the error-compensated split issues %.0fx that many tensor-core flops (tensor_flops_issued_TFLOPps / peak = the "
-                        "tensor-pipe fraction); peak = dense bf16 (cuBLAS).  The kernel is bound by the shared-memory pipe that feeds the "
-                        "tensor core (an M=128 N=96 K=16 MMA needs 56 wavefronts of operands for 48 cycles of math, profiles/README.md). "
-                        "share of step = %.1f%%" % (mma_per_flop, 100.0 * conv["share_ms_per_step"] / sum(k["share_ms_per_step"] for k in kernels.values())),
+                        "tensor-pipe fraction); peak = dense bf16 (cuBLAS).  ncu on the CTA-pair kernel: tensor pipe 82-88 %% active; the single-"
+                        "CTA ring kernel is bound by the shared-memory pipe that feeds the tensor core (an M=128 N=96 K=16 MMA needs 56 "
+                        "wavefronts of operands for 48 cycles of math; the pair needs 44), profiles/README.md. share of step = %.1f%%" % (mma_per_flop, 100.0 * conv["share_ms_per_step"] / sum(k["share_ms_per_step"] for k in kernels.values())),
                 "tensor_flops_issued_TFLOPps": (conv.get("TFLOPps") or 0.0) * mma_per_flop,
                 "tensor_pipe_frac_issued": (conv.get("TFLOPps") or 0.0) * mma_per_flop / peaks["bf16_sustained"]}
     cpu_base, _ = (None, None)

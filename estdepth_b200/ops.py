@@ -265,7 +265,7 @@ def check_status_async(device):
                                "call; its results are invalid -- use precision='3xtf32' or 'fp32' for this model")
         ent = None
     if ent is None:
-        host = torch.empty(1, dtype=torch.int32).pin_memory()
+        host = torch.empty(1, dtype=torch.int32, device="cpu").pin_memory()
         host.copy_(flag, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(flag.device))
