@@ -51,7 +51,7 @@ struct Shape {
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;
     static_assert(COLS <= 512, "ring accumulators must fit TMEM");
     static_assert(SMEM + 2048 <= 227 * 1024, "stages must fit shared memory");
-    static_assert(COUT % 16 == 0 && COUT <= 48 && N3 <= 256 && N3 % 32 == 0 && (MT == 2 || MT == 4), "bad shape");
+    static_assert(COUT % 16 == 0 && COUT <= 48 && N3 <= 256 && N3 % 16 == 0 && (MT == 2 || MT == 4), "bad shape");
 };
 
 
@@ -393,7 +393,7 @@ int dispatch_ring2(const estd_conv3d_desc* d, cudaStream_t stream, bool count_on
     const int nks = (cin_chunks + 3) / 4;                         // 16 channels per stage
     ESTD_REQUIRE(!d->planar && (d->dilation == 0 || d->dilation == 1), "estd_conv3d(ring2): 3x3x3, dilation 1 only");
 #define ESTD_RING2(NKS, COUT, MT) if (nks == NKS && d->cout_pad == COUT) return launch<Shape<NKS, COUT, MT>>(d, stream, count_only, n_ctas)
-    ESTD_RING2(2, 32, 4); ESTD_RING2(3, 32, 4);
+    ESTD_RING2(2, 32, 4); ESTD_RING2(3, 32, 4); ESTD_RING2(1, 16, 4); ESTD_RING2(2, 16, 4); ESTD_RING2(3, 48, 2);
 #undef ESTD_RING2
     return fail(ESTD_EUNSUPPORTED, "estd_conv3d(ring2): no kernel for %d input chunks -> cout_pad %d", cin_chunks, d->cout_pad);
 }

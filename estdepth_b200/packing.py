@@ -150,7 +150,7 @@ def pack_weight_ring(packed, cout_pad_tc=None, scale=None):
     return torch.stack(rots, dim=0).contiguous().view(torch.float32), k
 
 
-RING2_SHAPES = ((2, 32), (3, 32))
+RING2_SHAPES = ((2, 32), (3, 32), (1, 16), (2, 16), (3, 48))
 
 
 def pack_weight_ring2(packed, cout_pad_tc=None, scale=None):

@@ -59,7 +59,7 @@ extern "C" {
 
 #define ESTD_PREC_3XF16_RING2 4     /* ESTD_PREC_3XF16_RING on CTA pairs (tcgen05 cta_group::2, conv3d_ring2.cu): M = 256 per MMA, each CTA of
                                        the cluster holds half of the weight rows; `weight_tc` = packing [7 masks][3 rotations][nks][2 CTAs]
-                                       [9][hi,lo][2][3*cout_pad/2 rows][16 B]; cout_pad 32, 8 or 9 input chunks */
+                                       [9][hi,lo][2][3*cout_pad/2 rows][16 B]; same shapes as ESTD_PREC_3XF16_RING */
 
 ESTD_API int estd_version(void);
 ESTD_API const char* estd_last_error(void);
