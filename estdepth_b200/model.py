@@ -16,6 +16,8 @@ Protocol quirks reproduced on purpose: Q3 first window of 
 Q4 the returned hidden-state pose is the LAST MEMORY pose once a memory exists, Q5 targets are fused in order and
 later targets attend to already-fused values, Q6 mean-not-sum attention, Q7 rel_pose = P_j P_i^-1.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -82,7 +84,8 @@ class _Workspace(object):
 
 class DepthNetHybrid(nn.Module):
     def __init__(self, ndepths=64, depth_min=0.01, depth_max=10.0, resnet=50, IF_EST_transformer=True,
-                 align_corners=False, fix_stale_pose=False, precision="3xf16r2", feature_precision="3xf16", geometry="torch"):
+                 align_corners=False, fix_stale_pose=False, precision="3xf16r2", feature_precision="3xf16", geometry="torch",
+                 merged_pre2=True):
         """First five arguments: hybrid_models/model_hybrid.py:15-16.  Extra, keyword-only in practice:
 
         align_corners   grid_sample semantics of the warps: False = torch >= 1.3 (what the reference computes when run
@@ -121,6 +124,10 @@ class DepthNetHybrid(nn.Module):
         if precision not in ops.PRECISION:
             raise ValueError("precision must be one of %s" % sorted(ops.PRECISION))
         self.precision = precision
+        # merged_pre2: one pre2 convolution per target on the SUM of both sources' pre1 outputs (see _cost_volume)
+        self.merged_pre2 = bool(merged_pre2)
+        # overlap_context: context encoder / decoder on a second stream beside the matching-feature net (see prepare)
+        self.overlap_context = os.environ.get("ESTD_OVERLAP_CONTEXT", "1") != "0"
 
         self.matchingFeature = MatchingFeatureNet()
         self.matchingFeature.tensor_cores = (feature_precision == "3xf16")
@@ -178,11 +185,12 @@ class DepthNetHybrid(nn.Module):
             self._ws = _Workspace(device, D, H, W, rows)
         return self._ws
 
-    def _side_stream(self, device):
-        key = str(device)
-        if getattr(self, "_side", None) is None or self._side[0] != key:
-            self._side = (key, torch.cuda.Stream(device=device))
-        return self._side[1]
+    def _side_stream(self, device, name="geometry"):
+        key = (str(device), name)
+        streams = self.__dict__.setdefault("_side_streams", {})
+        if key not in streams:
+            streams[key] = torch.cuda.Stream(device=device)
+        return streams[key]
 
     def _conv(self, pc, *args, **kwargs):
         return ops.conv3d(pc, *args, precision=self.precision, **kwargs)
@@ -194,13 +202,26 @@ class DepthNetHybrid(nn.Module):
 
     # ------------------------------------------------------------------ the 3-D path for one batch element
     def _cost_volume(self, L, ws, ref_mix, src_mix, poses, K4, t, depth_values, out):
-        """get_costvolume (model_hybrid.py:62-102) for target view t+1 with sources t and t+2."""
+        """get_costvolume (model_hybrid.py:62-102) for target view t+1 with sources t and t+2:
+        cost = sum_s [x0_s + pre2(pre1(x0_s))] / 2  (:94-97, :100).
+
+        ``merged_pre2`` (default): pre2 = Conv3d + eval-mode BN is affine, so pre2(y_a) + pre2(y_b) = s * W (y_a + y_b) + 2 b
+        (SURVEY.md Appendix A.1): the second pre1 adds y_a in its epilogue (after its ReLU) and ONE pre2 with the doubled
+        offset runs per target -- 3 instead of 4 convolutions, same value up to fp32 summation order."""
+        homo = [self._homo_table[2 * t + n] if self._homo_table is not None else None for n in (0, 1)]
+        if self.merged_pre2:
+            assert out is not ws.x0 and out is not ws.a
+            h = homo[0] if homo[0] is not None else ops.homography_setup(poses[t + 1], poses[t], K4, ws.homo)
+            ops.warp_cost(ref_mix[t + 1], src_mix[t], h, depth_values, ws.x0, self.align_corners)
+            self._conv(L["pre1"], ws.x0, ws.y)
+            h = homo[1] if homo[1] is not None else ops.homography_setup(poses[t + 1], poses[t + 2], K4, ws.homo)
+            ops.warp_cost(ref_mix[t + 1], src_mix[t + 2], h, depth_values, ws.b, self.align_corners)
+            self._conv(L["pre1"], ws.b, ws.a, res0=ws.y)                                    # relu(bn(conv(x0_b))) + y_a
+            self._conv(L["pre2_pair"], ws.a, out, res0=ws.x0, res1=ws.b, post_scale=0.5)
+            return out
         for n, s in enumerate((t, t + 2)):
-            if self._homo_table is not None:
-                homo = self._homo_table[2 * t + n]
-            else:
-                homo = ops.homography_setup(poses[t + 1], poses[s], K4, ws.homo)
-            ops.warp_cost(ref_mix[t + 1], src_mix[s], homo, depth_values, ws.x0, self.align_corners)
+            h = homo[n] if homo[n] is not None else ops.homography_setup(poses[t + 1], poses[s], K4, ws.homo)
+            ops.warp_cost(ref_mix[t + 1], src_mix[s], h, depth_values, ws.x0, self.align_corners)
             self._conv(L["pre1"], ws.x0, ws.y)
             if n == 0:      # cost = x0 + pre2(pre1(x0))
                 self._conv(L["pre2"], ws.y, ws.cost, res0=ws.x0)
@@ -312,9 +333,28 @@ class DepthNetHybrid(nn.Module):
 
         # ---- 2-D feeders (cuDNN) ----
         t_prof = ops._pb()
-        feats = self.matchingFeature(imgs.reshape(B * V, 3, Hi, Wi)).reshape(B, V, 32, H, W)
-        maps = self.semanticFeature(imgs[:, 1:1 + T].reshape(B * T, 3, Hi, Wi))
-        semantic_vs = self.CostRegNet.context(maps).contiguous()                 # [B*T, D, H, W]
+        if self.overlap_context:
+            # the context branch (ResNet + 2-D decoder on the T target frames) does not meet the matching branch before dres2:
+            # it runs on its own stream beside the matching-feature net.  Most of its layers work at 1/8 .. 1/32 resolution
+            # and launch fewer CTAs than there are SMs, so the two branches fill each other's idle SMs and launch gaps.
+            main = torch.cuda.current_stream(dev)
+            ctx = self._side_stream(dev, "context")
+            imgs_ready = torch.cuda.Event()
+            imgs_ready.record(main)
+            ctx.wait_event(imgs_ready)
+            with torch.cuda.stream(ctx):
+                maps = self.semanticFeature(imgs[:, 1:1 + T].reshape(B * T, 3, Hi, Wi))
+                semantic_vs = self.CostRegNet.context(maps).contiguous()             # [B*T, D, H, W]
+                ctx_done = torch.cuda.Event()
+                ctx_done.record(ctx)
+            feats = self.matchingFeature(imgs.reshape(B * V, 3, Hi, Wi)).reshape(B, V, 32, H, W)
+            main.wait_event(ctx_done)
+            for t_ in (semantic_vs, maps[0]):
+                t_.record_stream(main)           # allocated on the context stream, consumed (and released) on the main one
+        else:
+            feats = self.matchingFeature(imgs.reshape(B * V, 3, Hi, Wi)).reshape(B, V, 32, H, W)
+            maps = self.semanticFeature(imgs[:, 1:1 + T].reshape(B * T, 3, Hi, Wi))
+            semantic_vs = self.CostRegNet.context(maps).contiguous()                 # [B*T, D, H, W]
         ops._pe(t_prof, "cudnn_2d_feeders")
         # camera algebra of both warps with the reference's own torch ops (~90 tiny launches): issued AFTER the feeders so that
         # the GPU is already busy while the host spends its millisecond on them, and on a side stream so that they run beside
@@ -348,7 +388,7 @@ class DepthNetHybrid(nn.Module):
         keys, values = [], []
         for b in range(B):
             self._homo_table = None if homo_tables is None else homo_tables[b]
-            ref_mix = [ops.premix(feats[b, v], L["pre0_ref"], L["pre0_bias"]) for v in range(V)]
+            ref_mix = [ops.premix(feats[b, v], L["pre0_ref"], L["pre0_bias"]) if 1 <= v <= T else None for v in range(V)]   # targets only
             src_mix = [ops.premix(feats[b, v], L["pre0_src"], None) for v in range(V)]
             kb, vb = [], []
             for t in range(T):

@@ -12,6 +12,8 @@ The 33-channel tensors of the reference (context map concatenated as channel 0, 
 in a 36-channel "canonical" order here: [ref channels 1..32 | ref channel 0 | 3 zero pads] so that the 32 matching
 channels stay chunk aligned and the context channel is a separate 1-chunk tensor.
 """
+import copy
+
 import torch
 
 from .ops import PackedConv
@@ -315,6 +317,10 @@ def pack_layers(sd, device):
     for v in layers.values():
         if isinstance(v, PackedConv):
             attach_tc(v)
+    # pre2 applied ONCE to the sum of both sources' pre1 outputs (conv + eval-BN is affine: pre2(a) + pre2(b) =
+    # s * W (a + b) + 2 b): the same packed weights with the offset doubled
+    layers["pre2_pair"] = copy.copy(layers["pre2"])
+    layers["pre2_pair"].shift = (layers["pre2"].shift * 2.0).contiguous()
     w_ref, w_src, bias = split_pre0(sd)
     layers["pre0_ref"], layers["pre0_src"], layers["pre0_bias"] = w_ref.to(device), w_src.to(device), bias.to(device)
     return layers

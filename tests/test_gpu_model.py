@@ -229,3 +229,20 @@ def test_matching_feature_net_tensor_core_path_equals_cudnn_fp32():
     e_tc = (got.cpu() - want).abs().max().item()
     print("psm features: max|.|=%.2f  cuDNN fp32 err %.2e  tensor-core err %.2e" % (scale, e_cudnn, e_tc))
     assert e_tc < 2e-5 * max(1.0, scale)          # fp32 round-off through ~45 layers
+
+
+def test_merged_pre2_equals_two_pre2_convolutions():
+    """One pre2 per target on the sum of both sources' pre1 outputs (model.merged_pre2, the default) is the reference's
+    sum of two pre2 applications (hybrid_models/model_hybrid.py:94-97) up to fp32 summation order: pre2 is affine."""
+    torch.backends.cudnn.allow_tf32 = False
+    model, _ = synth_model_and_state(18, 32)
+    model.cuda()
+    runs = {}
+    for merged in (True, False):
+        model.merged_pre2 = merged
+        runs[merged] = _run_joint(model, 128, 160)
+    for (out_m, state_m, _), (out_s, state_s, _) in zip(runs[True], runs[False]):
+        for key in out_m:
+            d = float((out_m[key] - out_s[key]).abs().max())
+            assert d < (2e-4 if key[0] == "depth" else 5e-5), (key, d)
+        assert float((state_m["values"][0] - state_s["values"][0]).abs().max()) < 1e-4
