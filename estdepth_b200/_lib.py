@@ -41,6 +41,7 @@ SIGNATURES = {
     "estd_homography_from_proj": (_I, [_P, _P, _P, _P]),
     "estd_volume_warp_setup": (_I, [_P, _P, _P, _P, _P]),
     "estd_premix": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "estd_premix_batch": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "estd_warp_cost": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "estd_conv3d_num_ctas": (_I, [ctypes.POINTER(ConvDesc)]),
     "estd_conv3d": (_I, [ctypes.POINTER(ConvDesc), _P]),

@@ -92,6 +92,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nks = p.nks;
 
+    pdl_launch_dependents();                 // the next kernel of the stream may start its prologue as SMs free up
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], SPLIT_THREADS); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_THREADS); }
@@ -103,6 +104,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    pdl_wait();                              // the prologue above overlapped the previous kernel's tail; activations from here on
 
     const int n_mine = (p.n_units > (int)blockIdx.x) ? (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     auto unit_origin = [&](int k, int& d, int& h0, int& w0, int& slice) {
@@ -323,7 +325,10 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
         if (e != cudaSuccess) return fail(ESTD_ECUDA, "estd_conv3d(planar): cannot reserve %zu B of shared memory: %s", S::SMEM, cudaGetErrorString(e));
         attr_set = true;
     }
-    kern<<<grid, THREADS, S::SMEM, stream>>>(map0, map1, p);
+    {
+        cudaError_t e = launch_pdl(kern, grid, THREADS, S::SMEM, stream, map0, map1, p);
+        if (e != cudaSuccess) return fail(ESTD_ECUDA, "%s launch: %s", __FILE__, cudaGetErrorString(e));
+    }
     return check_launch("estd_conv3d(planar)");
 }
 

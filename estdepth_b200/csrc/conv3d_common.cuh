@@ -1,6 +1,8 @@
 // Pieces shared by the two implementations of K2 (conv3d.cu: exact fp32 SIMT; conv3d_tc.cu: 3xTF32 on tcgen05):
 // mbarrier / TMA PTX wrappers, the vol4 tensor-map builder and the fused epilogue.
 #pragma once
+#include <cstdlib>
+#include <utility>
 #include <cuda.h>
 #include "common.cuh"
 
@@ -136,6 +138,28 @@ inline int make_vol4_tensor_map(CUtensorMap* map, const float* base, int chunks,
     if (r != CUDA_SUCCESS)
         return fail(ESTD_ECUDA, "cuTensorMapEncodeTiled failed (%d) for vol4 [%d][%d][%d][%d][4]", (int)r, chunks, D, H, W);
     return ESTD_OK;
+}
+
+// ESTD_PDL=0 launches the tensor-core kernels without programmatic stream serialisation (default: on)
+inline bool pdl_enabled() {
+    static const bool on = []() { const char* e = getenv("ESTD_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+// <<<grid, threads, smem, stream>>> with the programmatic-stream-serialisation attribute (tc_ptx.cuh: pdl_wait)
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int threads, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 inline int sm_count() {

@@ -110,6 +110,7 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = cluster_ctarank();
 
+    pdl_launch_dependents();                 // the next kernel of the stream may start its prologue as SMs free up
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 2); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 2); }
@@ -121,6 +122,7 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    pdl_wait();                              // the prologue above overlapped the previous kernel's tail; activations from here on
 
     // every ring slot starts at zero: all MMAs accumulate
     if (warp >= 4 && warp < FIRST_SPLIT_WARP) {
@@ -372,7 +374,10 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
         if (e != cudaSuccess) return fail(ESTD_ECUDA, "estd_conv3d(ring2): cannot reserve %zu B of shared memory: %s", S::SMEM, cudaGetErrorString(e));
         attr_set = true;
     }
-    kern<<<grid, THREADS, S::SMEM, stream>>>(map0, map1, p);
+    {
+        cudaError_t e = launch_pdl(kern, grid, THREADS, S::SMEM, stream, map0, map1, p);
+        if (e != cudaSuccess) return fail(ESTD_ECUDA, "%s launch: %s", __FILE__, cudaGetErrorString(e));
+    }
     return check_launch("estd_conv3d(ring2)");
 }
 

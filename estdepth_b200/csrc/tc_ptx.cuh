@@ -84,6 +84,13 @@ __device__ __forceinline__ uint32_t make_idesc(uint32_t fmt, int n) {
 }
 
 
+// ---- programmatic dependent launch: a kernel launched with programmatic stream serialisation may start (prologue: barrier
+// init, TMEM allocation, parameter loads) while its predecessor in the stream drains; pdl_wait() returns once the
+// predecessor has completed and its writes are visible, and must precede every access to activations.  Both are no-ops
+// for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- CTA pair (cta_group::2): two CTAs of a cluster share one MMA (M = 256: 128 rows each; each CTA supplies half of B)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

@@ -127,7 +127,8 @@ class DepthNetHybrid(nn.Module):
         # merged_pre2: one pre2 convolution per target on the SUM of both sources' pre1 outputs (see _cost_volume)
         self.merged_pre2 = bool(merged_pre2)
         # overlap_context: context encoder / decoder on a second stream beside the matching-feature net (see prepare)
-        self.overlap_context = os.environ.get("ESTD_OVERLAP_CONTEXT", "1") != "0"
+        self.overlap_context = int(os.environ.get("ESTD_OVERLAP_CONTEXT", "2"))    # 0 off, 1 join after the feature nets, 2 join at dres2
+        self._ctx_done = None
 
         self.matchingFeature = MatchingFeatureNet()
         self.matchingFeature.tensor_cores = (feature_precision == "3xf16")
@@ -237,6 +238,9 @@ class DepthNetHybrid(nn.Module):
         self._conv(L["dres0.1"], ws.a, ws.b)
         self._conv(L["dres1.0"], ws.b, ws.a)
         self._conv(L["dres1.1"], ws.a, ws.b)
+        if self._ctx_done is not None:
+            torch.cuda.current_stream(dev).wait_event(self._ctx_done)
+            self._ctx_done = None
         ops.scalar_to_vol4(semantic_vs_t, ws.sem)
         self._conv(L["dres2"], ws.b, ws.z, in1=ws.sem)
         value = torch.empty(4, D, H, W, 4, device=dev, dtype=torch.float32)
@@ -348,9 +352,12 @@ class DepthNetHybrid(nn.Module):
                 ctx_done = torch.cuda.Event()
                 ctx_done.record(ctx)
             feats = self.matchingFeature(imgs.reshape(B * V, 3, Hi, Wi)).reshape(B, V, 32, H, W)
-            main.wait_event(ctx_done)
             for t_ in (semantic_vs, maps[0]):
                 t_.record_stream(main)           # allocated on the context stream, consumed (and released) on the main one
+            if self.overlap_context >= 2:
+                self._ctx_done = ctx_done        # joined where the context map is first needed (dres2 of the first target)
+            else:
+                main.wait_event(ctx_done)
         else:
             feats = self.matchingFeature(imgs.reshape(B * V, 3, Hi, Wi)).reshape(B, V, 32, H, W)
             maps = self.semanticFeature(imgs[:, 1:1 + T].reshape(B * T, 3, Hi, Wi))
@@ -388,8 +395,9 @@ class DepthNetHybrid(nn.Module):
         keys, values = [], []
         for b in range(B):
             self._homo_table = None if homo_tables is None else homo_tables[b]
-            ref_mix = [ops.premix(feats[b, v], L["pre0_ref"], L["pre0_bias"]) if 1 <= v <= T else None for v in range(V)]   # targets only
-            src_mix = [ops.premix(feats[b, v], L["pre0_src"], None) for v in range(V)]
+            mix = ops.premix_batch(feats[b], L["pre0_both"], L["pre0_both_bias"])          # [V, 16, H, W, 4], one launch
+            ref_mix = [mix[v, :8] for v in range(V)]
+            src_mix = [mix[v, 8:] for v in range(V)]
             kb, vb = [], []
             for t in range(T):
                 self._cost_volume(L, ws, ref_mix, src_mix, poses[b], K4[b], t, depth_values, ws.cost)

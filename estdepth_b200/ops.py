@@ -180,6 +180,18 @@ def premix(fea_chw, weight, bias=None, out=None):
     return out
 
 
+def premix_batch(fea_nchw, weight, bias=None, out=None):
+    """fea [N,Cin,H,W], weight [Cout,Cin], bias [Cout]|None -> [N,Cout/4,H,W,4] (N map4 tensors, one launch)."""
+    n, cin, H, W = fea_nchw.shape
+    cout = weight.shape[0]
+    out = torch.empty(n, cout // 4, H, W, 4, device=fea_nchw.device, dtype=torch.float32) if out is None else out
+    t = _pb()
+    check(_lib.get().estd_premix_batch(_ptr(fea_nchw), _ptr(weight), _ptr(bias), _ptr(out), n, cin, cout, H, W, _stream()),
+          "estd_premix_batch")
+    _pe(t, "premix", 2.0 * n * cin * cout * H * W, 4.0 * n * (cin + cout) * H * W)
+    return out
+
+
 def warp_cost(ref_mix, src_mix, homo12, depth_values, out=None, align_corners=False):
     """map4 [C/4,H,W,4] x2, [12], [D] -> vol4 [C/4,D,H,W,4]."""
     chunks, H, W, _ = ref_mix.shape

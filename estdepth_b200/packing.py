@@ -323,4 +323,7 @@ def pack_layers(sd, device):
     layers["pre2_pair"].shift = (layers["pre2"].shift * 2.0).contiguous()
     w_ref, w_src, bias = split_pre0(sd)
     layers["pre0_ref"], layers["pre0_src"], layers["pre0_bias"] = w_ref.to(device), w_src.to(device), bias.to(device)
+    # both halves stacked: one premix launch per sequence gives every frame's target-side (chunks 0..7) and source-side mix
+    layers["pre0_both"] = torch.cat([layers["pre0_ref"], layers["pre0_src"]], 0).contiguous()
+    layers["pre0_both_bias"] = torch.cat([layers["pre0_bias"], torch.zeros_like(layers["pre0_bias"])]).contiguous()
     return layers

@@ -92,6 +92,11 @@ ESTD_API int estd_volume_warp_setup(const float* pose_i, const float* pose_j, co
 ESTD_API int estd_premix(const float* fea_chw, const float* weight, const float* bias, float* out_map4,
                 int cin, int cout, int H, int W, void* stream);
 
+/* The same for n_maps maps in one launch: fea [n_maps][Cin][H][W] -> out [n_maps][C/4][H][W][4].  With the two halves of
+ * pre0 stacked into one [2*32][32] matrix, chunks 0..7 of a map are its target-side mix and 8..15 its source-side mix. */
+ESTD_API int estd_premix_batch(const float* fea_nchw, const float* weight, const float* bias, float* out_map4,
+                int n_maps, int cin, int cout, int H, int W, void* stream);
+
 /* x0 vol4 [C/4][D][H][W][4] = ref_mix[c,h,w] + bilinear_zeros(src_mix[c], homography(d,h,w)).
  * homo12: device pointer from estd_homography_setup.  depth_values: device [D].
  * align_corners: 0 = grid_sample semantics of torch >= 1.3 (what the oracle runs), 1 = torch 1.2 (quirk Q1). */

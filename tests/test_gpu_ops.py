@@ -70,6 +70,22 @@ def test_premix_matches_matmul():
     assert maxdiff(out, want) < 2e-5            # 32-term fp32 dot products of O(1) values
 
 
+def test_premix_batch_is_the_stacked_single_map_premix():
+    """One launch for all frames and both halves of pre0 (what the model issues) == per-map, per-half launches, bit for bit
+    (ragged pixel count: 33 * 37 is not a multiple of the 32-pixel warp tile)."""
+    g = torch.Generator().manual_seed(3)
+    fea = torch.randn(5, 32, 33, 37, generator=g).to(DEV)
+    w_ref, w_src = (torch.randn(32, 32, generator=g) / 5).to(DEV), (torch.randn(32, 32, generator=g) / 5).to(DEV)
+    b = torch.randn(32, generator=g).to(DEV)
+    both = ops.premix_batch(fea, torch.cat([w_ref, w_src], 0).contiguous(), torch.cat([b, torch.zeros_like(b)]).contiguous())
+    assert tuple(both.shape) == (5, 16, 33, 37, 4)
+    for v in range(5):
+        assert torch.equal(both[v, :8], ops.premix(fea[v], w_ref, b))
+        assert torch.equal(both[v, 8:], ops.premix(fea[v], w_src, None))
+    want = to_map4((torch.einsum("oc,chw->ohw", w_src.double().cpu(), fea[4].double().cpu())).float())
+    assert maxdiff(both[4, 8:], want) < 2e-5
+
+
 @pytest.mark.parametrize("src", [0, 2])
 def test_homo_warping_vs_reference_golden(src):
     """ops.homo_warping == the reference's homo_warping on the same inputs (golden from oracle/make_golden.py)."""
