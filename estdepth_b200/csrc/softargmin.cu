@@ -153,6 +153,40 @@ __global__ void __launch_bounds__(256) vol4_to_nchw_kernel(const float* __restri
     }
 }
 
+// Bilinear resize (ATen upsample_bilinear2d, align_corners=False: src = max(0, (dst + 0.5) * in/out - 0.5), second tap clamped to
+// the last row / column) of small NCHW maps [N][C][h][w] straight into vol4 [C/4][N][H][W][4], with an optional per-channel
+// offset + ReLU applied to the taps as they are read (the SPP branches of the matching-feature net: 1x1 conv + BN + ReLU on the
+// pooled map, F.upsample, torch.cat -- networks/psm_submodule.py:56-76,104-114).  One thread = one output pixel of one chunk.
+__global__ void __launch_bounds__(256) upsample_bilinear_vol4_kernel(const float* __restrict__ src, const float* __restrict__ bias,
+                                                                     float* __restrict__ vol4, int C, int N, int h, int w,
+                                                                     int H, int W, int relu, size_t total) {
+    const float rh = (float)h / (float)H, rw = (float)w / (float)W;
+    const size_t HW = (size_t)H * W, hw = (size_t)h * w;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = i % HW;
+        const size_t n = (i / HW) % N;
+        const size_t j = i / (HW * N);
+        const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+        const float sy = fmaxf(__fadd_rn(__fmul_rn(rh, (float)y + 0.5f), -0.5f), 0.0f);
+        const float sx = fmaxf(__fadd_rn(__fmul_rn(rw, (float)x + 0.5f), -0.5f), 0.0f);
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int yp = (y0 < h - 1) ? w : 0, xp = (x0 < w - 1) ? 1 : 0;
+        const float ly1 = sy - (float)y0, ly0 = 1.0f - ly1, lx1 = sx - (float)x0, lx0 = 1.0f - lx1;
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = (int)j * 4 + k;
+            const float* s = src + (n * C + c) * hw + (size_t)y0 * w + x0;
+            float v00 = __ldg(s), v01 = __ldg(s + xp), v10 = __ldg(s + yp), v11 = __ldg(s + yp + xp);
+            if (bias) { const float b = __ldg(bias + c); v00 += b; v01 += b; v10 += b; v11 += b; }
+            if (relu) { v00 = fmaxf(v00, 0.0f); v01 = fmaxf(v01, 0.0f); v10 = fmaxf(v10, 0.0f); v11 = fmaxf(v11, 0.0f); }
+            o[k] = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01))),
+                             __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11))));
+        }
+        st4(vol4 + i * 4, make_float4(o[0], o[1], o[2], o[3]));
+    }
+}
+
 __global__ void __launch_bounds__(256) scalar_to_vol4_kernel(const float* __restrict__ in, float* __restrict__ out, size_t vox) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vox; i += (size_t)gridDim.x * blockDim.x)
         st4(out + i * 4, make_float4(__ldg(in + i), 0.0f, 0.0f, 0.0f));
@@ -205,6 +239,16 @@ extern "C" int estd_vol4_to_nchw(const float* vol4, float* nchw, int N, int C, i
     const size_t HW = (size_t)H * W, total = HW * N * (C / 4);
     estd::vol4_to_nchw_kernel<<<estd::ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(vol4, nchw, C, N, HW, total);
     return estd::check_launch("estd_vol4_to_nchw");
+}
+
+extern "C" int estd_upsample_bilinear_vol4(const float* src_nchw, const float* bias, float* vol4, int N, int C, int h, int w,
+                                           int H, int W, int relu, void* stream) {
+    ESTD_REQUIRE(src_nchw && vol4 && C > 0 && (C % 4) == 0 && N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && estd::aligned16(vol4),
+                 "estd_upsample_bilinear_vol4: bad arguments");
+    const size_t total = (size_t)H * W * N * (C / 4);
+    estd::upsample_bilinear_vol4_kernel<<<estd::ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(src_nchw, bias, vol4, C, N, h, w,
+                                                                                                  H, W, relu, total);
+    return estd::check_launch("estd_upsample_bilinear_vol4");
 }
 
 extern "C" int estd_scalar_to_vol4(const float* dhw, float* vol4_1chunk, int D, int H, int W, void* stream) {

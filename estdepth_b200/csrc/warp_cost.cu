@@ -17,48 +17,86 @@ namespace estd {
 constexpr int kPremixMaxC = 64;
 
 // One warp = 32 consecutive pixels x ONE output chunk (4 channels) of one map; a block = 32 pixels x all chunks, persistent
-// over the flat (map, pixel tile) list so that the weights are staged in shared memory once per block.  (A thread per pixel
-// computing every output left the kernel latency bound -- 75 blocks, 1024 dependent FMAs each: 28 us for 2.5 MB -- and a
-// block per tile paid the weight prologue 20 times per SM: 176 us for 5 maps.)  CIN > 0: compile-time input width, weights
-// read as broadcast 16-byte vectors.  The accumulation order (ci ascending, bias last) is part of the parity contract and
-// does not depend on the tiling.
+// over the flat (map, pixel tile) list so that the weights are staged in shared memory once per block.  CIN > 0 (compile-time
+// input width): the block stages the tile's CIN x 32 inputs in shared memory -- a few loads per thread, all in flight at once,
+// the next tile's issued before this tile's FMAs -- and reads the weights as broadcast 16-byte vectors.
+// History: a thread per pixel computing every output was latency bound (75 blocks, 1024 dependent FMA+LDS each: 28 us for
+// 2.5 MB); a block per tile paid the weight prologue 20 times per SM (176 us for 5 maps); per-thread register loads of the 32
+// inputs were scheduled 3 at a time by ptxas whatever the source order (78 us).
+// The accumulation order (ci ascending, bias last) is part of the parity contract and does not depend on the tiling.
 template <int CIN>
 __global__ void __launch_bounds__(512) premix_kernel(const float* __restrict__ fea, const float* __restrict__ weight,
                                                      const float* __restrict__ bias, float* __restrict__ out,
                                                      int cin_rt, int cout, int HW, int n_maps) {
     extern __shared__ __align__(16) float s_w[];        // [cout][cin] then [cout] bias
+    constexpr int XS = CIN > 0 ? CIN : 1;
+    constexpr int PER = (XS * 32 + 127) / 128;          // staged elements per thread at the smallest block (128 threads)
+    __shared__ float s_x[2][XS][32];
     const int cin = CIN > 0 ? CIN : cin_rt;
     float* s_b = s_w + cout * cin;
     for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) s_w[i] = weight[i];
     for (int i = threadIdx.x; i < cout; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.0f;
     __syncthreads();
-    const int c4 = 4 * (threadIdx.x >> 5);
-    if (c4 >= cout) return;
+    const int lane = threadIdx.x & 31;
+    const int c4 = 4 * (threadIdx.x >> 5);              // blockDim.x == 32 * cout / 4: every warp owns a chunk
     const int tiles = (HW + 31) >> 5;
+    const int units = tiles * n_maps;
     const float b0 = s_b[c4], b1 = s_b[c4 + 1], b2 = s_b[c4 + 2], b3 = s_b[c4 + 3];
-    for (int u = blockIdx.x; u < tiles * n_maps; u += gridDim.x) {
-        const int map = u / tiles;
-        const int p = (u - map * tiles) * 32 + (threadIdx.x & 31);
-        if (p >= HW) continue;
-        const float* f = fea + (size_t)map * cin * HW + p;
-        float* o = out + (size_t)map * cout * HW;
-        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if constexpr (CIN > 0) {
-            float x[CIN];
+
+    if constexpr (CIN > 0) {
+        float r[PER];
+        auto fetch = [&](int u) {                        // this thread's share of tile u's inputs -> registers
+            const int map = u / tiles, p0 = (u - map * tiles) * 32;
+            const float* f = fea + (size_t)map * CIN * HW;
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci) x[ci] = __ldg(f + (size_t)ci * HW);
+            for (int q = 0; q < PER; ++q) {
+                const int e = (int)threadIdx.x + q * (int)blockDim.x;
+                const int ci = e >> 5, p = p0 + (e & 31);
+                r[q] = (e < CIN * 32 && p < HW) ? __ldg(f + (size_t)ci * HW + p) : 0.0f;
+            }
+        };
+        auto park = [&](int buf) {
 #pragma unroll
-            for (int ci = 0; ci < CIN; ci += 4) {
+            for (int q = 0; q < PER; ++q) {
+                const int e = (int)threadIdx.x + q * (int)blockDim.x;
+                if (e < CIN * 32) s_x[buf][e >> 5][e & 31] = r[q];
+            }
+        };
+        int buf = 0;
+        if ((int)blockIdx.x < units) { fetch(blockIdx.x); park(0); }
+        __syncthreads();
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int un = u + (int)gridDim.x;
+            if (un < units) fetch(un);                   // in flight during this tile's FMAs
+            const int map = u / tiles;
+            const int p = (u - map * tiles) * 32 + lane;
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float4 w = *reinterpret_cast<const float4*>(s_w + (c4 + k) * CIN + ci);
-                    acc[k] = fmaf(w.x, x[ci], acc[k]);
-                    acc[k] = fmaf(w.y, x[ci + 1], acc[k]);
-                    acc[k] = fmaf(w.z, x[ci + 2], acc[k]);
-                    acc[k] = fmaf(w.w, x[ci + 3], acc[k]);
+            for (int k = 0; k < 4; ++k) {
+                const float4* wr = reinterpret_cast<const float4*>(s_w + (c4 + k) * CIN);
+#pragma unroll
+                for (int ci = 0; ci < CIN; ci += 4) {
+                    const float4 w = wr[ci >> 2];
+                    acc[k] = fmaf(w.x, s_x[buf][ci][lane], acc[k]);
+                    acc[k] = fmaf(w.y, s_x[buf][ci + 1][lane], acc[k]);
+                    acc[k] = fmaf(w.z, s_x[buf][ci + 2][lane], acc[k]);
+                    acc[k] = fmaf(w.w, s_x[buf][ci + 3][lane], acc[k]);
                 }
             }
-        } else {
+            if (p < HW)
+                st4(out + (size_t)map * cout * HW + ((size_t)(c4 >> 2) * HW + p) * 4,
+                    make_float4(acc[0] + b0, acc[1] + b1, acc[2] + b2, acc[3] + b3));
+            if (un < units) park(buf ^ 1);               // the other buffer: nobody reads it before the barrier below
+            __syncthreads();
+            buf ^= 1;
+        }
+    } else {
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int map = u / tiles;
+            const int p = (u - map * tiles) * 32 + lane;
+            if (p >= HW) continue;
+            const float* f = fea + (size_t)map * cin * HW + p;
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             float x[kPremixMaxC];
 #pragma unroll
             for (int ci = 0; ci < kPremixMaxC; ++ci)
@@ -70,8 +108,9 @@ __global__ void __launch_bounds__(512) premix_kernel(const float* __restrict__ f
                 for (int ci = 0; ci < kPremixMaxC; ++ci)
                     if (ci < cin) acc[k] = fmaf(wr[ci], x[ci], acc[k]);
             }
+            st4(out + (size_t)map * cout * HW + ((size_t)(c4 >> 2) * HW + p) * 4,
+                make_float4(acc[0] + b0, acc[1] + b1, acc[2] + b2, acc[3] + b3));
         }
-        st4(o + ((size_t)(c4 >> 2) * HW + p) * 4, make_float4(acc[0] + b0, acc[1] + b1, acc[2] + b2, acc[3] + b3));
     }
 }
 
@@ -202,7 +241,7 @@ extern "C" int estd_premix_batch(const float* fea_nchw, const float* weight, con
     }
     const int grid = (int)(units < 2ll * sms ? units : 2ll * sms);
     const int threads = 32 * (cout / 4);
-    if (cin == 32)
+    if (cin == 32 && threads >= 128)             // the staged kernel spreads a tile's 32 x 32 inputs over >= 128 threads
         estd::premix_kernel<32><<<grid, threads, smem, (cudaStream_t)stream>>>(fea_nchw, weight, bias, out_map4, cin, cout, HW, n_maps);
     else
         estd::premix_kernel<0><<<grid, threads, smem, (cudaStream_t)stream>>>(fea_nchw, weight, bias, out_map4, cin, cout, HW, n_maps);

@@ -286,8 +286,15 @@ class MatchingFeatureNet(nn.Module):
             br = getattr(self, "branch%d" % idx)
             # the pooling windows nest (4, 8, 16, 32): each level is the 2x2 average of the previous one
             pooled = F.avg_pool2d(deep, 4, 4) if pooled is None else F.avg_pool2d(pooled, 2, 2)
-            b = F.interpolate(_folded(pooled, br[1][0], br[1][1], relu=True), size=(H, W), mode="bilinear", align_corners=False)
-            ops.nchw_to_vol4(b.contiguous(), cat[48 + 8 * slot:56 + 8 * slot])
+            # 1x1 conv + BN + ReLU on the pooled map, bilinear resize, concat: one small GEMM (folded weights) + one kernel that
+            # adds the offset, applies the ReLU to the taps, interpolates and writes the branch's chunks of `cat`
+            wf, bf = _folded.params(br[1][0], br[1][1])
+            n_, c_, ph, pw = pooled.shape
+            tf32 = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False             # strict fp32, whatever the caller's global setting
+            y = torch.matmul(wf.view(wf.shape[0], c_), pooled.reshape(n_, c_, ph * pw)).view(n_, wf.shape[0], ph, pw)
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            ops.upsample_bilinear_vol4(y, cat[48 + 8 * slot:56 + 8 * slot], bias=bf, relu=True)
         fused = self._conv_tc(P["fuse"], cat, vol(32))
         return ops.vol4_to_nchw(self._conv_tc(P["last"], fused, vol(8), taps=1))
 

@@ -371,6 +371,20 @@ def vol4_to_nchw(v, out=None):
     return out
 
 
+def upsample_bilinear_vol4(src, out, bias=None, relu=False):
+    """F.interpolate(relu?(src + bias), size=out's, mode='bilinear', align_corners=False) of NCHW maps [N,C,h,w], written as
+    vol4 [C/4,N,H,W,4] into ``out`` (which may be a chunk slice of a wider vol4 buffer)."""
+    N, C, h, w = src.shape
+    chunks, N2, H, W, _ = out.shape
+    if chunks * 4 != C or N2 != N:
+        raise RuntimeError("upsample_bilinear_vol4: %s does not hold %s" % (tuple(out.shape), tuple(src.shape)))
+    t = _pb()
+    check(_lib.get().estd_upsample_bilinear_vol4(_ptr(src), _ptr(bias), _ptr(out), N, C, h, w, H, W, int(bool(relu)), _stream()),
+          "estd_upsample_bilinear_vol4")
+    _pe(t, "layout", 0.0, 4.0 * N * C * (h * w + H * W))
+    return out
+
+
 def est_attend(key_t, src_keys, src_values, warp30, depth_values, depth_min, depth_interval, out=None,
                align_corners=False):
     """key_t vol4 [4,D,H,W,4]; lists of N source key/value vol4; warp30 [N,30] -> h vol4 [4,D,H,W,4]."""

@@ -176,6 +176,11 @@ ESTD_API int estd_ncdhw_to_vol4(const float* ncdhw, float* vol4, int C, int D, i
  * tensor-core convolutions of the matching-feature net (networks/psm_submodule.py:14-37,51-54) */
 ESTD_API int estd_nchw_to_vol4(const float* nchw, float* vol4, int N, int C, int H, int W, void* stream);
 ESTD_API int estd_vol4_to_nchw(const float* vol4, float* nchw, int N, int C, int H, int W, void* stream);
+/* vol4 [C/4][N][H][W][4] = bilinear resize (align_corners = 0, ATen upsample_bilinear2d arithmetic) of relu?(src + bias[c]),
+ * src NCHW [N][C][h][w]; bias may be NULL.  Replaces conv-bias/ReLU + F.upsample + torch.cat of the SPP branches
+ * (networks/psm_submodule.py:56-76,104-114); `vol4` may be a chunk slice of a wider vol4 buffer. */
+ESTD_API int estd_upsample_bilinear_vol4(const float* src_nchw, const float* bias, float* vol4, int N, int C, int h, int w,
+                                int H, int W, int relu, void* stream);
 /* out vol4 (1 chunk) = (in[d,h,w], 0, 0, 0): the 2-D context map entering dres2 as one 3-D channel
  * (hybrid_depth_decoder.py:195, quirk Q13) */
 ESTD_API int estd_scalar_to_vol4(const float* dhw, float* vol4_1chunk, int D, int H, int W, void* stream);

@@ -63,3 +63,9 @@ prob = [torch.empty(4 * H, 4 * W, device=dev) for _ in range(3)]
 report("K4 head+argmin", timed(lambda i: ops.head_softargmin(dv, hidden=keys[i % 4], head_w=hw, head_b=hb, logits_out=logits[i % 3],
                                                              depth_out=depth[i % 3], prob_out=prob[i % 3], up=4)),
        4.0 * (16 * D * H * W + D * H * W + 2 * 16 * H * W))
+
+# premix: both halves of pre0 on every frame of a window, one launch (5 x [32,H,W] -> 5 x [16 chunks,H,W,4])
+fea = [torch.randn(5, 32, H, W, generator=g).to(dev) for _ in range(3)]
+w64, b64 = (torch.randn(64, 32, generator=g) / 5).to(dev), torch.randn(64, generator=g).to(dev)
+mix = [torch.empty(5, 16, H, W, 4, device=dev) for _ in range(3)]
+report("premix x5", timed(lambda i: ops.premix_batch(fea[i % 3], w64, b64, out=mix[i % 3])), 4.0 * 5 * (32 + 64) * H * W)

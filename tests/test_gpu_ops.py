@@ -86,6 +86,23 @@ def test_premix_batch_is_the_stacked_single_map_premix():
     assert maxdiff(both[4, 8:], want) < 2e-5
 
 
+@pytest.mark.parametrize("h,w,H,W", [(3, 5, 120, 160), (7, 10, 120, 160), (15, 20, 120, 160), (30, 40, 120, 160), (1, 1, 9, 7), (5, 4, 13, 11)])
+def test_upsample_bilinear_vol4_matches_interpolate(h, w, H, W):
+    """SPP branch tail (networks/psm_submodule.py:104-114): ReLU(conv + b) -> F.upsample(bilinear) -> cat, as one kernel
+    writing a chunk slice of a wider vol4 buffer; arithmetic of ATen's upsample_bilinear2d (align_corners=False)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(h * 100 + w)
+    src = torch.randn(3, 8, h, w, generator=g).to(DEV)
+    bias = torch.randn(8, generator=g).to(DEV)
+    wide = torch.full((5, 3, H, W, 4), 7.0, device=DEV)
+    ops.upsample_bilinear_vol4(src, wide[2:4], bias=bias, relu=True)
+    want = F.interpolate(F.relu(src + bias.view(1, -1, 1, 1)), size=(H, W), mode="bilinear", align_corners=False)
+    assert maxdiff(wide[2:4], ops.nchw_to_vol4(want.contiguous()).cpu()) < 2e-6
+    assert float((wide[:2] - 7.0).abs().max()) == 0.0 and float((wide[4:] - 7.0).abs().max()) == 0.0      # neighbours untouched
+    plain = ops.upsample_bilinear_vol4(src, torch.empty(2, 3, H, W, 4, device=DEV))
+    assert maxdiff(plain, ops.nchw_to_vol4(F.interpolate(src, size=(H, W), mode="bilinear", align_corners=False).contiguous()).cpu()) < 2e-6
+
+
 @pytest.mark.parametrize("src", [0, 2])
 def test_homo_warping_vs_reference_golden(src):
     """ops.homo_warping == the reference's homo_warping on the same inputs (golden from oracle/make_golden.py)."""
