@@ -257,6 +257,16 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    # host issue time of a step (informational): two steps enqueued on an idle GPU without waiting -- few enough launches to
+    # fit the driver's launch queue, so the host is not throttled by the device.  Well below ms_per_step = the GPU is the
+    # bottleneck and the host runs ahead; close to it = the step is launch/host bound.
+    barrier()
+    import time as _time
+    t0 = _time.perf_counter()
+    step_resident()
+    step_resident()
+    host_issue_ms = (_time.perf_counter() - t0) * 1e3 / 2
+    barrier()
 
     # profile pass: CUDA events around every kernel family of the library (same stream, same shapes)
     ops.PROFILE = ops.KernelProfile()
@@ -355,7 +365,7 @@ def run_ours(args):
                        "l2": "volumes are 157 MB each (> 126 MB L2); no explicit flush", "cudnn_tf32": False,
                        "camera_parameters": "host tensors (matrices of the warps derived on the host with the reference's torch ops)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_base}
+            "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_base}
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()

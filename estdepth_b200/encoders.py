@@ -17,6 +17,8 @@ written against small functional helpers rather than mirroring the reference's m
 import numpy as np
 import torch
 import torch.nn as nn
+import weakref
+
 import torch.nn.functional as F
 import torchvision.models as tvm
 
@@ -59,13 +61,16 @@ class _FoldedConv(object):
         ver = (conv.weight.data_ptr(), conv.weight._version, bn.weight._version, bn.bias._version,
                bn.running_mean._version, bn.running_var._version)
         ent = self.cache.get(id(conv))
-        if ent is None or ent[0] != ver:
+        # the entry remembers WHICH module it was derived from: this cache outlives models, and a new model's layer can get a
+        # dead layer's id() -- and, through the caching allocator, its weight address and version counters too
+        if ent is None or ent[0] != ver or ent[3]() is not conv:
             with torch.no_grad():
                 s = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
                 w = (conv.weight.double() * s.view(-1, 1, 1, 1)).float().contiguous()
                 b = (bn.bias.double() - bn.running_mean.double() * s).float().contiguous()
-            ent = (ver, w, b)
-            self.cache[id(conv)] = ent
+            key = id(conv)
+            ent = (ver, w, b, weakref.ref(conv, lambda _, key=key, cache=self.cache: cache.pop(key, None)))
+            self.cache[key] = ent
         return ent[1], ent[2]
 
     def __call__(self, x, conv, bn, relu=False, residual=None):

@@ -67,7 +67,9 @@ def _pe(start, family, flops=0.0, nbytes=0.0):
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """cudaStream_t of torch's current stream on the current device, as an int for the c_void_p parameter.  (Through
+    torch.cuda.current_stream() this cost 1.5 us x 2100 launches = 3 ms of host time per step, profiles/host_profile.py.)"""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _ptr(t, dtype=torch.float32):
@@ -207,11 +209,12 @@ def warp_cost(ref_mix, src_mix, homo12, depth_values, out=None, align_corners=Fa
 class PackedConv(object):
     """Folded, packed parameters of one 3x3x3 layer (see packing.pack_conv3d)."""
     __slots__ = ("weight", "scale", "shift", "cin_chunks", "cout_pad", "out_chunks", "act_split", "act_lo", "act_hi",
-                 "cin", "cout", "weight_tc", "cout_pad_tc", "weight_f16", "scale_f16", "weight_ring", "weight_ring2", "scale_ring")
+                 "cin", "cout", "weight_tc", "cout_pad_tc", "weight_f16", "scale_f16", "weight_ring", "weight_ring2", "scale_ring", "_desc")
 
     def __init__(self, weight, scale, shift, cin_chunks, cout_pad, out_chunks, act_split, act_lo, act_hi,
                  cin=None, cout=None, weight_tc=None, cout_pad_tc=None):
         self.weight, self.scale, self.shift = weight, scale, shift
+        self._desc = None                                              # per-(arithmetic, mode) descriptor templates (_conv_desc)
         self.weight_tc, self.cout_pad_tc = weight_tc, cout_pad_tc      # tcgen05 packings (packing.attach_tc)
         self.weight_f16, self.scale_f16 = None, None
         self.weight_ring = None                                        # plane-ring packing (packing.pack_weight_ring)
@@ -284,15 +287,22 @@ def check_status_async(device):
         _STATUS_ASYNC[key] = (host, ev)
 
 
-def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision, planar=0, dilation=1):
-    chunks0, D, H, W, _ = in0.shape
+def _act_ptr(t, dtype=torch.float32):
+    """Device address of an activation tensor as a plain int (c_void_p fields take ints), with _ptr's checks."""
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        _ptr(t, dtype)                     # raises with the full message
+    return t.data_ptr()
+
+
+def _desc_template(pc, precision, planar, dilation, device):
+    """The layer-constant half of an estd_conv3d_desc (weights, affine arrays, activation codes, arithmetic), built once per
+    (layer, arithmetic, mode, device) and byte-copied per launch: filling a ctypes structure field by field costs more host
+    time than everything else a launch does.  The tensors the pointers refer to stay alive through ``pc`` / status_flag."""
     d = ConvDesc()
     d.precision = PRECISION[precision]
     d.planar, d.dilation = int(planar), int(dilation)
-    d.in0, d.in0_chunks = _ptr(in0), chunks0
-    d.in1, d.in1_chunks = (_ptr(in1), in1.shape[0]) if in1 is not None else (None, 0)
-    if d.in0_chunks + d.in1_chunks != pc.cin_chunks:
-        raise RuntimeError("conv3d: layer packed for %d input chunks, got %d" % (pc.cin_chunks, d.in0_chunks + d.in1_chunks))
     tc = precision != "fp32"
     d.weight = _ptr(pc.weight)
     f16 = precision in ("3xf16", "3xf16r", "3xf16r2")
@@ -301,15 +311,35 @@ def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, pr
     ring = precision in ("3xf16r", "3xf16r2")
     d.scale, d.shift = _ptr(pc.scale_ring if ring else pc.scale_f16 if f16 else pc.scale), _ptr(pc.shift)
     d.cout_pad = pc.cout_pad_tc if tc else pc.cout_pad
-    d.status = _ptr(status_flag(in0.device), torch.int32) if f16 else None
+    d.status = _ptr(status_flag(device), torch.int32) if f16 else None
     d.act_split, d.act_lo, d.act_hi = pc.act_split, pc.act_lo, pc.act_hi
-    d.res0, d.res1 = _ptr(res0), _ptr(res1)
-    d.post_scale = float(post_scale)
-    d.out0, d.out0_chunks = _ptr(out0), out0.shape[0]
-    d.out1, d.out1_chunks = (_ptr(out1), out1.shape[0]) if out1 is not None else (None, 0)
+    return bytes(d)
+
+
+def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision, planar=0, dilation=1):
+    chunks0, D, H, W, _ = in0.shape
+    key = (precision, planar, dilation, in0.device.index)
+    cache = pc._desc
+    if cache is None:
+        cache = pc._desc = {}
+    tmpl = cache.get(key)
+    if tmpl is None:
+        tmpl = cache[key] = _desc_template(pc, precision, planar, dilation, in0.device)
+    d = ConvDesc.from_buffer_copy(tmpl)
+    d.in0, d.in0_chunks = _act_ptr(in0), chunks0
+    if in1 is not None:
+        d.in1, d.in1_chunks = _act_ptr(in1), in1.shape[0]
+    if d.in0_chunks + d.in1_chunks != pc.cin_chunks:
+        raise RuntimeError("conv3d: layer packed for %d input chunks, got %d" % (pc.cin_chunks, d.in0_chunks + d.in1_chunks))
+    d.res0, d.res1 = _act_ptr(res0), _act_ptr(res1)
+    d.post_scale = post_scale
+    d.out0, d.out0_chunks = _act_ptr(out0), out0.shape[0]
+    if out1 is not None:
+        d.out1, d.out1_chunks = _act_ptr(out1), out1.shape[0]
     if d.out0_chunks + d.out1_chunks != pc.out_chunks:
         raise RuntimeError("conv3d: layer produces %d chunks, outputs hold %d" % (pc.out_chunks, d.out0_chunks + d.out1_chunks))
-    d.gn_partials = _ptr(gn_partials, torch.float64)
+    if gn_partials is not None:
+        d.gn_partials = _act_ptr(gn_partials, torch.float64)
     d.D, d.H, d.W = D, H, W
     return d
 

@@ -321,6 +321,7 @@ def pack_layers(sd, device):
     # s * W (a + b) + 2 b): the same packed weights with the offset doubled
     layers["pre2_pair"] = copy.copy(layers["pre2"])
     layers["pre2_pair"].shift = (layers["pre2"].shift * 2.0).contiguous()
+    layers["pre2_pair"]._desc = None              # descriptor templates hold the offsets' address: never shared with pre2
     w_ref, w_src, bias = split_pre0(sd)
     layers["pre0_ref"], layers["pre0_src"], layers["pre0_bias"] = w_ref.to(device), w_src.to(device), bias.to(device)
     # both halves stacked: one premix launch per sequence gives every frame's target-side (chunks 0..7) and source-side mix
