@@ -25,6 +25,15 @@ from . import ops, packing
 from .encoders import ContextDecoder2D, ContextEncoder, MatchingFeatureNet
 
 
+def _upload(t, dev):
+    """Small host tensor (camera matrices, warp tables) -> device WITHOUT blocking the host.  A plain ``.to(dev)`` of pageable
+    memory -- and a blocking copy of pinned memory -- first waits for everything already enqueued on the stream: with four such
+    copies per step the host could never run ahead of the GPU, and every step started on an idle device."""
+    if t.is_cuda:
+        return (t if t.device == dev else t.to(dev)).contiguous()
+    return t.contiguous().pin_memory().to(dev, non_blocking=True)
+
+
 def _conv_bn3(cin, cout, k):
     return nn.Sequential(nn.Conv3d(cin, cout, k, padding=(k - 1) // 2, bias=False), nn.BatchNorm3d(cout))
 
@@ -329,7 +338,7 @@ class DepthNetHybrid(nn.Module):
         host_geometry = self.geometry == "torch" and not cam_poses.is_cuda and not cam_intr.is_cuda
         K4_src = self.scale_cam_intr(cam_intr.to(torch.float32), 0.25).contiguous()
         poses_src = cam_poses.to(torch.float32).contiguous()
-        K4, poses = K4_src.to(dev), poses_src.to(dev)
+        K4, poses = _upload(K4_src, dev), _upload(poses_src, dev)
         inputs_ready = None
         if self.geometry == "torch" and not host_geometry:
             inputs_ready = torch.cuda.Event()
@@ -369,9 +378,9 @@ class DepthNetHybrid(nn.Module):
         homo_tables, warp_tables = None, None
         pairs = [(t + 1, s) for t in range(T) for s in (t, t + 2)]
         if host_geometry:
-            homo_tables = [ops.homography_table_torch(poses_src[b], K4_src[b], pairs).to(dev) for b in range(B)]
+            homo_tables = [_upload(ops.homography_table_torch(poses_src[b], K4_src[b], pairs), dev) for b in range(B)]
             if memory_poses is not None and all(not p.is_cuda for p in memory_poses):
-                warp_tables = [[tab.to(dev) for tab in ops.volume_warp_tables_torch(
+                warp_tables = [[_upload(tab, dev) for tab in ops.volume_warp_tables_torch(
                     [poses_src[b, t + 1] for t in range(T)] + [p[b].to(torch.float32).contiguous() for p in memory_poses],
                     T, K4_src[b])] for b in range(B)]
         elif self.geometry == "torch":
@@ -383,7 +392,7 @@ class DepthNetHybrid(nn.Module):
                     # the EST warps' matrices too, when the memory poses are already known (forward(); a clip-pipeline rank
                     # that prepares ahead of its predecessor's state derives them in fuse())
                     warp_tables = [ops.volume_warp_tables_torch(
-                        [poses[b, t + 1] for t in range(T)] + [p[b].to(device=dev, dtype=torch.float32).contiguous() for p in memory_poses],
+                        [poses[b, t + 1] for t in range(T)] + [_upload(p[b].to(torch.float32), dev) for p in memory_poses],
                         T, K4[b]) for b in range(B)]
                 homo_ready = torch.cuda.Event()
                 homo_ready.record(side)
@@ -435,7 +444,7 @@ class DepthNetHybrid(nn.Module):
             all_poses = [poses[b, t + 1] for t in range(T)]
             if use_est:
                 # memory volumes are appended after the current ones (hybrid_depth_decoder.py:220-224)
-                all_poses += [p[b].to(device=dev, dtype=torch.float32).contiguous() for p in pre_cam_poses]
+                all_poses += [_upload(p[b].to(torch.float32), dev) for p in pre_cam_poses]
                 values += [self._state_to_vol4(v, b) for v in pre_costs["values"]]
                 keys += [self._state_to_vol4(k, b) for k in pre_costs["keys"]]
             tables = None
@@ -444,7 +453,7 @@ class DepthNetHybrid(nn.Module):
                     tables = prep["warp_tables"][b]                  # derived on the side stream during prepare()
                 elif prep.get("host_geometry") and all(not p.is_cuda for p in pre_cam_poses):
                     host_poses = [prep["poses_host"][b, t + 1] for t in range(T)] + [p[b].to(torch.float32).contiguous() for p in pre_cam_poses]
-                    tables = [tab.to(dev) for tab in ops.volume_warp_tables_torch(host_poses, T, prep["K4_host"][b])]
+                    tables = [_upload(tab, dev) for tab in ops.volume_warp_tables_torch(host_poses, T, prep["K4_host"][b])]
                 else:
                     tables = ops.volume_warp_tables_torch(all_poses, T, K4[b])
             for i in range(T):
