@@ -342,8 +342,8 @@ def run_ours(args):
     # still in L2 when the kernel ends)
     traffic = {"3xf16r2": 332.6e6, "3xf16r": 375.8e6}.get(model.precision) if args.workload == "cfg2" else None
     kname = {"3xf16r": "estd::ring::conv3d_ring_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule, fp16 two-term split)",
-             "3xf16r2": "estd::ring2::conv3d_ring2_kernel / ring::conv3d_ring_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule, "
-                        "CTA pairs where specialised, fp16 two-term split)"}.get(
+             "3xf16r2": "estd::ring2::conv3d_ring2_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule on CTA pairs / "
+                        "cta_group::2, fp16 two-term split)"}.get(
         model.precision, "estd conv3d kernel (%s)" % model.precision)
     roofline = {"kernel": kname if conv_name in kernels else dom[0], "bound": "tensor",
                 "achieved": conv.get("TFLOPps"), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
@@ -357,7 +357,7 @@ def run_ours(args):
                 "tensor_flops_issued_TFLOPps": (conv.get("TFLOPps") or 0.0) * mma_per_flop,
                 "tensor_pipe_frac_issued": (conv.get("TFLOPps") or 0.0) * mma_per_flop / peaks["bf16_sustained"]}
     cpu_base, _ = (None, None)
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:             # reported at N = 1 only (rank 0's host cores)
         cpu_base, _ = oracle_sample(args.workload, 1, 1, budget_s=60.0)
     h2d = host[0].numel() * host[0].element_size() + 4 * (6 * 12 + 9 * 30)      # images + the warps' matrix tables
     d2h = sum(t.numel() * t.element_size() for t in host_out)

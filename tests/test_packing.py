@@ -159,3 +159,47 @@ def test_ring2_packing_is_the_ring_packing_split_over_the_cta_pair():
                 assert torch.equal(blk, ring[r][..., 32 * slot:32 * slot + 32, :])
             else:
                 assert float(blk.view(torch.int32).abs().max()) == 0.0
+
+
+def test_conv_descriptor_templates_are_per_layer_and_per_arithmetic(monkeypatch):
+    """Host logic of ops._conv_desc: the layer-constant half of estd_conv3d_desc is cached on the PackedConv as a byte
+    template.  A template must never leak between layers that share packed weights (pre2 / pre2_pair differ only in the
+    offsets) or between arithmetics of one layer, and the per-launch fields must be filled on a fresh copy every time."""
+    import ctypes
+    from estdepth_b200 import ops
+    from tests.helpers import synth_model_and_state
+
+    def host_ptr(t, dtype=torch.float32):
+        if t is None:
+            return None
+        assert t.dtype == dtype and t.is_contiguous()
+        return t.data_ptr()
+    flag = torch.zeros(1, dtype=torch.int32)
+    monkeypatch.setattr(ops, "_ptr", lambda t, dtype=torch.float32: None if t is None else ctypes.c_void_p(host_ptr(t, dtype)))
+    monkeypatch.setattr(ops, "_act_ptr", host_ptr)
+    monkeypatch.setattr(ops, "status_flag", lambda device: flag)
+
+    model, _ = synth_model_and_state(18, 32)
+    L = model._layers(torch.device("cpu"))
+    pre2, pair = L["pre2"], L["pre2_pair"]
+    assert pair.weight_ring2 is pre2.weight_ring2 and pair.shift is not pre2.shift
+    assert torch.equal(pair.shift, 2 * pre2.shift)
+    x, y, r0, r1 = (torch.zeros(8, 2, 8, 8, 4) for _ in range(4))
+    d_pre2 = ops._conv_desc(pre2, x, None, y, None, r0, None, 1.0, None, "3xf16r2")
+    d_pair = ops._conv_desc(pair, x, None, y, None, r0, r1, 0.5, None, "3xf16r2")
+    assert d_pre2.shift == pre2.shift.data_ptr() and d_pair.shift == pair.shift.data_ptr()
+    assert d_pre2.weight_tc == d_pair.weight_tc == pre2.weight_ring2.data_ptr()
+    assert (d_pre2.res1, d_pre2.post_scale) == (None, 1.0) and (d_pair.res1, d_pair.post_scale) == (r1.data_ptr(), 0.5)
+    # a second launch of the same layer starts from the template again, not from the previous launch's descriptor
+    d_again = ops._conv_desc(pair, x, None, y, None, None, None, 1.0, None, "3xf16r2")
+    assert (d_again.res0, d_again.res1, d_again.post_scale) == (None, None, 1.0)
+    # another arithmetic of the same layer: its own template (weights, multiplier array, padded width)
+    d_fp32 = ops._conv_desc(pre2, x, None, y, None, None, None, 1.0, None, "fp32")
+    assert d_fp32.precision == ops.PRECISION["fp32"] and d_fp32.weight == pre2.weight.data_ptr()
+    assert d_fp32.scale == pre2.scale.data_ptr() and d_pre2.scale == pre2.scale_ring.data_ptr()
+    assert d_fp32.status is None and d_pre2.status == flag.data_ptr()
+    assert set(pre2._desc) == {("3xf16r2", 0, 1, None), ("fp32", 0, 1, None)}
+    # shape errors are still caught per launch
+    import pytest
+    with pytest.raises(RuntimeError):
+        ops._conv_desc(pre2, torch.zeros(4, 2, 8, 8, 4), None, y, None, None, None, 1.0, None, "3xf16r2")
