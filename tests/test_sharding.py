@@ -87,3 +87,36 @@ def test_clip_pipeline_world2_equals_sequential(n_frames):
         assert p.exitcode == 0
     want = _sequential(n_frames)
     assert torch.allclose(torch.tensor(got), want, rtol=0, atol=0)
+
+
+def _dp_worker(rank, world, port, n_seq, q):
+    """BASELINE cfg4 in miniature: independent sequences partitioned over the ranks, depth maps all_gather'ed (ragged)."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    start, stop = sharding.partition(n_seq, world, rank)
+    local = torch.stack([_frames(s)[0].sum(dim=(0, 1, 2)) for s in range(start, stop)]) if stop > start else torch.zeros(0, 4, 4)
+    gathered = sharding.gather_maps(local)
+    if rank == 0:
+        q.put(torch.cat(gathered).tolist())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_seq", [5, 1])
+def test_data_parallel_sequences_world2_gather_in_order(n_seq):
+    """No data-path collective: each rank owns a contiguous block of sequences; one ragged all_gather at the end returns
+    the maps in sequence order (a rank may own nothing: n_seq = 1)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, n_seq, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = torch.tensor(q.get(timeout=120))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = torch.stack([_frames(s)[0].sum(dim=(0, 1, 2)) for s in range(n_seq)])
+    assert got.shape == want.shape and torch.equal(got, want)
