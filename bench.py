@@ -248,9 +248,16 @@ def run_ours(args):
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(3, args.warmup)):
-        step_resident()
+    # nvidia-smi is started BEFORE the warm-up and the warm-up lasts until it has had time to initialise NVML and take its first
+    # sample (>= W steps and >= 0.4 s of the same load): started right at the timed region, its start-up (a process spawn + driver
+    # queries) stalled the first timed launches by several ms -- 1 ms per step at K = 5.  Every sample is taken under load.
     sampler = ClockSampler(local) if rank == 0 else None
+    t_warm, n_warm = time.perf_counter(), 0
+    while n_warm < max(3, args.warmup) or (n_warm < 60 and time.perf_counter() - t_warm < 0.4):
+        step_resident()
+        n_warm += 1
+        if n_warm >= max(3, args.warmup):
+            torch.cuda.current_stream().synchronize()      # the 0.4 s are GPU time, not enqueue time
     launches0 = _lib.launch_count()
     ms_resident = timed(step_resident, args.steps)
     launches = (_lib.launch_count() - launches0) // args.steps
