@@ -16,6 +16,7 @@ Protocol quirks reproduced on purpose: Q3 first window of 
 Q4 the returned hidden-state pose is the LAST MEMORY pose once a memory exists, Q5 targets are fused in order and
 later targets attend to already-fused values, Q6 mean-not-sum attention, Q7 rel_pose = P_j P_i^-1.
 """
+import collections
 import os
 
 import torch
@@ -156,6 +157,8 @@ class DepthNetHybrid(nn.Module):
         self._packed_key = None
         self._ws = None
         self._depth_dev = None
+        self._feat_cache = collections.OrderedDict()     # (batch slot, frame id) -> matching features [32, H/4, W/4] (frame_ids=)
+        self.feature_cache_size = 16
 
     # ------------------------------------------------------------------ parameter packing
     def _param_fingerprint(self, device):
@@ -165,17 +168,58 @@ class DepthNetHybrid(nn.Module):
 
     def load_state_dict(self, *args, **kwargs):
         self._packed = None
+        self._feat_cache.clear()
         return super().load_state_dict(*args, **kwargs)
 
     def _apply(self, fn, *args, **kwargs):
         self._packed = None
         self._depth_dev = None
         self._ws = None
+        if "_feat_cache" in self.__dict__:
+            self._feat_cache.clear()
         return super()._apply(fn, *args, **kwargs)
 
     def repack(self):
         """Re-fold BN and re-pack the 3-D weights (call after mutating parameters in place)."""
         self._packed = None
+        self._feat_cache.clear()
+
+    def _matching_features(self, imgs, frame_ids=None):
+        """psm_feature_extraction over every view (model_hybrid.py:126-131): imgs [B,V,3,Hi,Wi] (normalised) -> [B,V,32,Hi/4,Wi/4].
+
+        ``frame_ids`` (optional): one hashable id per view -- a sequence of V ids, or B such sequences.
+        Consecutive windows of a scene overlap (Joint: 2 of 5 frames, ``eval_hybrid.py:195-196``; ESTM: 2 of 3,
+        ``eval_hybrid_seq.py:169-190``) and the reference recomputes the shared frames' features every window; with ids the
+        features of a frame are computed once and kept for the next ``feature_cache_size`` frames.  The caller promises that an
+        id names the same image; the cache is dropped whenever the parameters change."""
+        B, V, _, Hi, Wi = imgs.shape
+        if frame_ids is None:
+            return self.matchingFeature(imgs.reshape(B * V, 3, Hi, Wi)).reshape(B, V, 32, Hi // 4, Wi // 4)
+        ids = list(frame_ids)
+        if B == 1 and len(ids) == V and not (V == 1 and isinstance(ids[0], (list, tuple))):
+            ids = [ids]
+        if len(ids) != B or any(len(row) != V for row in ids):
+            raise ValueError("frame_ids must hold one id per view: %d x %d" % (B, V))
+        cache = self._feat_cache
+        keys = [[(b, ids[b][v], Hi, Wi, str(imgs.device)) for v in range(V)] for b in range(B)]
+        pending = collections.OrderedDict()              # key -> (b, v) of the first view that shows this frame
+        for b in range(B):
+            for v in range(V):
+                if keys[b][v] not in cache and keys[b][v] not in pending:
+                    pending[keys[b][v]] = (b, v)
+        if pending:
+            new = self.matchingFeature(torch.stack([imgs[b, v] for b, v in pending.values()]))
+            for i, key in enumerate(pending):
+                cache[key] = new[i]
+        rows = []
+        for b in range(B):
+            for v in range(V):
+                cache.move_to_end(keys[b][v])
+            rows.append(torch.stack([cache[keys[b][v]] for v in range(V)]))
+        feats = torch.stack(rows)
+        while len(cache) > max(self.feature_cache_size, B * V):
+            cache.popitem(last=False)
+        return feats
 
     def _layers(self, device):
         key = self._param_fingerprint(device)
@@ -292,12 +336,12 @@ class DepthNetHybrid(nn.Module):
         return ops.ncdhw_to_vol4(t[b].detach().to(torch.float32).contiguous())
 
     # ------------------------------------------------------------------ forward
-    def forward(self, imgs, cam_poses, cam_intr, sample=None, pre_costs=None, pre_cam_poses=None, mode='train'):
+    def forward(self, imgs, cam_poses, cam_intr, sample=None, pre_costs=None, pre_cam_poses=None, mode='train', frame_ids=None):
         """imgs [B,V,3,H,W] (0..255), cam_poses [B,V,4,4] cam->world, cam_intr [B,3,3]; V-2 target views.
 
         mode='val' -> (outputs, {"keys": [k], "values": [v]}, [pose]) exactly as the reference
         (hybrid_models/model_hybrid.py:183-184).  'train' / 'test' (loss / metric heads) are outside the inference
-        hot path and raise.
+        hot path and raise.  ``frame_ids`` (extension, optional): see ``_matching_features``.
         """
         if mode != 'val':
             raise NotImplementedError("estdepth_b200 implements the inference path (mode='val'); got mode=%r" % (mode,))
@@ -306,13 +350,14 @@ class DepthNetHybrid(nn.Module):
         if self.precision in ("3xf16", "3xf16r", "3xf16r2") or self.feature_precision == "3xf16":
             ops.check_status_async(imgs.device)     # fp16 range flag of earlier calls, without draining the GPU
         with torch.no_grad():
-            return self._forward_val(imgs, cam_poses, cam_intr, pre_costs, pre_cam_poses)
+            return self._forward_val(imgs, cam_poses, cam_intr, pre_costs, pre_cam_poses, frame_ids)
 
-    def _forward_val(self, imgs, cam_poses, cam_intr, pre_costs, pre_cam_poses):
+    def _forward_val(self, imgs, cam_poses, cam_intr, pre_costs, pre_cam_poses, frame_ids=None):
         memory_poses = pre_cam_poses if (self.IF_EST_transformer and pre_costs is not None) else None
-        return self.fuse(self.prepare(imgs, cam_poses, cam_intr, memory_poses=memory_poses), pre_costs, pre_cam_poses)
+        return self.fuse(self.prepare(imgs, cam_poses, cam_intr, memory_poses=memory_poses, frame_ids=frame_ids),
+                         pre_costs, pre_cam_poses)
 
-    def prepare(self, imgs, cam_poses, cam_intr, memory_poses=None):
+    def prepare(self, imgs, cam_poses, cam_intr, memory_poses=None, frame_ids=None):
         """Everything that does not depend on the hidden state (about 89 % of the FLOPs of a step):
         2-D feeders, cost volumes, matching net, key/value volumes, initial depth.  ``forward`` is
         ``fuse(prepare(...), pre_costs, pre_cam_poses)``; the split lets a rank of the ESTM clip pipeline
@@ -360,7 +405,7 @@ class DepthNetHybrid(nn.Module):
                 semantic_vs = self.CostRegNet.context(maps).contiguous()             # [B*T, D, H, W]
                 ctx_done = torch.cuda.Event()
                 ctx_done.record(ctx)
-            feats = self.matchingFeature(imgs.reshape(B * V, 3, Hi, Wi)).reshape(B, V, 32, H, W)
+            feats = self._matching_features(imgs, frame_ids)
             for t_ in (semantic_vs, maps[0]):
                 t_.record_stream(main)           # allocated on the context stream, consumed (and released) on the main one
             if self.overlap_context >= 2:
@@ -368,7 +413,7 @@ class DepthNetHybrid(nn.Module):
             else:
                 main.wait_event(ctx_done)
         else:
-            feats = self.matchingFeature(imgs.reshape(B * V, 3, Hi, Wi)).reshape(B, V, 32, H, W)
+            feats = self._matching_features(imgs, frame_ids)
             maps = self.semanticFeature(imgs[:, 1:1 + T].reshape(B * T, 3, Hi, Wi))
             semantic_vs = self.CostRegNet.context(maps).contiguous()                 # [B*T, D, H, W]
         ops._pe(t_prof, "cudnn_2d_feeders")

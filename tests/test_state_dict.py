@@ -34,3 +34,36 @@ def test_synthetic_weights_are_deterministic():
     c = synth.synth_state_dict(m.state_dict(), seed=1)
     assert all(torch.equal(a[k], b[k]) for k in a)
     assert not torch.equal(a["pre1.0.weight"], c["pre1.0.weight"])
+
+
+def test_frame_id_feature_cache_computes_each_frame_once():
+    """Host logic of DepthNetHybrid._matching_features, on the CPU path of the matching-feature net:
+    with frame ids, the frames two consecutive windows share are not recomputed, the features equal the uncached ones, and
+    the cache is bounded and dropped when the parameters change."""
+    import torch
+    from tests.helpers import synth_model_and_state
+    model, sd = synth_model_and_state(18, 32)
+    g = torch.Generator().manual_seed(0)
+    frames = torch.rand(8, 3, 128, 160, generator=g) * 2 - 1
+    batches = []
+    inner = model.matchingFeature.forward
+    model.matchingFeature.forward = lambda x: (batches.append(x.shape[0]), inner(x))[1]
+    with torch.no_grad():
+        w1 = model._matching_features(frames[0:5].unsqueeze(0), frame_ids=[0, 1, 2, 3, 4])
+        w2 = model._matching_features(frames[3:8].unsqueeze(0), frame_ids=[3, 4, 5, 6, 7])           # Joint stride: 2 frames shared
+        assert batches == [5, 3]
+        plain = model._matching_features(frames[3:8].unsqueeze(0))
+        assert batches == [5, 3, 5] and tuple(w2.shape) == tuple(plain.shape) == (1, 5, 32, 32, 40)
+        assert float((w2 - plain).abs().max()) < 1e-5 * float(plain.abs().max())
+        assert torch.equal(w1[0, 3:5], w2[0, 0:2])
+        # a frame shown twice in one call is computed once; B sequences of ids; bounded size
+        model.feature_cache_size = 4
+        two = model._matching_features(torch.stack([frames[0:3], frames[[0, 0, 2]]]), frame_ids=[["a", "b", "c"], ["a", "a", "c"]])
+        assert batches[-1] == 5 and torch.equal(two[1, 0], two[1, 1]) and len(model._feat_cache) == 6
+        model._matching_features(frames[0:3].unsqueeze(0), frame_ids=[10, 11, 12])
+        assert len(model._feat_cache) == 4
+        import pytest
+        with pytest.raises(ValueError):
+            model._matching_features(frames[0:3].unsqueeze(0), frame_ids=[1, 2])
+        model.load_state_dict(sd)
+        assert len(model._feat_cache) == 0
