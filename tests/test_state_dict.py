@@ -67,3 +67,21 @@ def test_frame_id_feature_cache_computes_each_frame_once():
             model._matching_features(frames[0:3].unsqueeze(0), frame_ids=[1, 2])
         model.load_state_dict(sd)
         assert len(model._feat_cache) == 0
+
+
+def test_forward_and_constructor_signatures_are_drop_in():
+    """The boundary of SURVEY.md 8b: positional order and names of the reference's constructor
+    (hybrid_models/model_hybrid.py:15-16) and forward (:110); extensions may only follow them, with defaults."""
+    import inspect
+    from estdepth_b200 import DepthNetHybrid
+    ctor = list(inspect.signature(DepthNetHybrid.__init__).parameters.values())[1:]
+    assert [(p.name, p.default) for p in ctor[:5]] == [("ndepths", 64), ("depth_min", 0.01), ("depth_max", 10.0), ("resnet", 50),
+                                                       ("IF_EST_transformer", True)]
+    assert all(p.default is not inspect.Parameter.empty for p in ctor[5:])
+    fwd = list(inspect.signature(DepthNetHybrid.forward).parameters.values())[1:]
+    assert [p.name for p in fwd[:7]] == ["imgs", "cam_poses", "cam_intr", "sample", "pre_costs", "pre_cam_poses", "mode"]
+    assert fwd[4].default is None and fwd[5].default is None and fwd[6].default == "train"
+    assert all(p.default is not inspect.Parameter.empty for p in fwd[7:])
+    # the shim the eval drivers import (eval_hybrid.py:11, eval_hybrid_seq.py:10)
+    from hybrid_models.model_hybrid import DepthNetHybrid as Shim
+    assert Shim is DepthNetHybrid
