@@ -5,7 +5,9 @@ Same constructor, ``forward`` signature, return values and ``state_dict`` keys a
 (``mode='val'``, the mode both eval drivers use: eval_hybrid.py:113-121, eval_hybrid_seq.py:180-183).
 
 What runs where:
-  * 2-D feature nets and the 2-D context decoder / refinement: PyTorch + cuDNN (``encoders.py``; "kept" rows);
+  * 2-D feature nets and the 2-D context decoder / refinement (``encoders.py``; the "kept" rows of SURVEY.md 8a): their
+    stride-1 3x3 and 1x1 convolutions on the planar tcgen05 kernel of the same library (``feature_precision="3xf16"``), the
+    stems / pools / resizes on PyTorch + cuDNN in strict fp32;
   * everything 3-D -- plane-sweep warp + folded pre0 (K1), every 3x3x3 convolution with its BN/activation/residual
     (K2), the EST warp+attention (K3), soft-argmin (K4), GroupNorm/GRU glue (K5), the camera algebra -- runs in the
     hand-written CUDA library through ``ops.py``.  The 3-D ``nn.Conv3d``/``BatchNorm3d``/``GroupNorm`` modules below
