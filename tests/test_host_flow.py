@@ -138,3 +138,23 @@ def test_val_mode_only_and_cpu_tensors_rejected():
     with pytest.raises(AssertionError):
         with torch.no_grad():
             m.prepare(imgs[:, :2], poses[:, :2], K)      # views_num must exceed 2 (model_hybrid.py:123)
+
+
+def test_frame_ids_reach_the_feature_cache_through_the_public_flow(recorder):
+    """ESTM windows share 2 of their 3 frames: with frame ids only the new frame goes through the matching-feature net."""
+    m = _model()
+    batches = []
+    inner = m.matchingFeature.forward
+    m.matchingFeature.forward = lambda x: (batches.append(x.shape[0]), inner(x))[1]
+    mem = []
+    with torch.no_grad():
+        for step in range(3):
+            imgs, poses, K = _window(step, views=3)
+            pre = sharding._flatten_memory(mem)
+            _, costs, cposes = m._forward_val(imgs, poses, K, pre[0], pre[1], frame_ids=[step, step + 1, step + 2])
+            mem = (mem + [(costs, cposes)])[-2:]
+    assert batches == [3, 1, 1]
+    batches.clear()
+    with torch.no_grad():
+        m._forward_val(*_window(0, views=3), None, None)
+    assert batches == [3]                                 # no ids: the reference's behaviour, every view recomputed
