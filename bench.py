@@ -249,11 +249,13 @@ def run_ours(args):
         return float(ms.item())
 
     # nvidia-smi is started BEFORE the warm-up and the warm-up lasts until it has had time to initialise NVML and take its first
-    # sample (>= W steps and >= 0.4 s of the same load): started right at the timed region, its start-up (a process spawn + driver
-    # queries) stalled the first timed launches by several ms -- 1 ms per step at K = 5.  Every sample is taken under load.
+    # samples, and until a GPU that was idle has ramped its clocks (>= W steps and >= 1 s of the same load): started right at the
+    # timed region, its start-up (a process spawn + driver queries) stalled the first timed launches by several ms, and a bench
+    # that was the first work on a fresh box timed its first steps on a GPU still leaving its idle power state -- together
+    # 1 ms per step at K = 5 (profiles/ab_r01.txt, bench_v1 vs bench_u1).  Every sample is taken under load.
     sampler = ClockSampler(local) if rank == 0 else None
     t_warm, n_warm = time.perf_counter(), 0
-    while n_warm < max(3, args.warmup) or (n_warm < 60 and time.perf_counter() - t_warm < 0.4):
+    while n_warm < max(3, args.warmup) or (n_warm < 120 and time.perf_counter() - t_warm < 1.0):
         step_resident()
         n_warm += 1
         if n_warm >= max(3, args.warmup):
