@@ -376,6 +376,7 @@ def run_ours(args):
             "config": {"workload": "%s: 5-frame %dx%d Joint window, D=%d, ResNet-%d, steady-state EST window (1 memory volume), "
                                    "3 depth maps/step, 1 sequence per GPU" % (args.workload, H, W, D, resnet),
                        "l2": "volumes are 157 MB each (> 126 MB L2); no explicit flush", "cudnn_tf32": False,
+                       "warmup_steps_run": n_warm,
                        "camera_parameters": "host tensors (matrices of the warps derived on the host with the reference's torch ops)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_base}
