@@ -259,7 +259,7 @@ def run_ours(args):
         step_resident()
         n_warm += 1
         if n_warm >= max(3, args.warmup):
-            torch.cuda.current_stream().synchronize()      # the 0.4 s are GPU time, not enqueue time
+            torch.cuda.current_stream().synchronize()      # the second is GPU time, not enqueue time
     launches0 = _lib.launch_count()
     ms_resident = timed(step_resident, args.steps)
     launches = (_lib.launch_count() - launches0) // args.steps
