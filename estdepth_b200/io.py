@@ -1,0 +1,88 @@
+"""Asynchronous depth-map writer -- the save path of the reference's eval drivers without their stalls.
+
+The drivers save each map as ``np.save(path, np.float16(outputs[key].squeeze(1).cpu().numpy()))`` (eval_hybrid.py:260-264,
+282-286, 276-277, 306-307): a blocking device->host copy of fp32 data, a host-side cast and a synchronous file write per map,
+with the GPU idle meanwhile.  ``DepthMapWriter.save`` produces byte-identical files but casts to fp16 ON THE DEVICE (half the
+bytes over PCIe; torch and numpy both round to nearest even), copies into pinned memory on a side stream behind the work that
+produced the map, and leaves the wait for that copy and the file write to a worker thread.  The caller's stream is never
+synchronised.  Host tensors take the same route minus the copy (that is what the CPU test pins against the reference's formula).
+"""
+import queue
+import threading
+
+import numpy as np
+import torch
+
+
+class DepthMapWriter(object):
+    def __init__(self, max_pending=16):
+        self._q = queue.Queue(maxsize=max_pending)       # back-pressure: at most max_pending maps in flight
+        self._error = None
+        self._streams = {}
+        self._thread = threading.Thread(target=self._drain, name="estd-depth-writer", daemon=True)
+        self._thread.start()
+
+    # ------------------------------------------------------------------ producer side
+    def save(self, tensor, path, squeeze_channel=True):
+        """tensor [B,1,H,W] (or any shape) fp32, CUDA or host -> ``path`` (.npy, float16).  ``squeeze_channel`` drops dim 1 as
+        the drivers do for depth maps (``.squeeze(1)``); pass False and a pre-squeezed tensor for the probability maps
+        (``.squeeze()``)."""
+        if self._error is not None:
+            self.close()
+        t = tensor.detach()
+        if squeeze_channel and t.dim() >= 2 and t.shape[1] == 1:
+            t = t.squeeze(1)
+        if t.is_cuda:
+            main = torch.cuda.current_stream(t.device)
+            side = self._streams.get(t.device)
+            if side is None:
+                side = self._streams[t.device] = torch.cuda.Stream(device=t.device)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                half = t.to(torch.float16)
+                host = torch.empty(half.shape, dtype=torch.float16, pin_memory=True)
+                host.copy_(half, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(side)
+            t.record_stream(side)                        # the producer may free / reuse the map as soon as the cast has read it
+        else:
+            host, done = t.to(torch.float16), None
+        self._q.put((host, done, str(path)))
+
+    def save_outputs(self, outputs, paths):
+        """``paths``: {output key: file path}, e.g. {("depth", 0, 2): ".../init_depth/frame-000010.color.npy", ...}."""
+        for key, path in paths.items():
+            self.save(outputs[key], path)
+
+    # ------------------------------------------------------------------ consumer side
+    def _drain(self):
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            host, done, path = item
+            try:
+                if self._error is None:
+                    if done is not None:
+                        done.synchronize()               # waits for this copy only, on this thread only
+                    np.save(path, host.numpy())
+            except BaseException as e:                   # surfaced to the producer by close() / the next save()
+                self._error = e
+
+    def close(self):
+        """Waits until every submitted map is on disk; re-raises the first write error."""
+        if self._thread.is_alive():
+            self._q.put(None)
+            self._thread.join()
+        if self._error is not None:
+            err, self._error = self._error, None
+            raise err
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
