@@ -4,18 +4,26 @@
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA kernels through the C ABI)
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
 
-Workload (BASELINE.json configs[1], "cfg2"): one 5-frame 480x640 window, D=64 depth planes, ResNet-50 context
-encoder, Joint mode, STEADY-STATE window (window 2 of a scene: EST fusion active with one memory volume,
-SURVEY.md 8d) -> 3 depth maps per step.  Synthetic images / poses / random-init weights (estdepth_b200.synth).
-One process per GPU; every rank runs its own independent sequence (weak scaling, no data-path collective:
-sequences are independent units); value = total depth maps / max-over-ranks device time.
+Workload (BASELINE.json configs[1], "cfg2"): one 5-frame 480x640 window, D=64 depth planes, ResNet-50 context encoder,
+Joint mode, STEADY-STATE window (window 2 of a scene: EST fusion active with one memory volume) -> 3 depth
+maps per step.  Synthetic images / poses / random-init weights (estdepth_b200.synth).  One process per GPU; every rank runs
+its own independent sequence (weak scaling: sequences are independent units); at N > 1 every step ends with the
+one exchange the path has in data-parallel mode -- the NCCL all_gather of the depth maps a driver saves (BASELINE configs[3]) --
+inside the timed region.  value = total depth maps / max-over-ranks device time.
 
-Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM.  `e2e`: the same step through the public call
-with host buffers -- pinned H2D of the window's images/poses/intrinsics and D2H of the depth maps a driver saves
-(eval_hybrid.py:259-286) inside the timed region.  `roofline`: the dominant kernel (3-D convolution) timed live
-with CUDA events; `kernels`: the same for every kernel family, incl. the HBM roofline of the fused warp->cost
-kernel.  `cpu_baseline`: the oracle (a port of the reference's algorithm) timed on this box's host cores on a
-bounded sample.
+Timing: after the warm-up, R = 5 repetitions of EXACTLY K steps each, every repetition bracketed by barrier +
+torch.cuda.synchronize() and timed with CUDA events (max over ranks); the line reports the MEDIAN repetition
+(``ms_per_step``, ``value``) and all of them (``repeats_ms_per_step``).  Resident and end-to-end repetitions alternate.
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM.  `e2e`: the same step through the public call with host
+buffers -- pinned H2D of the window's images and D2H of the depth maps a driver saves (eval_hybrid.py:259-286) inside the
+timed region.  `roofline`: the dominant kernel (3-D convolution) timed live with CUDA events; `kernels`: the same for every
+kernel family, incl. the HBM rooflines of the fused warp->cost kernel, the EST attention gather and the soft-argmin.
+`cpu_baseline`: the oracle (a port of the reference's algorithm) timed on this box's host cores on a bounded sample.
+`extras` (N = 1): the drivers' real call with CUDA camera parameters, BASELINE cfg3 (ESTM 20-frame clip), cfg5 (640x960,
+D=128) and the reference algorithm as plain PyTorch-CUDA ops on the same GPU (north_star's >= 10x denominator);
+(N > 1): BASELINE cfg4 (32 sequences partitioned over the ranks + gather, checked against rank 0's own run of all 32) and
+the cfg3 clip cut over the ranks with the NCCL hidden-state hand-off (checked bit for bit against the sequential loop).
 """
 import argparse
 import json
@@ -39,6 +47,7 @@ WORKLOADS = {
     "cfg1": (5, 128, 160, 32, 18),
     "cfg5": (5, 640, 960, 128, 50),
 }
+REPEATS = 5
 
 
 def measured_peaks():
@@ -103,21 +112,35 @@ def dist_env():
     return rank, world, local
 
 
-# --------------------------------------------------------------------------------------------- reference arm (CPU)
 def workload_string(workload):
     V, H, W, D, resnet = WORKLOADS[workload]
     return ("%s: %d-frame %dx%d Joint window, D=%d, ResNet-%d, steady-state EST window (1 memory volume), %d depth maps/step, "
             "1 sequence per GPU" % (workload, V, H, W, D, resnet, V - 2))
 
 
+def config_dict(workload):
+    """The SAME dict in both arms (the driver compares them)."""
+    return {"workload": workload_string(workload),
+            "inputs": "synthetic low-passed noise images, synthetic camera track, seeded random-init weights (estdepth_b200.synth)",
+            "precision": "fp32 inputs / outputs / parity gate; strict fp32 (no TF32) in both arms",
+            "l2": "volumes are 157 MB each (> 126 MB L2); no explicit flush",
+            "camera_parameters": "host tensors (the warps' matrices are derived with the reference's torch ops on the host)"}
+
+
+def median(xs):
+    xs = sorted(xs)
+    n = len(xs)
+    return xs[n // 2] if n % 2 else 0.5 * (xs[n // 2 - 1] + xs[n // 2])
+
+
+# --------------------------------------------------------------------------------------------- reference arm (CPU)
 def oracle_sample(workload, steps, warmup, budget_s=150.0):
     """Times the oracle (CPU port of the reference's algorithm) on the bench workload itself.
 
     One step = ONE steady-state window of the workload (cfg2: 5 frames -> 3 depth maps, EST fusion of every target with the
     two other targets and one memory volume), exactly what a step of the GPU arm computes; the memory volume is synthetic
-    (the arithmetic does not depend on its values).  About 8 s of CPU per window on 16 cores.  (Round 1 first sampled one
-    3-frame ESTM step instead: 3.9 s per depth map against 4.7 s per map for the full window on 8 cores -- a 20 % flattering
-    of the baseline.)  The run stops early once ``budget_s`` is spent, with at least one timed step.
+    (the arithmetic does not depend on its values).  About 8 s of CPU per window on 16 cores.  The run stops early once
+    ``budget_s`` is spent, with at least one timed step.
     """
     from estdepth_b200 import synth
     from estdepth_b200.model import DepthNetHybrid
@@ -158,28 +181,35 @@ def run_reference(args):
     if rank != 0:
         return
     base, mean = oracle_sample(args.workload, args.steps, max(0, min(args.warmup, 1)))
-    V, H, W, D, resnet = WORKLOADS[args.workload]
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": base["steps"],
             "warmup": max(0, min(args.warmup, 1)), "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_string(args.workload), "arm": "CPU oracle port of the reference's algorithm, all host cores"},
+            "config": config_dict(args.workload),
+            "arm": "CPU oracle port of the reference's algorithm (oracle/estdepth_oracle.py), all host cores; the Python reference "
+                   "itself cannot travel to the GPU box",
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------- this repo's arm (GPU)
-def kernel_rooflines(prof, workload, peaks):
-    """Per-kernel-family achieved throughput from the CUDA-event profile pass; algorithmic bytes/flops of SURVEY.md 8(d)."""
-    V, H, W, D, _ = WORKLOADS[workload]
-    P = (H // 4) * (W // 4)
-    Vx = D * P
+INCLUSIVE = "(inclusive)"
+
+
+def kernel_rooflines(prof, peaks):
+    """Per-kernel-family achieved throughput from the CUDA-event profile pass; algorithmic bytes/flops of SURVEY.md 8(d).
+    Stage brackets appear with their EXCLUSIVE time (torch / cuDNN ops that are not one of the library's families); their
+    inclusive time is listed under ``<name>(inclusive)`` and is not part of any share."""
     out = {}
+    total = sum(ms for name, (ms, _, _, _) in prof.items() if not name.endswith(INCLUSIVE))
     for name, (ms, calls, flops, bytes_) in prof.items():
+        if name.endswith(INCLUSIVE):
+            out[name] = {"ms_per_step": ms}
+            continue
         if calls == 0:
             continue
         avg_s = ms / calls * 1e-3
-        entry = {"calls_per_step": calls, "avg_us": avg_s * 1e6, "share_ms_per_step": ms}
+        entry = {"calls_per_step": calls, "avg_us": avg_s * 1e6, "share_ms_per_step": ms, "share_of_step": ms / total if total else None}
         if bytes_:
             entry["algorithmic_MB"] = bytes_ / calls / 1e6
             entry["GBps"] = bytes_ / calls / avg_s / 1e9
@@ -189,6 +219,280 @@ def kernel_rooflines(prof, workload, peaks):
             entry["TFLOPps"] = flops / calls / avg_s / 1e12
         out[name] = entry
     return out
+
+
+def batch_time(fn, n=30, warm=3):
+    """Back-to-back launches bracketed by one event pair (amortises the ~3 us event / launch gap); seconds per call."""
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e-3
+
+
+def isolated_kernels(model, dev, H, W, D, peaks):
+    """The kernels the roofline targets name, timed alone: K1 warp->cost, K2 32->32, K3 EST attention (N = 1, 2, 3), K4
+    soft-argmin with the fused 1x1x1 head.  Outputs rotate over buffers larger than L2."""
+    from estdepth_b200 import ops, synth
+    out = {}
+    L = model._layers(dev)
+    Hq, Wq = H // 4, W // 4
+    g = torch.Generator(device="cpu").manual_seed(5)
+    maps = [torch.randn(8, Hq, Wq, 4, generator=g).to(dev) for _ in range(2)]
+    poses = synth.camera_track(5).to(dev)
+    K4 = model.scale_cam_intr(synth.intrinsics(H, W).unsqueeze(0), 0.25)[0].to(dev).contiguous()
+    homo = ops.homography_setup(poses[1].contiguous(), poses[0].contiguous(), K4)
+    vols = [torch.empty(8, D, Hq, Wq, 4, device=dev) for _ in range(3)]
+    dvals = model._depth_dev
+    t = batch_time(lambda i: ops.warp_cost(maps[0], maps[1], homo, dvals, vols[i % 3]))
+    nbytes = 4.0 * 32 * Hq * Wq * (D + 2)
+    out["warp_cost"] = {"us": t * 1e6, "algorithmic_MB": nbytes / 1e6, "GBps": nbytes / t / 1e9, "hbm_frac": nbytes / t / 1e9 / peaks["hbm"]}
+    vols[0].normal_()
+    t = batch_time(lambda i: ops.conv3d(L["dres0.0"], vols[0], vols[1 + i % 2], precision=model.precision))
+    flops = 54.0 * 32 * 32 * D * Hq * Wq
+    out["conv3d_32to32"] = {"us": t * 1e6, "algorithmic_GFLOP": flops / 1e9, "TFLOPps": flops / t / 1e12,
+                            "frac_of_burst_bf16": flops / t / 1e12 / peaks["bf16"], "issued_frac_of_burst_bf16": 3 * flops / t / 1e12 / peaks["bf16"]}
+    del vols, maps
+    # K3: key / value volumes of 3 sources + the target key; warps between neighbouring frames of the synthetic track
+    kv = [torch.randn(4, D, Hq, Wq, 4, generator=g).to(dev) for _ in range(8)]
+    hs = [torch.empty(4, D, Hq, Wq, 4, device=dev) for _ in range(2)]
+    tabs = ops.volume_warp_tables_torch([poses[2], poses[1], poses[3], poses[0]], 1, K4)[0].contiguous()      # [3, 30]
+    for n in (1, 2, 3):
+        t = batch_time(lambda i: ops.est_attend(kv[0], [kv[1 + 2 * j] for j in range(n)], [kv[2 + 2 * j] for j in range(n)], tabs[:n].contiguous(),
+                                                dvals, model.depth_min, model.depth_interval, out=hs[i % 2]), n=20)
+        nbytes = 4.0 * 16 * D * Hq * Wq * (2 + 2 * n)
+        out["est_attend_n%d" % n] = {"us": t * 1e6, "algorithmic_MB": nbytes / 1e6, "GBps": nbytes / t / 1e9, "hbm_frac": nbytes / t / 1e9 / peaks["hbm"]}
+    logits = torch.empty(D, Hq, Wq, device=dev)
+    dep, prob = torch.empty(H, W, device=dev), torch.empty(H, W, device=dev)
+    t = batch_time(lambda i: ops.head_softargmin(dvals, hidden=kv[i % 8], head_w=L["head0_w"], head_b=L["head0_b"], logits_out=logits,
+                                                 depth_out=dep, prob_out=prob, up=4))
+    nbytes = 4.0 * (16 * D * Hq * Wq + D * Hq * Wq + 2 * H * W)
+    out["head_softargmin"] = {"us": t * 1e6, "algorithmic_MB": nbytes / 1e6, "GBps": nbytes / t / 1e9, "hbm_frac": nbytes / t / 1e9 / peaks["hbm"]}
+    return out
+
+
+def make_model(workload, dev, args):
+    from estdepth_b200 import DepthNetHybrid, synth
+    V, H, W, D, resnet = WORKLOADS[workload]
+    model = DepthNetHybrid(ndepths=D, depth_min=0.1, depth_max=10.0, resnet=resnet,
+                           **({"precision": args.precision} if args.precision else {}),
+                           **({"geometry": args.geometry} if args.geometry else {}))
+    sd = synth.synth_state_dict(model.state_dict(), seed=0)
+    model.load_state_dict(sd)
+    return model.eval().to(dev), sd
+
+
+def estm_sequential(model, frames, n_frames, window=3, memory_size=2):
+    """eval_hybrid_seq.py:169-193: one forward per new frame, a memory of the last ``memory_size`` hidden states."""
+    from estdepth_b200 import sharding
+    memory, maps = [], []
+    for s in range(n_frames - window + 1):
+        pre = sharding._flatten_memory(memory)
+        out, costs, cposes = model(*frames(s), None, pre[0], pre[1], mode="val")
+        memory.append((costs, cposes))
+        if len(memory) > memory_size:
+            memory.pop(0)
+        maps.append(torch.cat([out[("depth", 0, 2)], out[("depth", 0, 0)]], 1))
+    return torch.cat(maps)
+
+
+def extras_single_gpu(model, sd, dev, args, step_ms, host, state, pstate):
+    """N = 1 extras (each a few seconds): see the module docstring."""
+    from estdepth_b200 import synth
+    V, H, W, D, resnet = WORKLOADS[args.workload]
+    T = V - 2
+    ex = {}
+
+    def timed_loop(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    # (1) the drivers' real call: camera parameters on the GPU (eval_hybrid.py: tocuda(sample)) -- the matrices of the warps are
+    # then derived by ~90 tiny torch launches on a side stream
+    imgs_dev, poses_dev, K_dev = host[0].to(dev), host[1].to(dev), host[2].to(dev)
+    pstate_dev = [p.to(dev) for p in pstate]
+    ms = timed_loop(lambda: model(imgs_dev, poses_dev, K_dev, None, state, pstate_dev, mode="val"), max(5, args.steps))
+    ex["cuda_camera_parameters"] = {"ms_per_step": ms, "frames_per_s": T / ms * 1e3, "vs_host_parameters": step_ms / ms}
+
+    # (2) BASELINE cfg3: ESTM sequential mode, 20-frame clip -> 18 forwards of 3 frames, memory 2 (eval_hybrid_seq.py:169-193)
+    if args.workload == "cfg2":
+        n_frames = 20
+        clip = [synth.synth_inputs(3, H, W, seed=0, start=s) for s in range(n_frames - 2)]
+        clip = [(c[0].to(dev), c[1], c[2]) for c in clip]
+        ms = timed_loop(lambda: estm_sequential(model, lambda s: clip[s], n_frames), 3)
+        ex["cfg3_estm"] = {"clip_frames": n_frames, "forwards": n_frames - 2, "ms_per_clip": ms, "ms_per_forward": ms / (n_frames - 2),
+                           "frames_per_s": (n_frames - 2) / ms * 1e3, "note": "images resident; hidden-state carry through the public forward()"}
+        del clip
+
+    # (3) the reference ALGORITHM as plain PyTorch-CUDA ops on this GPU (the oracle's op sequence with every tensor on the
+    # device = the reference's eval path: cuDNN convolutions, ATen grid_sample, ~60 host-syncing inverses) -- north_star's
+    # ">= 10x the reference PyTorch-CUDA eval frames/sec" denominator.  Baseline only.
+    if not args.no_torch_cuda_baseline:
+        from oracle import estdepth_oracle as orc
+        sd_dev = {k: v.to(dev) for k, v in sd.items()}
+        cfg = dict(ndepths=D, depth_min=0.1, depth_max=10.0, resnet=resnet, est=True)
+        base = {}
+        flags = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+        torch.set_default_device(dev)
+        try:
+            with torch.no_grad():
+                for name, tf32 in (("as_shipped_cudnn_tf32", True), ("strict_fp32", False)):
+                    torch.backends.cudnn.allow_tf32 = tf32
+                    torch.backends.cuda.matmul.allow_tf32 = False
+                    torch.backends.cudnn.benchmark = True                     # eval_hybrid.py:13
+                    orc.forward(sd_dev, cfg, imgs_dev, poses_dev, K_dev, state, pstate_dev)
+                    ms = timed_loop(lambda: orc.forward(sd_dev, cfg, imgs_dev, poses_dev, K_dev, state, pstate_dev), 4)
+                    base[name] = {"ms_per_step": ms, "frames_per_s": T / ms * 1e3, "speedup_of_this_repo": ms / step_ms}
+        finally:
+            torch.set_default_device("cpu")
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = flags
+        base["what"] = "oracle/estdepth_oracle.py (the reference's op sequence) with all tensors on cuda:0, same window, same weights"
+        ex["torch_cuda_baseline"] = base
+        del sd_dev
+        torch.cuda.empty_cache()
+
+    # (4) BASELINE cfg5: 640x960, D=128 -- frames/s and the fused warp->cost kernel against the HBM roofline
+    if args.workload == "cfg2" and not args.no_cfg5:
+        peaks = measured_peaks()
+        m5, _ = make_model("cfg5", dev, args)
+        V5, H5, W5, D5, _ = WORKLOADS["cfg5"]
+        a = synth.synth_inputs(V5, H5, W5, seed=0, start=0)
+        b = synth.synth_inputs(V5, H5, W5, seed=0, start=V5 - 2)
+        _, st5, ps5 = m5(a[0].to(dev), a[1], a[2], None, mode="val")
+        b0 = b[0].to(dev)
+        ms = timed_loop(lambda: m5(b0, b[1], b[2], None, st5, ps5, mode="val"), 5)
+        iso = isolated_kernels(m5, dev, H5, W5, D5, peaks)
+        ex["cfg5"] = {"workload": workload_string("cfg5"), "ms_per_step": ms, "frames_per_s": (V5 - 2) / ms * 1e3,
+                      "warp_cost": iso["warp_cost"], "conv3d_32to32": iso["conv3d_32to32"], "est_attend_n3": iso["est_attend_n3"]}
+        m5.check()
+        del m5, st5, ps5
+        torch.cuda.empty_cache()
+    return ex
+
+
+def extras_multi_gpu(model, dev, args, rank, world):
+    """N > 1 extras: BASELINE cfg4 and the cfg3 clip pipeline, both with their collective inside the timed region."""
+    import torch.distributed as dist
+    from estdepth_b200 import sharding, synth
+    V, H, W, D, resnet = WORKLOADS[args.workload]
+    T = V - 2
+    ex = {}
+
+    def synced_ms(fn):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = fn()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), res
+
+    # ---- cfg4: 32 sequences (steady-state windows) partitioned over the ranks, depth maps all_gather'ed (sizes known from
+    # the partition: one collective, no host read)
+    n_seq = args.cfg4_sequences
+    lo, hi = sharding.partition(n_seq, world, rank)
+    counts = [b - a for a, b in (sharding.partition(n_seq, world, r) for r in range(world))]
+
+    def prime(seq):
+        w1 = synth.synth_inputs(V, H, W, seed=1000 + seq, start=0)
+        w2 = synth.synth_inputs(V, H, W, seed=1000 + seq, start=V - 2)
+        _, st, ps = model(w1[0].to(dev), w1[1], w1[2], None, mode="val")
+        return w2[0].to(dev), w2[1], w2[2], st, ps
+
+    def run_block(block):
+        maps = []
+        for imgs, poses, K, st, ps in block:
+            out, _, _ = model(imgs, poses, K, None, st, ps, mode="val")
+            maps.append(torch.stack([out[("depth", t, s)][0, 0] for t in range(T) for s in (2, 0)]))
+        return torch.stack(maps) if maps else torch.zeros(0, 2 * T, H, W, device=dev)
+
+    mine = [prime(s) for s in range(lo, hi)]
+    run_block(mine[:1])
+    ms, gathered = synced_ms(lambda: torch.cat(sharding.gather_maps(run_block(mine), counts=counts)))
+    info = {"sequences": n_seq, "per_rank": counts, "ms": ms, "frames_per_s": n_seq * T / ms * 1e3,
+            "gather_bytes_per_rank": int(max(counts) * 2 * T * H * W * 4), "collective": "one NCCL all_gather_into_tensor of the saved maps, inside the timed region"}
+    if rank == 0:
+        # the same 32 sequences on ONE rank: the gathered maps must be what a single process computes
+        worst, equal = 0.0, True
+        for s in range(n_seq):
+            blk = mine[s - lo] if lo <= s < hi else prime(s)
+            ref = run_block([blk])[0]
+            worst = max(worst, float((ref - gathered[s]).abs().max()))
+            equal = equal and bool(torch.equal(ref, gathered[s]))
+        info["max_abs_diff_vs_single_rank"] = worst
+        info["bit_identical_to_single_rank"] = equal
+    ex["cfg4"] = info
+    del mine, gathered
+    torch.cuda.empty_cache()
+
+    # ---- cfg3 clip pipeline: ONE 20-frame ESTM sequence cut into contiguous clips over the ranks; the last memory_size hidden
+    # states (2 x 78.6 MB each) travel rank -> rank+1 over NCCL p2p as one message
+    n_frames = 20
+
+    def frames(s):
+        # camera parameters on the GPU (what the drivers pass): a state received from another rank carries a CUDA pose, and
+        # the comparison below needs the sequential loop to derive its matrices on the same device as the pipeline
+        imgs, poses, K, _ = synth.synth_inputs(3, H, W, seed=0, start=s)
+        return imgs.to(dev), poses.to(dev), K.to(dev)
+
+    cache = {}
+
+    def frames_cached(s):
+        if s not in cache:
+            cache[s] = frames(s)
+        return cache[s]
+
+    lo, hi = sharding.clip_steps(n_frames, 3, world, rank)
+    for s in range(lo, hi):
+        frames_cached(s)
+    pipe = sharding.EstmClipPipeline(model, window=3, memory_size=2)
+
+    def run_pipe():
+        (a, b), results = pipe.run(n_frames, frames_cached, (1, 16, D, H // 4, W // 4), dev)
+        local = torch.cat([torch.cat([r[("depth", 0, 2)], r[("depth", 0, 0)]], 1) for r in results]) if results else torch.zeros(0, 2, H, W, device=dev)
+        steps = [q[1] - q[0] for q in (sharding.clip_steps(n_frames, 3, world, r) for r in range(world))]
+        return torch.cat(sharding.gather_maps(local, counts=steps))
+
+    run_pipe()                                             # warm-up (NCCL p2p channels)
+    ms, piped = synced_ms(run_pipe)
+    wait = torch.tensor([pipe.recv_wait_ms()], device=dev, dtype=torch.float64)
+    dist.all_reduce(wait, op=dist.ReduceOp.MAX)
+    info = {"clip_frames": n_frames, "forwards": n_frames - 2, "ms_per_clip": ms, "frames_per_s": (n_frames - 2) / ms * 1e3,
+            "max_recv_wait_ms": float(wait.item()), "state_message_bytes": 2 * (2 * 16 * D * (H // 4) * (W // 4) * 4 + 64),
+            "collective": "NCCL isend/irecv of the last 2 hidden states between neighbouring ranks + one all_gather of the maps"}
+    if rank == 0:
+        for s in range(n_frames - 2):
+            frames_cached(s)
+        estm_sequential(model, frames_cached, n_frames)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        seq = estm_sequential(model, frames_cached, n_frames)
+        e1.record()
+        torch.cuda.synchronize()
+        info["sequential_ms_per_clip_one_gpu"] = e0.elapsed_time(e1)
+        info["speedup_vs_one_gpu"] = e0.elapsed_time(e1) / ms
+        info["max_abs_diff_vs_sequential"] = float((seq - piped).abs().max())
+        info["bit_identical_to_sequential"] = bool(torch.equal(seq, piped))
+    ex["estm_pipeline"] = info
+    dist.barrier()
+    return ex
 
 
 def run_ours(args):
@@ -202,18 +506,14 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    torch.backends.cudnn.benchmark = True                  # as shipped (eval_hybrid.py:13)
-    torch.backends.cudnn.allow_tf32 = False                # strict fp32 in the cuDNN feeders: parity gate is 1e-3
-    torch.backends.cuda.matmul.allow_tf32 = False
+    # cuDNN only runs the two stem convolutions / pools here.  benchmark stays off so that every rank (and every run) picks the
+    # same algorithm: the multi-GPU extras compare maps across ranks bit for bit.  The library forces strict fp32 itself.
+    torch.backends.cudnn.benchmark = False
 
-    from estdepth_b200 import DepthNetHybrid, synth, ops, _lib
+    from estdepth_b200 import synth, ops, _lib, sharding
     V, H, W, D, resnet = WORKLOADS[args.workload]
     T = V - 2
-    model = DepthNetHybrid(ndepths=D, depth_min=0.1, depth_max=10.0, resnet=resnet,
-                           **({"precision": args.precision} if args.precision else {}),
-                           **({"geometry": args.geometry} if args.geometry else {}))
-    model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=0))
-    model.eval().to(dev)
+    model, sd = make_model(args.workload, dev, args)
 
     # window 1 (frames 0..4) primes the hidden state, window 2 (frames 3..7) is the timed steady-state step
     seed = 100 * rank
@@ -222,19 +522,28 @@ def run_ours(args):
     host = [t.pin_memory() for t in w2[:3]]
     dev_in = [t.to(dev, non_blocking=True) for t in host]
     # camera poses / intrinsics (5 x 4x4 + 3x3 floats) are host-side metadata in both arms: the model derives the warps'
-    # matrices from them with the reference's own torch ops on the host, which is what the parity tests pin
-    # (tests/run_fullsize_parity.py); the images are what "resident" refers to
+    # matrices from them with the reference's own torch ops on the host (extras.cuda_camera_parameters times the other way)
     _, state, pstate = model(w1[0].to(dev), w1[1], w1[2], None, mode="val")
-
-    def step_resident():
-        return model(dev_in[0], host[1], host[2], None, state, pstate, mode="val")
 
     save_keys = [("depth", t, s) for t in range(T) for s in (2, 0)]        # what eval_hybrid.py writes out
     host_out = [torch.empty(1, 1, H, W).pin_memory() for _ in save_keys]
+    gathered = torch.empty(world * len(save_keys), H, W, device=dev) if world > 1 else None
+
+    def gather(outputs):
+        """BASELINE configs[3]: NCCL gather of the depth maps -- the one collective of the data-parallel path."""
+        local_maps = torch.stack([outputs[k][0, 0] for k in save_keys])
+        torch.distributed.all_gather_into_tensor(gathered, local_maps)
+
+    def step_resident():
+        outputs, _, _ = model(dev_in[0], host[1], host[2], None, state, pstate, mode="val")
+        if world > 1:
+            gather(outputs)
 
     def step_e2e():
         imgs_dev = host[0].to(dev, non_blocking=True)
         outputs, _, _ = model(imgs_dev, host[1], host[2], None, state, pstate, mode="val")
+        if world > 1:
+            gather(outputs)
         for buf, key in zip(host_out, save_keys):
             buf.copy_(outputs[key], non_blocking=True)
         torch.cuda.current_stream().synchronize()         # the driver consumes the maps before the next window
@@ -258,136 +567,115 @@ def run_ours(args):
         return float(ms.item())
 
     # nvidia-smi is started BEFORE the warm-up and the warm-up lasts until it has had time to initialise NVML and take its first
-    # samples, and until a GPU that was idle has ramped its clocks (>= W steps and >= 1 s of the same load): started right at the
-    # timed region, its start-up (a process spawn + driver queries) stalled the first timed launches by several ms, and a bench
-    # that was the first work on a fresh box timed its first steps on a GPU still leaving its idle power state -- together
-    # 1 ms per step at K = 5 (profiles/ab_r01.txt, bench_v1 vs bench_u1).  Every sample is taken under load.
+    # samples, and until a GPU that was idle has ramped its clocks (>= W steps and >= 1.5 s of the same load).
     sampler = ClockSampler(local) if rank == 0 else None
     t_warm, n_warm = time.perf_counter(), 0
-    while n_warm < max(3, args.warmup) or (n_warm < 120 and time.perf_counter() - t_warm < 1.0):
-        step_resident()
-        n_warm += 1
-        if n_warm >= max(3, args.warmup):
-            torch.cuda.current_stream().synchronize()      # the second is GPU time, not enqueue time
-    launches0 = _lib.launch_count()
-    ms_resident = timed(step_resident, args.steps)
-    launches = (_lib.launch_count() - launches0) // args.steps
-    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        # a step contains a collective: every rank must run the SAME number of warm-up steps
+        n_warm = max(3, args.warmup, 100)
+        for _ in range(n_warm):
+            step_resident()
+        torch.cuda.synchronize()
+    else:
+        while n_warm < max(3, args.warmup) or (n_warm < 200 and time.perf_counter() - t_warm < 1.5):
+            step_resident()
+            n_warm += 1
+            if n_warm >= max(3, args.warmup):
+                torch.cuda.current_stream().synchronize()      # the wait is GPU time, not enqueue time
     step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-    # host issue time of a step (informational): two steps enqueued on an idle GPU without waiting -- few enough launches to
-    # fit the driver's launch queue, so the host is not throttled by the device.  Well below ms_per_step = the GPU is the
-    # bottleneck and the host runs ahead; close to it = the step is launch/host bound.
+    launches0 = _lib.launch_count()
+    rep_res, rep_e2e = [], []
+    for _ in range(REPEATS):                               # resident and end-to-end repetitions alternate
+        rep_res.append(timed(step_resident, args.steps) / args.steps)
+        rep_e2e.append(timed(step_e2e, args.steps) / args.steps)
+    launches = (_lib.launch_count() - launches0) // (2 * REPEATS * args.steps)
+    clocks = sampler.stop() if sampler else None
+    model.check()                                          # fp16-range flag of everything timed above
+    ms_resident, ms_e2e = median(rep_res), median(rep_e2e)
+    # host issue time of a step (informational): two steps enqueued on an idle GPU without waiting
     barrier()
-    import time as _time
-    t0 = _time.perf_counter()
+    t0 = time.perf_counter()
     step_resident()
     step_resident()
-    host_issue_ms = (_time.perf_counter() - t0) * 1e3 / 2
+    host_issue_ms = (time.perf_counter() - t0) * 1e3 / 2
     barrier()
 
-    # profile pass: CUDA events around every kernel family of the library (same stream, same shapes)
-    # (the context branch stays on the main stream for this pass: with it running beside the 3-D kernels an event pair would
-    # time a kernel that shares the SMs, and the roofline wants the kernel alone)
+    # profile pass: CUDA events around every kernel family of the library (same stream, same shapes; the context branch stays
+    # on the main stream for this pass so that an event pair times its kernel alone)
     ops.PROFILE = ops.KernelProfile()
     overlap, model.overlap_context = model.overlap_context, 0
     barrier()
     prof_steps = max(1, min(args.steps, 5))
     for _ in range(prof_steps):
-        step_resident()
+        model(dev_in[0], host[1], host[2], None, state, pstate, mode="val")
     torch.cuda.synchronize()
     prof = ops.PROFILE.summary(prof_steps)
     ops.PROFILE = None
     model.overlap_context = overlap
 
-    # isolated timing of the two kernels the roofline targets name: back-to-back launches (events bracket the whole batch,
-    # so the ~3 us per-launch event/launch gap of the in-step profile is amortised); outputs rotate over buffers > L2
-    isolated = {}
-    if rank == 0:
-        L = model._layers(dev)
-        Hq, Wq = H // 4, W // 4
-        g = torch.Generator(device="cpu").manual_seed(5)
-        maps = [torch.randn(8, Hq, Wq, 4, generator=g).to(dev) for _ in range(2)]
-        homo = ops.homography_setup(dev_in[1][0, 1].contiguous(), dev_in[1][0, 0].contiguous(),
-                                    model.scale_cam_intr(dev_in[2], 0.25)[0].contiguous())
-        vols = [torch.empty(8, D, Hq, Wq, 4, device=dev) for _ in range(3)]
-        dvals = model._depth_dev
+    peaks = measured_peaks()
+    isolated = isolated_kernels(model, dev, H, W, D, peaks) if rank == 0 else {}
 
-        def batch(fn, n=30):
-            for i in range(3):
-                fn(i)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for i in range(n):
-                fn(i)
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / n * 1e-3
-
-        t = batch(lambda i: ops.warp_cost(maps[0], maps[1], homo, dvals, vols[i % 3]))
-        nbytes = 4.0 * 32 * Hq * Wq * (D + 2)
-        isolated["warp_cost"] = {"us": t * 1e6, "algorithmic_MB": nbytes / 1e6, "GBps": nbytes / t / 1e9}
-        vols[0].normal_()
-        t = batch(lambda i: ops.conv3d(L["dres0.0"], vols[0], vols[1 + i % 2], precision=model.precision))
-        flops = 54.0 * 32 * 32 * D * Hq * Wq
-        isolated["conv3d_32to32"] = {"us": t * 1e6, "algorithmic_GFLOP": flops / 1e9, "TFLOPps": flops / t / 1e12}
-        del vols, maps
+    extras = {}
+    if not args.no_extras:
+        if world > 1:
+            extras = extras_multi_gpu(model, dev, args, rank, world)
+        else:
+            extras = extras_single_gpu(model, sd, dev, args, ms_resident, host, state, pstate)
 
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
         return
 
-    peaks = measured_peaks()
-    frames = T * world * args.steps
+    frames = T * world
     value = frames / (ms_resident * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
-    kernels = kernel_rooflines(prof, args.workload, peaks)
+    kernels = kernel_rooflines(prof, peaks)
     for name, iso in isolated.items():
-        if "GBps" in iso:
-            iso["hbm_frac"] = iso["GBps"] / peaks["hbm"]
-        target = "warp_cost" if name == "warp_cost" else "conv3d_" + model.precision
+        target = {"warp_cost": "warp_cost", "conv3d_32to32": "conv3d_" + model.precision, "head_softargmin": "head_softargmin"}.get(name, "est_attend")
         if target in kernels:
             kernels[target]["isolated_" + name] = iso
-    dom = max(kernels.items(), key=lambda kv: kv[1]["share_ms_per_step"])
     conv_name = "conv3d_" + model.precision
+    dom = max(((k, v) for k, v in kernels.items() if "share_ms_per_step" in v), key=lambda kv: kv[1]["share_ms_per_step"])
     conv = kernels.get(conv_name, dom[1])
     mma_per_flop = {"fp32": 0.0, "3xtf32": 3.0, "3xf16": 3.0, "3xf16r": 3.0, "3xf16r2": 3.0}[model.precision]
     # dram__bytes_read.sum + dram__bytes_write.sum of one 32->32 launch at cfg2 size from the committed ncu --set full capture
-    # (profiles/kernels_r01_final.txt): CTA-pair kernel 217.5 + 115.2 MB, single-CTA ring kernel 256.9 + 119.0 MB, against
-    # 314.6 MB algorithmic (157.3 MB read + 157.3 MB written; the reads carry the 18x34 / 16x32 halo, part of the output is
-    # still in L2 when the kernel ends)
+    # (profiles/kernels_r01_final.txt): CTA-pair kernel 217.5 + 115.2 MB against 314.6 MB algorithmic (157.3 MB read + 157.3 MB
+    # written; the reads carry the 18x34 / 16x32 halo, part of the output is still in L2 when the kernel ends)
     traffic = {"3xf16r2": 332.6e6, "3xf16r": 375.8e6}.get(model.precision) if args.workload == "cfg2" else None
     kname = {"3xf16r": "estd::ring::conv3d_ring_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule, fp16 two-term split)",
              "3xf16r2": "estd::ring2::conv3d_ring2_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule on CTA pairs / "
-                        "cta_group::2, fp16 two-term split)"}.get(
-        model.precision, "estd conv3d kernel (%s)" % model.precision)
+                        "cta_group::2, fp16 two-term split)"}.get(model.precision, "estd conv3d kernel (%s)" % model.precision)
+    achieved = conv.get("TFLOPps") or 0.0
     roofline = {"kernel": kname if conv_name in kernels else dom[0], "bound": "tensor",
-                "achieved": conv.get("TFLOPps"), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": (conv.get("TFLOPps") or 0.0) / peaks["bf16_sustained"], "traffic": traffic,
+                "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "note": "achieved = ALGORITHMIC fp32 conv flops (54*Cin*Cout*Vx) / CUDA-event time, averaged over the step's launches; "
-                        "the error-compensated split issues %.0fx that many tensor-core flops (tensor_flops_issued_TFLOPps / peak = the "
-                        "tensor-pipe fraction); peak = dense bf16 (cuBLAS).  ncu on the CTA-pair kernel: tensor pipe 82-88 %% active; the single-"
-                        "CTA ring kernel is bound by the shared-memory pipe that feeds the tensor core (an M=128 N=96 K=16 MMA needs 56 "
-                        "wavefronts of operands for 48 cycles of math; the pair needs 44), profiles/README.md. share of step = %.1f%%" % (mma_per_flop, 100.0 * conv["share_ms_per_step"] / sum(k["share_ms_per_step"] for k in kernels.values())),
-                "tensor_flops_issued_TFLOPps": (conv.get("TFLOPps") or 0.0) * mma_per_flop,
-                "tensor_pipe_frac_issued": (conv.get("TFLOPps") or 0.0) * mma_per_flop / peaks["bf16_sustained"]}
-    cpu_base, _ = (None, None)
+                "share_of_step": conv.get("share_of_step"),
+                "note": "achieved = ALGORITHMIC fp32 conv flops (54*Cin*Cout*Vx) / CUDA-event time, averaged over the step's launches; the "
+                        "error-compensated split issues %.0fx that many tensor-core flops (tensor_pipe_frac_issued); peak = dense bf16 "
+                        "(cuBLAS).  share_of_step = this family's time / sum of all families' exclusive times (profile pass)." % mma_per_flop,
+                "tensor_flops_issued_TFLOPps": achieved * mma_per_flop,
+                "tensor_pipe_frac_issued": achieved * mma_per_flop / peaks["bf16_sustained"]}
+    cpu_base = None
     if not args.no_cpu_baseline and world == 1:             # reported at N = 1 only (rank 0's host cores)
         cpu_base, _ = oracle_sample(args.workload, 1, 1, budget_s=60.0)
     h2d = host[0].numel() * host[0].element_size() + 4 * (6 * 12 + 9 * 30)      # images + the warps' matrix tables
     d2h = sum(t.numel() * t.element_size() for t in host_out)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_resident / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (conv3d: %s)" % model.precision, "data": "synthetic",
-            "config": {"workload": workload_string(args.workload),
-                       "l2": "volumes are 157 MB each (> 126 MB L2); no explicit flush", "cudnn_tf32": False,
-                       "warmup_steps_run": n_warm,
-                       "camera_parameters": "host tensors (matrices of the warps derived on the host with the reference's torch ops)"},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_base}
+            "config": config_dict(args.workload),
+            "timing": {"repeats": REPEATS, "statistic": "median of %d repetitions of exactly %d steps, each bracketed by barrier + synchronize, "
+                                                        "CUDA events, max over ranks" % (REPEATS, args.steps),
+                       "repeats_ms_per_step": rep_res, "min_ms_per_step": min(rep_res), "max_ms_per_step": max(rep_res),
+                       "timed_region_s": sum(rep_res) * args.steps * 1e-3, "warmup_steps_run": n_warm,
+                       "collective_in_step": "all_gather_into_tensor of the saved depth maps (%d B per rank)" % d2h if world > 1 else None},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                    "repeats_ms_per_step": rep_e2e},
+            "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "clocks": clocks, "roofline": roofline,
+            "kernels": kernels, "extras": extras, "cpu_baseline": cpu_base}
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -396,13 +684,17 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default=None, choices=["fp32", "3xtf32", "3xf16", "3xf16r", "3xf16r2"], help="conv3d arithmetic (default: the model's)")
     ap.add_argument("--geometry", default=None, choices=["torch", "fp64"], help="camera-matrix derivation (default: the model's)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~1 min oracle timing on the host cores")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extras (cfg3 / cfg4 / cfg5 / PyTorch-CUDA baseline / clip pipeline)")
+    ap.add_argument("--no-torch-cuda-baseline", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true")
+    ap.add_argument("--cfg4-sequences", type=int, default=32)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -268,11 +268,11 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
     p.act_split = d->act_split; p.act_lo = d->act_lo; p.act_hi = d->act_hi;
     p.post_scale = d->post_scale;
     auto kern = conv3d_kernel<CIN_CHUNKS, COUT_PAD, RG>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;                  // the opt-in shared-memory limit is a PER-DEVICE function attribute
+    if (!attr_set.done()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
         if (e != cudaSuccess) return fail(ESTD_ECUDA, "estd_conv3d: cannot reserve %zu B of shared memory: %s", Cfg::SMEM, cudaGetErrorString(e));
-        attr_set = true;
+        attr_set.set();
     }
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(map0, map1, p);
     return check_launch("estd_conv3d");

@@ -162,14 +162,26 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int threads, siz
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+// A per-device "already done" flag (one bit per device ordinal, thread safe): function attributes such as the opt-in
+// dynamic shared-memory limit belong to the (function, device) pair, so a process-wide bool would leave every device after
+// the first without them.  Devices beyond ordinal 63 simply repeat the (cheap, idempotent) call.
+struct DeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    static int device() { int dev = 0; return cudaGetDevice(&dev) == cudaSuccess ? dev : 0; }
+    bool done() const { const int d = device(); return d < 64 && ((mask.load(std::memory_order_acquire) >> d) & 1ull); }
+    void set() { const int d = device(); if (d < 64) mask.fetch_or(1ull << d, std::memory_order_release); }
+};
+
+// SM count of the CURRENT device (cached per device ordinal)
 inline int sm_count() {
-    static int n = []() {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
-        return v > 0 ? v : 148;
-    }();
-    return n;
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64) { const int c = cache[dev].load(std::memory_order_relaxed); if (c > 0) return c; }
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    if (dev >= 0 && dev < 64) cache[dev].store(v, std::memory_order_relaxed);
+    return v;
 }
 
 // implemented in conv3d_tc.cu

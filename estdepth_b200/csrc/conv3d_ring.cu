@@ -370,11 +370,11 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
     p.D = d->D; p.H = d->H; p.W = d->W;
     p.tiles_h = tiles_h; p.tiles_w = tiles_w; p.total = (int)total;
     auto kern = conv3d_ring_kernel<S>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;                  // the opt-in shared-memory limit is a PER-DEVICE function attribute
+    if (!attr_set.done()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM);
         if (e != cudaSuccess) return fail(ESTD_ECUDA, "estd_conv3d(ring): cannot reserve %zu B of shared memory: %s", S::SMEM, cudaGetErrorString(e));
-        attr_set = true;
+        attr_set.set();
     }
     {
         cudaError_t e = launch_pdl(kern, grid, THREADS, S::SMEM, stream, map0, map1, p);

@@ -14,6 +14,8 @@ below only exist so that
 Parameter containers are registered under the reference's attribute names; the forward code is
 written against small functional helpers rather than mirroring the reference's module nesting.
 """
+import logging
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -65,9 +67,11 @@ class _FoldedConv(object):
         # dead layer's id() -- and, through the caching allocator, its weight address and version counters too
         if ent is None or ent[0] != ver or ent[3]() is not conv:
             with torch.no_grad():
-                s = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
-                w = (conv.weight.double() * s.view(-1, 1, 1, 1)).float().contiguous()
-                b = (bn.bias.double() - bn.running_mean.double() * s).float().contiguous()
+                # folded on the host in fp64, uploaded once (on the device this was ~10 tiny kernels per layer)
+                dev = conv.weight.device
+                s = bn.weight.detach().cpu().double() / torch.sqrt(bn.running_var.detach().cpu().double() + bn.eps)
+                w = (conv.weight.detach().cpu().double() * s.view(-1, 1, 1, 1)).float().contiguous().to(dev)
+                b = (bn.bias.detach().cpu().double() - bn.running_mean.detach().cpu().double() * s).float().contiguous().to(dev)
             key = id(conv)
             ent = (ver, w, b, weakref.ref(conv, lambda _, key=key, cache=self.cache: cache.pop(key, None)))
             self.cache[key] = ent
@@ -97,8 +101,9 @@ _folded.split_tf32 = _os.environ.get("ESTD_FEEDER_SPLIT_TF32", "0") == "1"
 
 
 def _bn_affine(bn):
-    scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
-    shift = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+    """Eval-mode BatchNorm -> per-channel (scale, shift), computed on the host in fp64."""
+    scale = bn.weight.detach().cpu().double() / torch.sqrt(bn.running_var.detach().cpu().double() + bn.eps)
+    shift = bn.bias.detach().cpu().double() - bn.running_mean.detach().cpu().double() * scale
     return scale.float(), shift.float()
 
 
@@ -133,12 +138,24 @@ def _run3x3(pcs, x4, out4=None, res4=None, dilation=1, in1=None, taps=9, post_sc
 
 
 def _as_vol4(t):
-    """NCHW feature map -> vol4, reusing the copy the encoder left on the tensor when there is one."""
+    """Feature map -> vol4: a 5-D tensor already is one (the tensor-core encoder returns its maps that way); an NCHW map is
+    converted, reusing the copy its producer left on the tensor when there is one."""
     from . import ops
+    if t.dim() == 5:
+        return t
     cached = getattr(t, "_estd_vol4", None)
     if cached is not None and cached.device == t.device and cached.shape[0] * 4 == t.shape[1]:
         return cached
     return ops.nchw_to_vol4(t.contiguous())
+
+
+def _as_nchw(t):
+    from . import ops
+    return ops.vol4_to_nchw(t) if t.dim() == 5 else t
+
+
+def _channels(t):
+    return t.shape[0] * 4 if t.dim() == 5 else t.shape[1]
 
 
 def _up2_vol4(x4):
@@ -203,10 +220,9 @@ class MatchingFeatureNet(nn.Module):
         self.out_channels = [32]
 
     # ------------------------------------------------------------------ tensor-core path (3x3 convs of layers 2-4, fuse conv)
-    def _bn_affine(self, bn):
-        scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
-        shift = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
-        return scale.float(), shift.float()
+    @staticmethod
+    def _bn_affine(bn):
+        return _bn_affine(bn)
 
     def _packed(self, device):
         from . import packing
@@ -337,20 +353,36 @@ class ContextEncoder(nn.Module):
         self._tc_cache = {}
 
     def _packed_block(self, blk, device):
-        """Bottleneck layers (conv1, conv2, conv3, downsample) packed for the planar tensor-core kernel; cached per block."""
+        """Layers of a torchvision Bottleneck (conv1 1x1, conv2 3x3, conv3 1x1, downsample) or BasicBlock (conv1 3x3, conv2 3x3,
+        downsample) packed for the planar tensor-core kernel; cached per block.  -> (kind, p1, p2, p3 | None, pd | None)"""
+        last = blk.conv3 if hasattr(blk, "conv3") else blk.conv2
         key = (str(device), blk.conv2.weight.data_ptr(), blk.conv1.weight._version, blk.conv2.weight._version,
-               blk.conv3.weight._version, blk.bn2.running_var._version)
+               last.weight._version, blk.bn2.running_var._version)
         ent = self._tc_cache.get(id(blk))
         if ent is None or ent[0] != key:
             pd = None if blk.downsample is None else _pack3x3(blk.downsample[0], blk.downsample[1], "none", device, any_stride=True)
-            ent = (key, (_pack3x3(blk.conv1, blk.bn1, "relu", device), _pack3x3(blk.conv2, blk.bn2, "relu", device, any_stride=True),
-                         _pack3x3(blk.conv3, blk.bn3, "add_relu", device), pd))
+            if hasattr(blk, "conv3"):
+                packed = ("bottleneck", _pack3x3(blk.conv1, blk.bn1, "relu", device), _pack3x3(blk.conv2, blk.bn2, "relu", device, any_stride=True),
+                          _pack3x3(blk.conv3, blk.bn3, "add_relu", device), pd)
+            else:
+                packed = ("basic", _pack3x3(blk.conv1, blk.bn1, "relu", device, any_stride=True), _pack3x3(blk.conv2, blk.bn2, "add_relu", device),
+                          None, pd)
+            if any(q is None for q in packed[1:3]) or (packed[0] == "bottleneck" and packed[3] is None) or \
+                    (blk.downsample is not None and pd is None):
+                # every torchvision ResNet the reference can ask for (resnet_encoder.py:23-31) has channel counts that are
+                # multiples of 16; anything else is not a silent cuDNN case but an error (feature_precision="fp32" is the
+                # explicit way to run the 2-D nets on cuDNN)
+                raise RuntimeError("estdepth_b200: ResNet block with a layer shape the planar tensor-core kernel does not take "
+                                   "(channels must be multiples of 16, stride 1 or 2); construct the model with "
+                                   "feature_precision='fp32' to run the 2-D networks on cuDNN")
+            ent = (key, packed)
             self._tc_cache[id(blk)] = ent
         return ent[1]
 
     @staticmethod
     def _block(blk, x):
-        """torchvision BasicBlock / Bottleneck in eval mode with folded BN and fused bias/residual/ReLU epilogues (cuDNN)."""
+        """torchvision BasicBlock / Bottleneck in eval mode with folded BN and fused bias/residual/ReLU epilogues (cuDNN;
+        the feature_precision="fp32" path)."""
         identity = x if blk.downsample is None else _folded(x, blk.downsample[0], blk.downsample[1])
         y = _folded(x, blk.conv1, blk.bn1, relu=True)
         if hasattr(blk, "conv3"):
@@ -359,33 +391,29 @@ class ContextEncoder(nn.Module):
         return _folded(y, blk.conv2, blk.bn2, relu=True, residual=identity)
 
     def _stage_tc(self, stage, x):
-        """One ResNet stage of Bottlenecks on the planar tcgen05 kernel; activations stay in vol4 inside the stage.  The
-        stride-2 3x3 of a stage's first block runs at stride 1 and keeps the even rows / columns (4x the flops of a
-        strided kernel, still several times faster than the fp32 CUDA-core one); its stride-2 1x1 shortcut runs on the
-        subsampled input.  x: NCHW in; returns (NCHW out, vol4 out)."""
-        from . import ops
-        x4 = None
+        """One ResNet stage (Bottlenecks: ResNet-50/101/152, BasicBlocks: ResNet-18/34) on the planar tcgen05 kernel;
+        activations stay in vol4 from the max-pool to the decoder (no NCHW copies between stages).  The stride-2 3x3 of a
+        stage's first block runs at stride 1 and keeps the even rows / columns; its stride-2 1x1 shortcut runs on the
+        subsampled input.  x4: vol4 [C/4, N, H, W, 4] in and out."""
         for blk in stage:
-            p1, p2, p3, pd = self._packed_block(blk, x.device if x is not None else x4.device)
-            if p1 is None or p2 is None or p3 is None or (blk.downsample is not None and pd is None):
-                x = self._block(blk, x if x is not None else ops.vol4_to_nchw(x4))     # not a shape the kernel takes: cuDNN
-                x4 = None
-                continue
-            if x4 is None:
-                x4 = ops.nchw_to_vol4(x.contiguous())
+            kind, p1, p2, p3, pd = self._packed_block(blk, x4.device)
+            strided = (blk.conv2 if kind == "bottleneck" else blk.conv1).stride != (1, 1)
             if blk.downsample is None:
                 identity4 = x4
             else:
                 xs = x4 if blk.downsample[0].stride == (1, 1) else x4[:, :, ::2, ::2, :].contiguous()
                 identity4 = _run3x3(pd, xs, taps=1)
-            y4 = _run3x3(p2, _run3x3(p1, x4, taps=1))
-            if blk.conv2.stride != (1, 1):
-                y4 = y4[:, :, ::2, ::2, :].contiguous()
-            x4 = _run3x3(p3, y4, res4=identity4, taps=1)
-            x = None
-        if x is None:
-            x = ops.vol4_to_nchw(x4)
-        return x, x4
+            if kind == "bottleneck":
+                y4 = _run3x3(p2, _run3x3(p1, x4, taps=1))
+                if strided:
+                    y4 = y4[:, :, ::2, ::2, :].contiguous()
+                x4 = _run3x3(p3, y4, res4=identity4, taps=1)
+            else:
+                y4 = _run3x3(p1, x4)
+                if strided:
+                    y4 = y4[:, :, ::2, ::2, :].contiguous()
+                x4 = _run3x3(p2, y4, res4=identity4)
+        return x4
 
     def forward(self, x):
         e = self.encoder
@@ -397,14 +425,17 @@ class ContextEncoder(nn.Module):
             return maps
         maps = [_folded(x, e.conv1, e.bn1, relu=True)]
         x = e.maxpool(maps[-1])
+        if self.tensor_cores and x.is_cuda:
+            # maps[1:] are returned in vol4 (5-D); the decoder's tensor-core path consumes them as they are (_as_vol4)
+            from . import ops
+            x4 = ops.nchw_to_vol4(x.contiguous())
+            for stage in (e.layer1, e.layer2, e.layer3, e.layer4):
+                x4 = self._stage_tc(stage, x4)
+                maps.append(x4)
+            return maps
         for stage in (e.layer1, e.layer2, e.layer3, e.layer4):
-            if self.tensor_cores and x.is_cuda and hasattr(stage[0], "conv3"):
-                x, x4 = self._stage_tc(stage, x)
-                if x4 is not None:
-                    x._estd_vol4 = x4          # the decoder takes the vol4 copy directly (saves a layout pass per map)
-            else:
-                for blk in stage:
-                    x = self._block(blk, x)
+            for blk in stage:
+                x = self._block(blk, x)
             maps.append(x)
         return maps
 
@@ -475,10 +506,20 @@ class ContextDecoder2D(nn.Module):
         P = self._packed(x.device)
         return P if all(P[n] is not None for n in names) else None
 
+    def _log_cudnn(self, what, x):
+        """The one shape the planar kernel does not take is a depth-plane count that is not a multiple of 16 (the decoder's
+        layers then have input channels that are not whole 16-channel k-steps).  That is an explicit decision, logged once
+        per module: the stage runs on cuDNN in strict fp32 -- not a silent fallback."""
+        if self.tensor_cores and x.is_cuda and not self.training and what not in self.__dict__.setdefault("_cudnn_logged", set()):
+            self._cudnn_logged.add(what)
+            logging.getLogger("estdepth_b200").warning(
+                "%s: ndepths is not a multiple of 16 -> this stage runs on cuDNN (strict fp32) instead of the planar "
+                "tcgen05 kernel; choose ndepths %% 16 == 0 for the tensor-core path", what)
+
     def context(self, maps):
         from . import ops
         P = self._use_tc(maps[4], ("upconv_4_0", "upconv_4_1", "upconv_3_0", "upconv_3_1", "upconv_2_0", "upconv_2_1"))
-        if P is not None and all(m.shape[1] % 16 == 0 for m in maps[1:]):
+        if P is not None and all(_channels(m) % 16 == 0 for m in maps[1:]):
             # same layers, planar tcgen05 kernel: torch.cat becomes a second input segment, activations stay in vol4
             x = _run3x3(P["upconv_4_0"], _as_vol4(maps[4]))
             x = _run3x3(P["upconv_4_1"], _up2_vol4(x), in1=_as_vol4(maps[3]))
@@ -486,7 +527,11 @@ class ContextDecoder2D(nn.Module):
             x = _run3x3(P["upconv_3_1"], _up2_vol4(x), in1=_as_vol4(maps[2]))
             x = _run3x3(P["upconv_2_0"], x)
             x = _run3x3(P["upconv_2_1"], _up2_vol4(x), in1=_as_vol4(maps[1]))
-            return ops.vol4_to_nchw(x)
+            out = ops.vol4_to_nchw(x)
+            out._estd_vol4 = x                  # refine() takes the vol4 copy (saves a layout pass)
+            return out
+        self._log_cudnn("context decoder", maps[4])
+        maps = [_as_nchw(m) for m in maps]
         x = self.upconv_4_0(maps[4])
         x = self.upconv_4_1(torch.cat([_up2(x), maps[3]], 1))
         x = self.upconv_3_0(x)
@@ -500,13 +545,14 @@ class ContextDecoder2D(nn.Module):
         P = self._use_tc(semantic_vs, ("upconv_1_0", "upconv_1_1", "upconv_0_0", "upconv_0_1", "dispconv_1", "dispconv_0"))
         if P is not None and semantic_vs.shape[1] % 16 == 0 and skip_half.shape[1] % 16 == 0:
             # whole refinement on the planar tcgen05 kernel: cat -> second input segment, sigmoid * depth_max in the epilogue
-            x = _run3x3(P["upconv_1_0"], ops.nchw_to_vol4(semantic_vs.contiguous()), in1=ops.nchw_to_vol4(F.relu(fused_logits)))
+            x = _run3x3(P["upconv_1_0"], _as_vol4(semantic_vs), in1=ops.nchw_to_vol4(F.relu(fused_logits)))
             x = _run3x3(P["upconv_1_1"], _up2_vol4(x), in1=ops.nchw_to_vol4(skip_half.contiguous()))
             d1 = _run3x3(P["dispconv_1"], x, post_scale=self.depth_max)                  # [1 chunk, N, H/2, W/2, 4]
             depth_half = _up2(d1[0, ..., 0].unsqueeze(1))
             x = _run3x3(P["upconv_0_1"], _up2_vol4(_run3x3(P["upconv_0_0"], x)))
             depth_full = _run3x3(P["dispconv_0"], x, post_scale=self.depth_max)[0, ..., 0].unsqueeze(1).contiguous()
             return depth_half, depth_full
+        self._log_cudnn("refinement", semantic_vs)
         x = self.upconv_1_0(torch.cat([semantic_vs, F.relu(fused_logits)], dim=1))
         x = self.upconv_1_1(torch.cat([_up2(x), skip_half], 1))
         depth_half = _up2(self.depth_max * torch.sigmoid(self.dispconv_1(x)))

@@ -15,7 +15,11 @@ import torch
 
 
 class DepthMapWriter(object):
-    def __init__(self, max_pending=16):
+    def __init__(self, max_pending=16, check=None):
+        """``check``: optional callable run by ``close()`` after the last map is on disk, e.g. ``model.check`` -- the blocking
+        fp16-range check of DepthNetHybrid, so that a sequence whose last windows overflowed is reported where its maps
+        are finalised (the per-call check inside ``forward`` is deliberately late by one or two calls)."""
+        self._check = check
         self._q = queue.Queue(maxsize=max_pending)       # back-pressure: at most max_pending maps in flight
         self._error = None
         self._streams = {}
@@ -79,6 +83,8 @@ class DepthMapWriter(object):
         if self._error is not None:
             err, self._error = self._error, None
             raise err
+        if self._check is not None:
+            self._check()
 
     def __enter__(self):
         return self

@@ -19,6 +19,7 @@ Q4 the returned hidden-state pose is the LAST MEMORY pose once a memory exists, 
 later targets attend to already-fused values, Q6 mean-not-sum attention, Q7 rel_pose = P_j P_i^-1.
 """
 import collections
+import contextlib
 import os
 
 import torch
@@ -35,6 +36,22 @@ def _upload(t, dev):
     if t.is_cuda:
         return (t if t.device == dev else t.to(dev)).contiguous()
     return t.contiguous().pin_memory().to(dev, non_blocking=True)
+
+
+@contextlib.contextmanager
+def _strict_fp32():
+    """The cuDNN-side 2-D layers (stems, pools' neighbours, the fp32 feature path) and the small fp32 GEMMs run in STRICT
+    fp32 whatever the process-wide flags say: PyTorch's default is ``cudnn.allow_tf32 = True`` and the reference's drivers
+    never change it (eval_hybrid.py:13 only sets ``benchmark``), but single-pass TF32 in these layers breaks the 1e-3 depth
+    gate.  The caller's flags are restored on exit."""
+    cudnn_tf32, matmul_tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32 = cudnn_tf32
+        torch.backends.cuda.matmul.allow_tf32 = matmul_tf32
 
 
 def _conv_bn3(cin, cout, k):
@@ -333,9 +350,19 @@ class DepthNetHybrid(nn.Module):
     def _state_to_vol4(t, b):
         """Hidden-state tensor [B,16,D,H,W] handed back by a driver -> this batch element's vol4."""
         cached = getattr(t, "_estd_vol4", None)
-        if cached is not None and cached[b].device == t.device:
+        if cached is not None and cached[b] is not None and cached[b].device == t.device:
             return cached[b]
-        return ops.ncdhw_to_vol4(t[b].detach().to(torch.float32).contiguous())
+        vol = ops.ncdhw_to_vol4(t[b].detach().to(torch.float32).contiguous())
+        # remembered on the tensor object: a state that arrived as plain NCDHW data (cloned by a driver, received from another
+        # rank) is converted once, not once per window it stays in the memory.  The caller must not modify a state in place.
+        if cached is None:
+            cached = [None] * t.shape[0]
+            try:
+                t._estd_vol4 = cached
+            except AttributeError:
+                return vol
+        cached[b] = vol
+        return vol
 
     # ------------------------------------------------------------------ forward
     def forward(self, imgs, cam_poses, cam_intr, sample=None, pre_costs=None, pre_cam_poses=None, mode='train', frame_ids=None):
@@ -349,21 +376,45 @@ class DepthNetHybrid(nn.Module):
             raise NotImplementedError("estdepth_b200 implements the inference path (mode='val'); got mode=%r" % (mode,))
         if not imgs.is_cuda:
             raise RuntimeError("estdepth_b200.DepthNetHybrid runs on CUDA only (no CPU fallback); imgs is on %s" % imgs.device)
-        if self.precision in ("3xf16", "3xf16r", "3xf16r2") or self.feature_precision == "3xf16":
-            ops.check_status_async(imgs.device)     # fp16 range flag of earlier calls, without draining the GPU
-        with torch.no_grad():
-            return self._forward_val(imgs, cam_poses, cam_intr, pre_costs, pre_cam_poses, frame_ids)
+        return self._forward_val(imgs, cam_poses, cam_intr, pre_costs, pre_cam_poses, frame_ids)
 
     def _forward_val(self, imgs, cam_poses, cam_intr, pre_costs, pre_cam_poses, frame_ids=None):
         memory_poses = pre_cam_poses if (self.IF_EST_transformer and pre_costs is not None) else None
         return self.fuse(self.prepare(imgs, cam_poses, cam_intr, memory_poses=memory_poses, frame_ids=frame_ids),
                          pre_costs, pre_cam_poses)
 
+    def _poll_status(self, device):
+        """fp16 range flag of EARLIER launches, examined without draining the GPU (ops.check_status_async): called at the start
+        of ``prepare`` and of ``fuse`` so that callers of the split API (the clip pipeline) are covered too.  The check is
+        late by design -- a violation in the last call of a run is only caught by ``check()``."""
+        if self.precision in ("3xf16", "3xf16r", "3xf16r2") or self.feature_precision == "3xf16":
+            ops.check_status_async(device)
+
+    def check(self, device=None):
+        """Blocking end-of-sequence check: raises if any fp16-split convolution launched so far saw an activation beyond
+        the fp16 range (its outputs, and every hidden state derived from them, are invalid).  One 4-byte read that
+        synchronises the device -- call it after the last window of a sequence, before trusting / saving its maps."""
+        if device is None:
+            device = next(self.parameters()).device
+        ops.check_status(device)
+
     def prepare(self, imgs, cam_poses, cam_intr, memory_poses=None, frame_ids=None):
         """Everything that does not depend on the hidden state (about 89 % of the FLOPs of a step):
         2-D feeders, cost volumes, matching net, key/value volumes, initial depth.  ``forward`` is
         ``fuse(prepare(...), pre_costs, pre_cam_poses)``; the split lets a rank of the ESTM clip pipeline
         (``sharding.py``) run ahead while it waits for its predecessor's memory."""
+        self._poll_status(imgs.device)
+        with torch.no_grad(), _strict_fp32():
+            return self._prepare(imgs, cam_poses, cam_intr, memory_poses, frame_ids)
+
+    def fuse(self, prep, pre_costs=None, pre_cam_poses=None):
+        """EST fusion against the memory (or the no-EST path, quirk Q3), stereo_head1 + soft-argmin, 2-D refinement,
+        outputs and the hidden state to hand to the next call (hybrid_depth_decoder.py:211-292 / :373-417)."""
+        self._poll_status(prep["dev"])
+        with torch.no_grad(), _strict_fp32():
+            return self._fuse_tail(prep, pre_costs, pre_cam_poses)
+
+    def _prepare(self, imgs, cam_poses, cam_intr, memory_poses=None, frame_ids=None):
         dev = imgs.device
         imgs = 2 * (imgs / 255.) - 1.
         B, V, _, Hi, Wi = imgs.shape
@@ -392,7 +443,7 @@ class DepthNetHybrid(nn.Module):
             inputs_ready.record(torch.cuda.current_stream(dev))
 
         # ---- 2-D feeders (cuDNN) ----
-        t_prof = ops._pb()
+        t_prof = ops._bracket_begin("torch_2d_feeders")
         if self.overlap_context:
             # the context branch (ResNet + 2-D decoder on the T target frames) does not meet the matching branch before dres2:
             # it runs on its own stream beside the matching-feature net.  Most of its layers work at 1/8 .. 1/32 resolution
@@ -408,8 +459,9 @@ class DepthNetHybrid(nn.Module):
                 ctx_done = torch.cuda.Event()
                 ctx_done.record(ctx)
             feats = self._matching_features(imgs, frame_ids)
-            for t_ in (semantic_vs, maps[0]):
-                t_.record_stream(main)           # allocated on the context stream, consumed (and released) on the main one
+            for t_ in (semantic_vs, maps[0], getattr(semantic_vs, "_estd_vol4", None)):
+                if t_ is not None:
+                    t_.record_stream(main)       # allocated on the context stream, consumed (and released) on the main one
             if self.overlap_context >= 2:
                 self._ctx_done = ctx_done        # joined where the context map is first needed (dres2 of the first target)
             else:
@@ -418,7 +470,7 @@ class DepthNetHybrid(nn.Module):
             feats = self._matching_features(imgs, frame_ids)
             maps = self.semanticFeature(imgs[:, 1:1 + T].reshape(B * T, 3, Hi, Wi))
             semantic_vs = self.CostRegNet.context(maps).contiguous()                 # [B*T, D, H, W]
-        ops._pe(t_prof, "cudnn_2d_feeders")
+        ops._bracket_end("torch_2d_feeders", t_prof)
         # camera algebra of both warps with the reference's own torch ops (~90 tiny launches): issued AFTER the feeders so that
         # the GPU is already busy while the host spends its millisecond on them, and on a side stream so that they run beside
         # the feeders instead of between them and the first warp
@@ -470,9 +522,7 @@ class DepthNetHybrid(nn.Module):
                     host_geometry=host_geometry, poses_host=poses_src if host_geometry else None,
                     K4_host=K4_src if host_geometry else None)
 
-    def fuse(self, prep, pre_costs=None, pre_cam_poses=None):
-        """EST fusion against the memory (or the no-EST path, quirk Q3), stereo_head1 + soft-argmin, 2-D refinement,
-        outputs and the hidden state to hand to the next call (hybrid_depth_decoder.py:211-292 / :373-417)."""
+    def _fuse_tail(self, prep, pre_costs=None, pre_cam_poses=None):
         B, T, D, H, W, Hi, Wi, dev = (prep[k] for k in ("B", "T", "D", "H", "W", "Hi", "Wi", "dev"))
         L = self._layers(dev)
         ws = self._workspace(dev, D, H, W, L)
@@ -520,9 +570,9 @@ class DepthNetHybrid(nn.Module):
         last_pose_src = (T + pre_num - 1) if (use_est and not self.fix_stale_pose) else (T - 1)
 
         # ---- 2-D refinement (cuDNN) ----
-        t_prof = ops._pb()
+        t_prof = ops._bracket_begin("torch_2d_refine")
         depth_half, depth_full = self.CostRegNet.refine(prep["semantic_vs"], fused_logits, prep["skip_half"])
-        ops._pe(t_prof, "cudnn_2d_refine")
+        ops._bracket_end("torch_2d_refine", t_prof)
         depth_half = depth_half.reshape(B, T, 1, Hi, Wi)
         depth_full = depth_full.reshape(B, T, 1, Hi, Wi)
 

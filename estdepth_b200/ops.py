@@ -29,10 +29,15 @@ DEFAULT_PRECISION = "fp32"
 
 class KernelProfile(object):
     """Optional per-kernel-family CUDA-event timing (bench.py's roofline pass).  Events are recorded on the stream the
-    kernels are launched on; algorithmic flops / bytes per launch follow SURVEY.md section 8(d)."""
+    kernels are launched on; algorithmic flops / bytes per launch follow SURVEY.md section 8(d).
+
+    Brackets (``bracket_begin`` / ``bracket_end``) time a whole stage that mixes library kernels and torch / cuDNN ops: the
+    families recorded inside a bracket are remembered as its children, so that the summary can report the stage's
+    EXCLUSIVE time (what is not one of the library's own families) and nothing is counted twice in the step's shares."""
 
     def __init__(self):
-        self.records = {}          # family -> list of (start_event, end_event, flops, bytes)
+        self.records = {}          # family -> list of (start_event, end_event, flops, bytes, enclosing bracket or None)
+        self.stack = []
 
     def begin(self):
         e = torch.cuda.Event(enable_timing=True)
@@ -42,15 +47,34 @@ class KernelProfile(object):
     def end(self, family, start, flops=0.0, nbytes=0.0):
         e = torch.cuda.Event(enable_timing=True)
         e.record(torch.cuda.current_stream())
-        self.records.setdefault(family, []).append((start, e, float(flops), float(nbytes)))
+        self.records.setdefault(family, []).append((start, e, float(flops), float(nbytes), self.stack[-1] if self.stack else None))
+
+    def bracket_begin(self, name):
+        self.stack.append(name)
+        return self.begin()
+
+    def bracket_end(self, name, start):
+        assert self.stack and self.stack[-1] == name
+        self.stack.pop()
+        self.end(name, start)
 
     def summary(self, steps):
-        """-> family -> (ms per step, calls per step, flops per step, bytes per step)"""
+        """-> family -> (ms per step, calls per step, flops per step, bytes per step).  A bracket's entry is its EXCLUSIVE
+        time; its inclusive time is reported under ``<name>(inclusive)`` with zero calls (bench.py leaves those out of the
+        shares)."""
         torch.cuda.synchronize()
-        out = {}
+        out, inner = {}, {}
         for fam, recs in self.records.items():
-            ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
+            ms = sum(r[0].elapsed_time(r[1]) for r in recs)
             out[fam] = (ms / steps, len(recs) / float(steps), sum(r[2] for r in recs) / steps, sum(r[3] for r in recs) / steps)
+            for r in recs:
+                if r[4] is not None:
+                    inner[r[4]] = inner.get(r[4], 0.0) + r[0].elapsed_time(r[1])
+        for name, ms_inner in inner.items():
+            if name in out:
+                incl = out[name]
+                out[name + "(inclusive)"] = (incl[0], 0.0, 0.0, 0.0)
+                out[name] = (max(0.0, incl[0] - ms_inner / steps), incl[1], 0.0, 0.0)
         return out
 
 
@@ -64,6 +88,15 @@ def _pb():
 def _pe(start, family, flops=0.0, nbytes=0.0):
     if start is not None:
         PROFILE.end(family, start, flops, nbytes)
+
+
+def _bracket_begin(name):
+    return PROFILE.bracket_begin(name) if PROFILE is not None else None
+
+
+def _bracket_end(name, start):
+    if start is not None:
+        PROFILE.bracket_end(name, start)
 
 
 def _stream():
@@ -224,6 +257,26 @@ class PackedConv(object):
         self.cout = cout if cout is not None else min(cout_pad, 4 * out_chunks)
         self.cin_chunks, self.cout_pad, self.out_chunks = cin_chunks, cout_pad, out_chunks
         self.act_split, self.act_lo, self.act_hi = act_split, ACT[act_lo], ACT[act_hi]
+
+    TENSORS = ("weight", "scale", "shift", "weight_tc", "weight_f16", "scale_f16", "weight_ring", "weight_ring2", "scale_ring")
+
+    def to(self, device, memo=None):
+        """Moves every buffer to ``device`` in place (one copy per buffer; ``memo`` de-duplicates buffers shared between
+        layers) and drops the cached descriptor templates, which hold device addresses.  Returns self."""
+        device = torch.device(device)
+        for name in self.TENSORS:
+            t = getattr(self, name)
+            if t is None or t.device == device:
+                continue
+            if memo is not None:
+                got = memo.get(id(t))
+                if got is None:
+                    got = memo[id(t)] = (t, t.to(device))
+                setattr(self, name, got[1])
+            else:
+                setattr(self, name, t.to(device))
+        self._desc = None
+        return self
 
 
 def _precision(pc, precision):

@@ -222,20 +222,26 @@ def attach_tc(pc):
 def pack_conv2d(weight, scale, shift, act, device, cout_slice=64):
     """2-D 3x3 conv [Cout,Cin,3,3] with folded per-channel affine -> list with ONE PackedConv for conv2d_tc.cu.
 
+    All arithmetic happens on the HOST (the parameters are copied back once if they live on the GPU) and only the packed
+    buffers are uploaded: packing on the device cost ~15 tiny torch kernels per layer, i.e. about a thousand launches before
+    a model's first real kernel.
+
     The planar tensor-core kernel is specialised for 64 / 32 / 16 output channels per accumulator; wider layers are packed
     as Cout/64 slices [slice][nks][9][2][128 rows][16 B] that the kernel runs as independent units of one launch
     (cout_pad = 64 * slices).  (A list is returned for the callers that iterate over per-launch pieces.)"""
     cout, cin = weight.shape[0], weight.shape[1]
+    host = torch.device("cpu")
+    weight, scale, shift = weight.detach().to(host), scale.detach().to(host), shift.detach().to(host)
     if cout > cout_slice:
         assert cout_slice == 64, "only 64-channel slices can be combined in one launch"
-        pieces = _pack_conv2d_slices(weight, scale, shift, act, device, 64)
+        pieces = _pack_conv2d_slices(weight, scale, shift, act, host, 64)
         total = 64 * len(pieces)
         pc = PackedConv(None, torch.cat([q.scale for q in pieces]), torch.cat([q.shift for q in pieces]), (cin + 3) // 4, total,
                         (cout + 3) // 4, total, act, act, cin=cin, cout=cout, cout_pad_tc=total)
         pc.weight_f16 = torch.cat([q.weight_f16.reshape(-1) for q in pieces]).contiguous()
         pc.scale_f16 = torch.cat([q.scale_f16 for q in pieces]).contiguous()
-        return [pc]
-    return _pack_conv2d_slices(weight, scale, shift, act, device, cout_slice)
+        return [pc.to(device)]
+    return [q.to(device) for q in _pack_conv2d_slices(weight, scale, shift, act, host, cout_slice)]
 
 
 def _pack_conv2d_slices(weight, scale, shift, act, device, cout_slice):
@@ -272,7 +278,12 @@ CANON36 = list(range(1, 33)) + [0, -1, -1, -1]            # canonical order of t
 
 
 def pack_layers(sd, device):
-    """All 3-D layers of the hot path -> dict name -> PackedConv (tensors on ``device``)."""
+    """All 3-D layers of the hot path -> dict name -> PackedConv (tensors on ``device``).
+
+    Folding / permuting / splitting runs on the host; the packed buffers are uploaded once at the end (see pack_conv2d)."""
+    target = torch.device(device)
+    device = torch.device("cpu")
+    sd = {k: v.detach().to(device) for k, v in sd.items()}
     def conv_bn(prefix, cin_order, cout_order, cout_pad, act_split, act_lo, act_hi, out_chunks):
         w = sd[prefix + ".0.weight"].to(device)
         scale, shift = fold_bn(sd, prefix + ".1")
@@ -327,4 +338,20 @@ def pack_layers(sd, device):
     # both halves stacked: one premix launch per sequence gives every frame's target-side (chunks 0..7) and source-side mix
     layers["pre0_both"] = torch.cat([layers["pre0_ref"], layers["pre0_src"]], 0).contiguous()
     layers["pre0_both_bias"] = torch.cat([layers["pre0_bias"], torch.zeros_like(layers["pre0_bias"])]).contiguous()
+    if target.type != "cpu":
+        memo = {}
+        for name, v in layers.items():
+            layers[name] = v.to(target, memo) if isinstance(v, PackedConv) else _upload(v, target, memo)
     return layers
+
+
+def _upload(t, device, memo=None):
+    """Host tensor -> device, once per distinct tensor (layers made with copy.copy share their buffers)."""
+    if t is None or not torch.is_tensor(t):
+        return t
+    if memo is None:
+        return t.to(device)
+    got = memo.get(id(t))
+    if got is None:
+        got = memo[id(t)] = (t, t.to(device))          # the source is kept alive so that its id() stays unique
+    return got[1]

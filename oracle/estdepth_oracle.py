@@ -211,15 +211,20 @@ def _force_outside(c):
     return torch.where((c > 1) | (c < -1), torch.full_like(c, 2.0), c)
 
 
-def plane_sweep_grid(src_proj, ref_proj, depth_values, H, W):
+def plane_sweep_grid(src_proj, ref_proj, depth_values, H, W, homo12=None):
     """Normalised sample coords of utils/homo_utils.py:469-491.  Returns xn, yn [D, H*W] (B=1).
 
-    src_proj/ref_proj [4,4]; depth_values [D].
+    src_proj/ref_proj [4,4]; depth_values [D].  ``homo12`` (test hook): the 12 numbers [rot (9) | trans (3)] of
+    ``src_proj @ inverse(ref_proj)`` computed elsewhere (e.g. by the same torch ops on a GPU, whose LU differs from
+    LAPACK's in the last bit) -- the rest of the arithmetic is unchanged.
     """
     # batched (B=1) matmuls on purpose: ATen picks bmm for [1,3,3]x[1,3,HW] and its fp32 summation order
     # differs from the 2-D mm kernel by a few 1e-7 -- enough to move taps by 3e-5 in feature units.
-    proj = torch.matmul(src_proj.unsqueeze(0), torch.inverse(ref_proj.unsqueeze(0)))
-    rot, trans = proj[:, :3, :3], proj[:, :3, 3:4]
+    if homo12 is None:
+        proj = torch.matmul(src_proj.unsqueeze(0), torch.inverse(ref_proj.unsqueeze(0)))
+        rot, trans = proj[:, :3, :3], proj[:, :3, 3:4]
+    else:
+        rot, trans = homo12[:9].reshape(1, 3, 3), homo12[9:12].reshape(1, 3, 1)
     y, x = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
     xyz = torch.stack((x.reshape(-1), y.reshape(-1), torch.ones(H * W))).unsqueeze(0)   # [1, 3, HW]
     rot_xyz = torch.matmul(rot, xyz)[0]                                                 # [3, HW]
@@ -231,11 +236,11 @@ def plane_sweep_grid(src_proj, ref_proj, depth_values, H, W):
     return xn, yn
 
 
-def homo_warp(src_fea, src_proj, ref_proj, depth_values, sampler="aten"):
+def homo_warp(src_fea, src_proj, ref_proj, depth_values, sampler="aten", homo12=None):
     """utils/homo_utils.py:458-504.  src_fea [1,C,H,W] -> [1,C,D,H,W]."""
     _, C, H, W = src_fea.shape
     D = depth_values.numel()
-    xn, yn = plane_sweep_grid(src_proj[0], ref_proj[0], depth_values.reshape(-1), H, W)
+    xn, yn = plane_sweep_grid(src_proj[0], ref_proj[0], depth_values.reshape(-1), H, W, homo12)
     if sampler == "aten":
         grid = torch.stack((xn, yn), dim=2).view(1, D * H, W, 2)
         out = F.grid_sample(src_fea, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
@@ -243,20 +248,26 @@ def homo_warp(src_fea, src_proj, ref_proj, depth_values, sampler="aten"):
     return bilinear_zeros(src_fea[0], xn.view(D, H, W), yn.view(D, H, W)).unsqueeze(0)
 
 
-def volume_warp_grid(rel_pose, cam_intr, depth_values, D, H, W, depth_min, depth_interval):
+def volume_warp_grid(rel_pose, cam_intr, depth_values, D, H, W, depth_min, depth_interval, table30=None):
     """Normalised coords of warp_volume (homo_utils.py:240-271 with helpers :40-62, :26-37, :107-134, :170-205).
 
     rel_pose [4,4] (= P_j . P_i^-1, hybrid_depth_decoder.py:235), cam_intr [3,3] (1/4-scaled K),
-    depth_values [D].  Returns xn, yn, zn [D, H*W].
+    depth_values [D].  Returns xn, yn, zn [D, H*W].  ``table30`` (test hook): [inverse(K) (9) | first three rows of
+    inverse(rel_pose) (12) | K (9)] computed elsewhere, used in place of the two ``torch.inverse`` calls.
     """
     y, x = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
     pix = torch.stack((x.reshape(-1), y.reshape(-1), torch.ones(H * W)))             # set_id_grid :7-14
     # the reference broadcasts the pixel grid over D *before* the K^-1 product (pixel grid [B,3,D,HW], :52-54)
     pix = pix.view(1, 3, 1, H * W).repeat(1, 1, D, 1).view(1, 3, -1)
-    ray = torch.inverse(cam_intr.unsqueeze(0)).bmm(pix).view(3, D, H * W)             # pixel2cam :51-54
+    if table30 is None:
+        kinv, rel_inv = torch.inverse(cam_intr.unsqueeze(0)), torch.inverse(rel_pose.unsqueeze(0))
+    else:
+        kinv = table30[:9].reshape(1, 3, 3)
+        rel_inv = torch.cat([table30[9:21].reshape(3, 4), torch.tensor([[0.0, 0.0, 0.0, 1.0]])], 0).unsqueeze(0)
+    ray = kinv.bmm(pix).view(3, D, H * W)                                             # pixel2cam :51-54
     cam = ray * depth_values.view(1, D, 1)                                            # [3, D, HW]
     cam4 = torch.cat([cam, torch.ones(1, D, H * W)], 0).reshape(1, 4, -1)
-    src = torch.bmm(torch.inverse(rel_pose.unsqueeze(0)), cam4)                       # cam2cam :26-37
+    src = torch.bmm(rel_inv, cam4)                                                    # cam2cam :26-37
     uvw = torch.bmm(cam_intr.unsqueeze(0), src[:, :3])[0]                             # cam2pixel_depth :116
     px = (uvw[0] / (uvw[2] + 1e-10)).view(D, H * W)
     py = (uvw[1] / (uvw[2] + 1e-10)).view(D, H * W)
@@ -267,10 +278,11 @@ def volume_warp_grid(rel_pose, cam_intr, depth_values, D, H, W, depth_min, depth
     return xn, yn, zn
 
 
-def warp_volume(vol, rel_pose, cam_intr, depth_values, depth_min, depth_interval, sampler="aten"):
+def warp_volume(vol, rel_pose, cam_intr, depth_values, depth_min, depth_interval, sampler="aten", table30=None):
     """utils/homo_utils.py:240-279, zeros padding.  vol [1,C,D,H,W] -> same shape."""
     _, C, D, H, W = vol.shape
-    xn, yn, zn = volume_warp_grid(rel_pose[0], cam_intr[0], depth_values.reshape(-1), D, H, W, depth_min, depth_interval)
+    xn, yn, zn = volume_warp_grid(rel_pose[0], cam_intr[0], depth_values.reshape(-1), D, H, W, depth_min, depth_interval,
+                                  table30)
     if sampler == "aten":
         grid = torch.stack((xn, yn, zn), dim=2).view(1, D, H, W, 3)
         return F.grid_sample(vol, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
@@ -281,8 +293,9 @@ def warp_volume(vol, rel_pose, cam_intr, depth_values, depth_min, depth_interval
 # cost volume (row a4/a6), matching net (a8), soft-argmin (a9), EST fusion (a11)
 # ----------------------------------------------------------------------------------------------
 
-def cost_volume(sd, feats, poses, cam_intr, depth_values, sampler="aten", taps=None):
-    """hybrid_models/model_hybrid.py:62-102.  feats: 3 maps [1,32,H,W]; poses [1,3,4,4]; middle = target."""
+def cost_volume(sd, feats, poses, cam_intr, depth_values, sampler="aten", taps=None, homo=None):
+    """hybrid_models/model_hybrid.py:62-102.  feats: 3 maps [1,32,H,W]; poses [1,3,4,4]; middle = target.
+    ``homo`` (test hook): [2, 12] precomputed [rot | trans] of the two sources (see plane_sweep_grid)."""
     ref = feats[1]
     D = depth_values.numel()
     ref_ext = torch.inverse(poses[:, 1])
@@ -293,7 +306,7 @@ def cost_volume(sd, feats, poses, cam_intr, depth_values, sampler="aten", taps=N
         src_proj, ref_proj = src_ext.clone(), ref_ext.clone()
         src_proj[:, :3, :4] = cam_intr @ src_ext[:, :3, :4]
         ref_proj[:, :3, :4] = cam_intr @ ref_ext[:, :3, :4]
-        warped = homo_warp(feats[v], src_proj, ref_proj, depth_values, sampler)
+        warped = homo_warp(feats[v], src_proj, ref_proj, depth_values, sampler, None if homo is None else homo[v // 2])
         x = _cb3(torch.cat([ref_volume, warped], 1), sd, "pre0")
         if taps is not None:
             taps.setdefault("x0", []).append(x)
@@ -372,13 +385,17 @@ def depth_planes(cfg):
     return torch.arange(0, cfg["ndepths"]).to(torch.float32) * interval + cfg["depth_min"], interval
 
 
-def forward(sd, cfg, imgs, cam_poses, cam_intr, pre_costs=None, pre_cam_poses=None, sampler="aten", taps=None):
+def forward(sd, cfg, imgs, cam_poses, cam_intr, pre_costs=None, pre_cam_poses=None, sampler="aten", taps=None, geometry=None):
     """``DepthNetHybrid.forward(..., mode='val')`` (model_hybrid.py:110-184 + hybrid_depth_decoder.py:138-432).
 
     cfg = dict(ndepths, depth_min, depth_max, resnet, est=True).  imgs [1,V,3,H,W] in 0..255,
     cam_poses [1,V,4,4] cam->world, cam_intr [1,3,3].  Returns (outputs, state, poses) exactly like the
     reference: state = {"keys": [k], "values": [v]}, poses = [pose] with the stale-pose quirk Q4.
     ``taps`` (optional dict) receives intermediate tensors for seam-level tests.
+    ``geometry`` (test hook, optional): {"homo": [2T, 12], "warp": list over targets of [n_sources, 30]} -- the camera
+    matrices of the two warps computed elsewhere (layout of estdepth_b200.ops.homography_table_torch /
+    volume_warp_tables_torch), used instead of this function's own ``torch.inverse`` products; everything downstream
+    of the matrices is unchanged.  Lets a test hand the CPU oracle the matrices a GPU's LU produced.
     """
     assert imgs.shape[0] == 1, "the reference (and this oracle) run at B=1 (quirk Q16)"
     imgs = 2 * (imgs / 255.) - 1.
@@ -393,7 +410,8 @@ def forward(sd, cfg, imgs, cam_poses, cam_intr, pre_costs=None, pre_cam_poses=No
     K4 = cam_intr.clone()
     K4[:, :2, :] *= 0.25                                                      # scale_cam_intr :104-108
     depth_values, interval = depth_planes(cfg)
-    cvs = [cost_volume(sd, feats[t:t + 3], cam_poses[:, t:t + 3], K4, depth_values, sampler, taps) for t in range(T)]
+    cvs = [cost_volume(sd, feats[t:t + 3], cam_poses[:, t:t + 3], K4, depth_values, sampler, taps,
+                       None if geometry is None else geometry["homo"][2 * t:2 * t + 2]) for t in range(T)]
     poses = [cam_poses[:, t + 1] for t in range(T)]
     if taps is not None:
         taps["features"] = feats
@@ -425,8 +443,9 @@ def forward(sd, cfg, imgs, cam_poses, cam_intr, pre_costs=None, pre_cam_poses=No
                 if j == i:
                     continue
                 rel = poses[j] @ torch.inverse(poses[i])                         # quirk Q7 (:235)
-                wk.append(warp_volume(keys[j], rel, K4, depth_values, cfg["depth_min"], interval, sampler))
-                wv.append(warp_volume(values[j], rel, K4, depth_values, cfg["depth_min"], interval, sampler))
+                tab = None if geometry is None else geometry["warp"][i][len(wk)]
+                wk.append(warp_volume(keys[j], rel, K4, depth_values, cfg["depth_min"], interval, sampler, tab))
+                wv.append(warp_volume(values[j], rel, K4, depth_values, cfg["depth_min"], interval, sampler, tab))
             fused = est_fuse(sd, keys[i], wk, values[i], wv)
             if taps is not None:
                 taps.setdefault("h", []).append(est_attention(keys[i], wk, wv))

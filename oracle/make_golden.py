@@ -10,11 +10,18 @@ outputs: its own ``DepthNetHybrid.forward(..., mode='val')``, ``homo_warping``, 
 and seeded synthetic weights (``estdepth_b200.synth``).  Inputs and weights are NOT stored -- tests
 regenerate them from the same seeds -- only the reference's outputs are.
 
+    python -m oracle.make_golden --fullsize     # the benchmark-size fixtures below (about 10 min of CPU)
+
 Fixtures:
   joint_r18_d32_128x160.npz   cfg1: 5-frame Joint windows 1 (no EST, quirk Q3) and 2 (EST, pre_num=1)
   joint_r50_d64_128x128.npz   same protocol, ResNet-50 / D=64 (the architecture of cfg2, small image)
   estm_r18_d32_128x160.npz    ESTM protocol: 5 sliding 3-frame calls, memory_size=2 (quirks Q4, Q5)
   ops_small.npz               op-level outputs on small tensors
+Benchmark-size fixtures (``--fullsize``; outputs stored SUB-SAMPLED, see ``subsample``):
+  joint_r50_d64_480x640_g3.npz    BASELINE cfg2: both Joint windows at 5 x 480 x 640, D=64, ResNet-50, head gain 3 (synth default)
+  joint_r50_d64_480x640_g10.npz   the same with the logit heads scaled by 10 (logit sigma ~ 3)
+  estm_r50_d64_480x640.npz        BASELINE cfg3 (first 4 steps): ESTM protocol, 3-frame windows, memory 2, 480 x 640
+  joint_r50_d128_640x960.npz      BASELINE cfg5: both Joint windows at 5 x 640 x 960, D=128
 """
 import os
 import sys
@@ -88,6 +95,80 @@ def estm_fixture(ref, resnet, ndepths, height, width, name, frames=7, memory=2):
     return out
 
 
+FULL_STRIDE = 4          # benchmark-size fixtures keep every 4th row / column of a map ...
+FULL_STATE_STRIDE = 16   # ... and every 16th of the hidden-state volumes
+
+
+def subsample(key, arr, stride=FULL_STRIDE):
+    """Which pixels of an output map a benchmark-size fixture keeps (shared by the generator and tests/test_gpu_fullsize_golden.py).
+
+    Works on torch tensors and numpy arrays [..., H, W].  ("depth", t, 3|2) and the probability maps are nearest x4
+    replications of quarter-resolution maps (hybrid_depth_decoder.py:202-209, 259-260): offset (0, 0) with stride 4 keeps
+    every quarter-resolution pixel once, i.e. those maps are stored WITHOUT loss.  ("depth", t, 1) is a x2 replication of a
+    half-resolution map: offset (2, 0) alternates between its even and odd rows' sources.  ("depth", t, 0) is a genuine
+    full-resolution map: offset (1, 2)."""
+    oy, ox = {1: (2, 0), 0: (1, 2)}.get(key[2], (0, 0)) if key[0] == "depth" else (0, 0)
+    return arr[..., oy::stride, ox::stride]
+
+
+def fullsize_joint_fixture(ref, resnet, ndepths, height, width, name, head_gain=synth.HEAD_GAIN, stride=FULL_STRIDE):
+    m = ref.model_hybrid.DepthNetHybrid(ndepths=ndepths, depth_min=0.1, depth_max=10.0, resnet=resnet, IF_EST_transformer=True)
+    m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=0, head_gain=head_gain))
+    m.eval()
+    out = {"meta": np.array([height, width, ndepths, resnet, stride, FULL_STATE_STRIDE, head_gain], dtype=np.float64)}
+    state, poses_state = None, None
+    with torch.no_grad():
+        for w, start in enumerate((0, 3)):
+            imgs, poses, K, sample = synth.synth_inputs(5, height, width, seed=0, start=start)
+            outputs, state, poses_state = m(imgs, poses, K, sample, state, poses_state, mode="val")
+            for key, val in outputs.items():
+                out["w%d/%s" % (w, "_".join(str(k) for k in key))] = _np(subsample(key, val, stride)).copy()
+            out["w%d/state_key" % w] = _np(state["keys"][0][..., ::FULL_STATE_STRIDE, ::FULL_STATE_STRIDE]).copy()
+            out["w%d/state_value" % w] = _np(state["values"][0][..., ::FULL_STATE_STRIDE, ::FULL_STATE_STRIDE]).copy()
+            out["w%d/state_pose" % w] = _np(poses_state[0])
+            print(name, "window", w, "done", flush=True)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name), **out)
+
+
+def fullsize_estm_fixture(ref, resnet, ndepths, height, width, name, steps=4, memory=2, stride=FULL_STRIDE):
+    """First ``steps`` calls of BASELINE cfg3 (eval_hybrid_seq.py:169-193: 3-frame windows, memory_size 2)."""
+    m = build_reference_model(ref, resnet, ndepths)
+    out = {"meta": np.array([height, width, ndepths, resnet, stride, FULL_STATE_STRIDE, synth.HEAD_GAIN], dtype=np.float64)}
+    mem_costs, mem_poses = [], []
+    with torch.no_grad():
+        for step in range(steps):
+            imgs, poses, K, sample = synth.synth_inputs(3, height, width, seed=0, start=step)
+            if mem_poses:
+                pre_costs = {"keys": [c["keys"][0] for c in mem_costs], "values": [c["values"][0] for c in mem_costs]}
+                pre_poses = [p[0] for p in mem_poses]
+            else:
+                pre_costs, pre_poses = None, None
+            outputs, costs, cposes = m(imgs, poses, K, sample, pre_costs, pre_poses, mode="val")
+            mem_costs.append(costs)
+            mem_poses.append(cposes)
+            if len(mem_costs) > memory:
+                mem_costs.pop(0)
+                mem_poses.pop(0)
+            for key, val in outputs.items():
+                out["s%d/%s" % (step, "_".join(str(k) for k in key))] = _np(subsample(key, val, stride)).copy()
+            out["s%d/state_value" % step] = _np(costs["values"][0][..., ::FULL_STATE_STRIDE, ::FULL_STATE_STRIDE]).copy()
+            out["s%d/state_pose" % step] = _np(cposes[0])
+            print(name, "step", step, "done", flush=True)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name), **out)
+
+
+def fullsize_main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref = load_reference()
+    fullsize_joint_fixture(ref, 50, 64, 480, 640, "joint_r50_d64_480x640_g3.npz")
+    fullsize_joint_fixture(ref, 50, 64, 480, 640, "joint_r50_d64_480x640_g10.npz", head_gain=10.0)
+    fullsize_estm_fixture(ref, 50, 64, 480, 640, "estm_r50_d64_480x640.npz")
+    fullsize_joint_fixture(ref, 50, 128, 640, 960, "joint_r50_d128_640x960.npz", stride=8)
+    for f in sorted(os.listdir(GOLDEN_DIR)):
+        print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)) // 1024, "KiB")
+
+
 def ops_inputs(seed=0):
     """Seeded small inputs shared by make_golden and the tests (pure function)."""
     g = torch.Generator().manual_seed(1234 + seed)
@@ -153,4 +234,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--fullsize" in sys.argv:
+        fullsize_main()
+    else:
+        main()

@@ -106,3 +106,27 @@ def test_attention_is_mean_not_sum():
     for n in (1, 2, 3):
         h = orc.est_attention(x["key_t"], [x["wkeys"][0]] * n, [v] * n)
         assert torch.allclose(h, v / n, atol=1e-6)
+
+
+def test_benchmark_size_first_window_cfg2():
+    """The oracle against the reference's outputs AT THE BENCHMARKED SIZE (5 x 480 x 640, D=64, ResNet-50; fixture made by
+    ``python -m oracle.make_golden --fullsize``): window 1 (the no-EST path, quirk Q3), about 15 s of CPU.  The second window and
+    the other benchmark-size fixtures (cfg3, cfg5, head gain 10) are checked against the CUDA path in tests/test_gpu_fullsize_golden.py."""
+    from oracle.make_golden import FULL_STATE_STRIDE, subsample
+    gold = np.load(os.path.join(GOLDEN, "joint_r50_d64_480x640_g3.npz"))
+    stride = int(gold["meta"][4])
+    sd, cfg = _sd(50, 64), cfg_of(50, 64)
+    imgs, poses, K, _ = synth.synth_inputs(5, 480, 640, seed=0, start=0)
+    with torch.no_grad():
+        outputs, state, pstate = orc.forward(sd, cfg, imgs, poses, K)
+    n = 0
+    for key, val in outputs.items():
+        name_ = "w0/%s" % "_".join(str(k) for k in key)
+        if name_ not in gold:
+            continue
+        assert np.abs(subsample(key, val, stride).numpy() - gold[name_]).max() < TOL, name_
+        n += 1
+    assert n == 18
+    s = FULL_STATE_STRIDE
+    assert np.abs(state["values"][0][..., ::s, ::s].numpy() - gold["w0/state_value"]).max() < TOL
+    assert np.array_equal(pstate[0].numpy(), gold["w0/state_pose"])

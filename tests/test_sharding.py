@@ -28,11 +28,16 @@ def test_partition_is_contiguous_balanced_and_complete():
 class ToyModel(object):
     """prepare: per-step feature; fuse: mixes in the memory exactly like the real protocol (order-sensitive)."""
     shape = (1, 16, 2, 3, 4)
+    in_flight = 0
+    max_in_flight = 0
 
     def prepare(self, imgs, poses, K):
+        ToyModel.in_flight += 1
+        ToyModel.max_in_flight = max(ToyModel.max_in_flight, ToyModel.in_flight)
         return {"x": imgs.sum() * torch.ones(self.shape), "pose": poses[:, 1]}
 
     def fuse(self, prep, pre_costs, pre_poses):
+        ToyModel.in_flight -= 1
         v = prep["x"].clone()
         if pre_costs is not None:
             for i, (k, p) in enumerate(zip(pre_costs["values"], pre_poses)):
@@ -55,14 +60,15 @@ def _sequential(n_frames):
         if len(mem) > 2:
             mem.pop(0)
         out.append(o[("depth", 0, 2)])
-    return torch.cat(out)
+    return torch.cat(out) if out else torch.zeros(0)
 
 
-def _worker(rank, world, port, n_frames, q):
+def _worker(rank, world, port, n_frames, q, max_ahead=4):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    pipe = sharding.EstmClipPipeline(ToyModel(), window=3, memory_size=2)
+    pipe = sharding.EstmClipPipeline(ToyModel(), window=3, memory_size=2, max_ahead=max_ahead)
     (start, stop), results = pipe.run(n_frames, _frames, ToyModel.shape, torch.device("cpu"))
+    assert ToyModel.max_in_flight <= max_ahead, (ToyModel.max_in_flight, max_ahead)      # bounded look-ahead
     local = torch.cat([r[("depth", 0, 2)] for r in results]).reshape(-1, 1) if results else torch.zeros(0, 1)
     gathered = sharding.gather_maps(local)
     if rank == 0:
@@ -71,14 +77,17 @@ def _worker(rank, world, port, n_frames, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_frames", [9, 4])
-def test_clip_pipeline_world2_equals_sequential(n_frames):
+@pytest.mark.parametrize("n_frames,max_ahead", [(9, 4), (9, 1), (4, 4), (3, 4), (2, 4)])
+def test_clip_pipeline_world2_equals_sequential(n_frames, max_ahead):
+    """9 frames: 7 steps cut 4 + 3 (two states travel); 4 frames: 1 + 1 (one state travels); 3 frames: rank 1 owns nothing and
+    nothing travels; 2 frames: no step at all -- neither rank may wait for the other.  max_ahead = 1: prepare and fuse
+    strictly alternate (bounded look-ahead)."""
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_frames, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_frames, q, max_ahead)) for r in range(2)]
     for p in procs:
         p.start()
     got = q.get(timeout=120)
@@ -96,6 +105,9 @@ def _dp_worker(rank, world, port, n_seq, q):
     start, stop = sharding.partition(n_seq, world, rank)
     local = torch.stack([_frames(s)[0].sum(dim=(0, 1, 2)) for s in range(start, stop)]) if stop > start else torch.zeros(0, 4, 4)
     gathered = sharding.gather_maps(local)
+    counts = [b - a for a, b in (sharding.partition(n_seq, world, r) for r in range(world))]
+    known = sharding.gather_maps(local, counts=counts)               # sizes known from the partition: one collective, no host read
+    assert all(torch.equal(a, b) for a, b in zip(gathered, known))
     if rank == 0:
         q.put(torch.cat(gathered).tolist())
     dist.barrier()
