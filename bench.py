@@ -689,7 +689,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default=None, choices=["fp32", "3xtf32", "3xf16", "3xf16r", "3xf16r2"], help="conv3d arithmetic (default: the model's)")
-    ap.add_argument("--geometry", default=None, choices=["torch", "fp64"], help="camera-matrix derivation (default: the model's)")
+    ap.add_argument("--geometry", default=None, choices=["auto", "torch", "fp64"], help="camera-matrix derivation (default: the model's)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~1 min oracle timing on the host cores")
     ap.add_argument("--no-extras", action="store_true", help="skip the extras (cfg3 / cfg4 / cfg5 / PyTorch-CUDA baseline / clip pipeline)")
     ap.add_argument("--no-torch-cuda-baseline", action="store_true")

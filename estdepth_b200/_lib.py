@@ -38,8 +38,10 @@ SIGNATURES = {
     "estd_last_error": (ctypes.c_char_p, []),
     "estd_launch_count": (ctypes.c_ulonglong, []),
     "estd_homography_setup": (_I, [_P, _P, _P, _P, _P]),
+    "estd_homography_table": (_I, [_P, _I, _P, ctypes.POINTER(ctypes.c_int), _I, _P, _P]),
     "estd_homography_from_proj": (_I, [_P, _P, _P, _P]),
     "estd_volume_warp_setup": (_I, [_P, _P, _P, _P, _P]),
+    "estd_volume_warp_table": (_I, [ctypes.POINTER(_P), _I, _P, ctypes.POINTER(ctypes.c_int), _I, _P, _P]),
     "estd_premix": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "estd_premix_batch": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "estd_warp_cost": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

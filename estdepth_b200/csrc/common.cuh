@@ -38,6 +38,19 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 __device__ __forceinline__ float sigmoidf_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
 
+// ---- truncation-bias compensation of the tensor-core convolutions ----
+// tcgen05.mma adds its 16-product sum into the fp32 accumulator with TRUNCATION, not round-to-nearest: every accumulating MMA
+// shrinks the accumulator by a fixed relative amount on average.  Measured on B200 against fp64 (profiles/trunc_probe.py): the
+// signed error of a layer is a clean multiplicative bias, slope = -(0.272 n + ~1) * 2^-24 for n accumulating MMAs with a
+// non-zero addend -- the same constant for the 3x3x3 ring schedule (n = 162), the output-stationary kernel (54) and the
+// planar kernel (36 ... 720), for signed and for non-negative inputs.  A systematic shrink of every layer compounds linearly
+// through the ~25 3-D and ~45 2-D layers of the net (the random part only grows like a square root), so the epilogues undo
+// it: the accumulator that received n such MMAs is multiplied by 1 + n * kTruncBiasPerMma.  n is counted per output
+// element: taps that fall outside the tensor are zero-filled by TMA, add exactly zero and do not truncate anything.
+constexpr float kTruncBiasPerMma = 0.272f * 5.9604644775390625e-08f;        // 0.272 * 2^-24
+// how many of the 3 taps (offsets -dil, 0, +dil) around index x lie inside [0, n)
+__device__ __forceinline__ int taps_inside(int x, int n, int dil) { return 3 - (x < dil ? 1 : 0) - (x >= n - dil ? 1 : 0); }
+
 // ATen grid_sampler_unnormalize (GridSampler.h): align_corners=False -> ((c+1)*size-1)/2, True -> (c+1)/2*(size-1)
 __device__ __forceinline__ float unnormalize(float c, int size, int align_corners) {
     return align_corners ? (c + 1.0f) * 0.5f * (float)(size - 1) : ((c + 1.0f) * (float)size - 1.0f) * 0.5f;

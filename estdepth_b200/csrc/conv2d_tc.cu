@@ -232,6 +232,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             };
             load_res(0);
             const float mult = s_scale[cbase];                     // uniform within a slice: the per-channel multiplier is folded into the weights
+            // truncation-bias compensation (common.cuh): the large-product accumulator received one MMA per k-step for every
+            // filter tap inside the map (the small products accumulate apart and need none)
+            const float comp = kTruncBiasPerMma * (float)(nks * (S::TAPS == 9 ? taps_inside(h, p.H, S::DIL) * taps_inside(w, p.W, S::DIL) : 1));
             if (e == 0) mbar_wait_polls(&acc_full[buf], (uint32_t)(use & 1));
             named_barrier(3, EPI_THREADS);
             tc_fence_after();
@@ -253,8 +256,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                     if (!ok || ch >= ep.out_chunks) continue;
                     const int act = (c < ep.act_split) ? ep.act_lo : ep.act_hi;
                     float v[4];
-                    v[0] = fmaf(a[4 * j + 0] + b[4 * j + 0], mult, sh[j].x); v[1] = fmaf(a[4 * j + 1] + b[4 * j + 1], mult, sh[j].y);
-                    v[2] = fmaf(a[4 * j + 2] + b[4 * j + 2], mult, sh[j].z); v[3] = fmaf(a[4 * j + 3] + b[4 * j + 3], mult, sh[j].w);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = fmaf(a[4 * j + i], comp, a[4 * j + i]) + b[4 * j + i];
+                    v[0] = fmaf(v[0], mult, sh[j].x); v[1] = fmaf(v[1], mult, sh[j].y);
+                    v[2] = fmaf(v[2], mult, sh[j].z); v[3] = fmaf(v[3], mult, sh[j].w);
                     if (act == ESTD_ACT_RELU) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.0f);

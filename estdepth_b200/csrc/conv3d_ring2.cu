@@ -306,11 +306,14 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
                     const int w = w0 + 8 * mt + mw;
                     const bool ok = (h < p.H) && (w < p.W);
                     const size_t pos = ((size_t)z * p.H + h) * p.W + w;
+                    // truncation-bias compensation (common.cuh): this voxel's slot received 3 products x NKS k-steps for every
+                    // filter tap that lies inside the volume
+                    const float mult_v = mult * (1.0f + kTruncBiasPerMma * (float)(3 * NKS * taps_inside(z, p.D, 1) * taps_inside(h, p.H, 1) * taps_inside(w, p.W, 1)));
                     const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N3 + slot * COUT);
                     if (e == 0) mbar_wait_polls(&acc_full[half], (uint32_t)(n_seen & 1));
                     named_barrier(3, 128 * S::MH);
                     tc_fence_after();
-                    ring_drain_slot<COUT>(ep, s_shift, mult, t0, ok, pos, vox, want_gn, gs, gq, [&]() {
+                    ring_drain_slot<COUT>(ep, s_shift, mult_v, t0, ok, pos, vox, want_gn, gs, gq, [&]() {
                         named_barrier(5, 128 * S::MH);                                   // this CTA's slot is drained and zeroed ...
                         if (e == 0 && lane == 0) mbar_arrive_remote(&acc_empty[half], 0);   // ... one arrival per CTA on the issuer's barrier
                     });

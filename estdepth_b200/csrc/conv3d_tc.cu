@@ -267,6 +267,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                 const int w = w0 + 8 * mt + mw;
                 const bool ok = (h < p.H) && (w < p.W);
                 const size_t pos = ((size_t)d * p.H + h) * p.W + w;
+                // truncation-bias compensation (common.cuh): the large-product accumulator(s) received one MMA per k-step for
+                // every filter tap inside the volume, shared between ASETS accumulator sets
+                const float comp = kTruncBiasPerMma * (float)(NKS * (S::PLANAR ? 1 : taps_inside(d, p.D, 1)) * taps_inside(h, p.H, S::DIL) * taps_inside(w, p.W, S::DIL)) / (float)S::ASETS;
 #pragma unroll 1
                 for (int c0 = 0; c0 < COUT; c0 += 16) {
                     float a[16], b[16];
@@ -282,7 +285,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                         for (int i = 0; i < 16; ++i) { a[i] += a2[i]; b[i] += b2[i]; }
                     }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) a[i] += b[i];
+                    for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], comp, a[i]) + b[i];
                     float ts[2] = {0.f, 0.f}, tq[2] = {0.f, 0.f};
                     conv_epilogue_store16(p.ep, a, c0, ok, pos, vox, ts, tq);
                     gs[0] += (double)ts[0]; gq[0] += (double)tq[0];

@@ -46,9 +46,8 @@ __device__ void projection(const double* K, const double* E, double* P) {
     for (int j = 0; j < 4; ++j) P[12 + j] = E[12 + j];
 }
 
-__global__ void homography_setup_kernel(const float* __restrict__ ref_pose, const float* __restrict__ src_pose,
-                                        const float* __restrict__ cam_intr, float* __restrict__ out12) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void homography_pair(const float* __restrict__ ref_pose, const float* __restrict__ src_pose,
+                                const float* __restrict__ cam_intr, float* __restrict__ out12) {
     double Pr[16], Ps[16], K[9], Er[16], Es[16], R[16], S[16], Rinv[16], M[16];
     for (int i = 0; i < 16; ++i) { Pr[i] = ref_pose[i]; Ps[i] = src_pose[i]; }
     for (int i = 0; i < 9; ++i) K[i] = cam_intr[i];
@@ -64,6 +63,20 @@ __global__ void homography_setup_kernel(const float* __restrict__ ref_pose, cons
     }
 }
 
+__global__ void homography_setup_kernel(const float* __restrict__ ref_pose, const float* __restrict__ src_pose,
+                                        const float* __restrict__ cam_intr, float* __restrict__ out12) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    homography_pair(ref_pose, src_pose, cam_intr, out12);
+}
+
+// every (reference view, source view) pair of a window in ONE launch: thread i -> row i of the [n][12] table
+struct HomographyBatch { int n; int ref[ESTD_MAX_GEOMETRY_PAIRS]; int src[ESTD_MAX_GEOMETRY_PAIRS]; };
+__global__ void homography_table_kernel(const float* __restrict__ poses, const float* __restrict__ cam_intr,
+                                        const HomographyBatch b, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b.n) homography_pair(poses + 16 * b.ref[i], poses + 16 * b.src[i], cam_intr, out + 12 * i);
+}
+
 __global__ void homography_from_proj_kernel(const float* __restrict__ src_proj, const float* __restrict__ ref_proj,
                                             float* __restrict__ out12) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -77,9 +90,8 @@ __global__ void homography_from_proj_kernel(const float* __restrict__ src_proj, 
     }
 }
 
-__global__ void volume_warp_setup_kernel(const float* __restrict__ pose_i, const float* __restrict__ pose_j,
-                                         const float* __restrict__ cam_intr, float* __restrict__ out30) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void volume_warp_pair(const float* __restrict__ pose_i, const float* __restrict__ pose_j,
+                                 const float* __restrict__ cam_intr, float* __restrict__ out30) {
     double Pi[16], Pj[16], K[9], Kinv[9], Piinv[16], rel[16], Minv[16];
     for (int i = 0; i < 16; ++i) { Pi[i] = pose_i[i]; Pj[i] = pose_j[i]; }
     for (int i = 0; i < 9; ++i) K[i] = cam_intr[i];
@@ -92,7 +104,51 @@ __global__ void volume_warp_setup_kernel(const float* __restrict__ pose_i, const
     for (int i = 0; i < 9; ++i) out30[21 + i] = (float)K[i];
 }
 
+__global__ void volume_warp_setup_kernel(const float* __restrict__ pose_i, const float* __restrict__ pose_j,
+                                         const float* __restrict__ cam_intr, float* __restrict__ out30) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    volume_warp_pair(pose_i, pose_j, cam_intr, out30);
+}
+
+// every (target, source) pair of an EST fusion step in ONE launch; the poses live in separate tensors (the window's targets,
+// the memory's poses), so their addresses travel by value
+struct VolumeWarpBatch { int n; const float* pose[ESTD_MAX_GEOMETRY_POSES]; int target[ESTD_MAX_GEOMETRY_PAIRS]; int source[ESTD_MAX_GEOMETRY_PAIRS]; };
+__global__ void volume_warp_table_kernel(const float* __restrict__ cam_intr, const VolumeWarpBatch b, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b.n) volume_warp_pair(b.pose[b.target[i]], b.pose[b.source[i]], cam_intr, out + 30 * i);
+}
+
 }  // namespace estd
+
+extern "C" int estd_homography_table(const float* poses, int n_views, const float* cam_intr, const int* pairs, int n_pairs,
+                                     float* out, void* stream) {
+    ESTD_REQUIRE(poses && cam_intr && pairs && out, "estd_homography_table: null pointer");
+    ESTD_REQUIRE(n_pairs >= 1 && n_pairs <= ESTD_MAX_GEOMETRY_PAIRS, "estd_homography_table: 1..%d pairs, got %d", ESTD_MAX_GEOMETRY_PAIRS, n_pairs);
+    estd::HomographyBatch b;
+    b.n = n_pairs;
+    for (int i = 0; i < n_pairs; ++i) {
+        b.ref[i] = pairs[2 * i]; b.src[i] = pairs[2 * i + 1];
+        ESTD_REQUIRE(b.ref[i] >= 0 && b.ref[i] < n_views && b.src[i] >= 0 && b.src[i] < n_views, "estd_homography_table: view index out of range");
+    }
+    estd::homography_table_kernel<<<1, ESTD_MAX_GEOMETRY_PAIRS, 0, (cudaStream_t)stream>>>(poses, cam_intr, b, out);
+    return estd::check_launch("estd_homography_table");
+}
+
+extern "C" int estd_volume_warp_table(const float* const* pose_ptrs, int n_poses, const float* cam_intr, const int* pairs,
+                                      int n_pairs, float* out, void* stream) {
+    ESTD_REQUIRE(pose_ptrs && cam_intr && pairs && out, "estd_volume_warp_table: null pointer");
+    ESTD_REQUIRE(n_poses >= 1 && n_poses <= ESTD_MAX_GEOMETRY_POSES, "estd_volume_warp_table: 1..%d poses, got %d", ESTD_MAX_GEOMETRY_POSES, n_poses);
+    ESTD_REQUIRE(n_pairs >= 1 && n_pairs <= ESTD_MAX_GEOMETRY_PAIRS, "estd_volume_warp_table: 1..%d pairs, got %d", ESTD_MAX_GEOMETRY_PAIRS, n_pairs);
+    estd::VolumeWarpBatch b;
+    b.n = n_pairs;
+    for (int i = 0; i < n_poses; ++i) { ESTD_REQUIRE(pose_ptrs[i], "estd_volume_warp_table: null pose"); b.pose[i] = pose_ptrs[i]; }
+    for (int i = 0; i < n_pairs; ++i) {
+        b.target[i] = pairs[2 * i]; b.source[i] = pairs[2 * i + 1];
+        ESTD_REQUIRE(b.target[i] >= 0 && b.target[i] < n_poses && b.source[i] >= 0 && b.source[i] < n_poses, "estd_volume_warp_table: pose index out of range");
+    }
+    estd::volume_warp_table_kernel<<<1, ESTD_MAX_GEOMETRY_PAIRS, 0, (cudaStream_t)stream>>>(cam_intr, b, out);
+    return estd::check_launch("estd_volume_warp_table");
+}
 
 extern "C" int estd_homography_setup(const float* ref_pose, const float* src_pose, const float* cam_intr,
                                      float* out12, void* stream) {

@@ -390,7 +390,7 @@ class ContextEncoder(nn.Module):
             return _folded(y, blk.conv3, blk.bn3, relu=True, residual=identity)
         return _folded(y, blk.conv2, blk.bn2, relu=True, residual=identity)
 
-    def _stage_tc(self, stage, x):
+    def _stage_tc(self, stage, x4):
         """One ResNet stage (Bottlenecks: ResNet-50/101/152, BasicBlocks: ResNet-18/34) on the planar tcgen05 kernel;
         activations stay in vol4 from the max-pool to the decoder (no NCHW copies between stages).  The stride-2 3x3 of a
         stage's first block runs at stride 1 and keeps the even rows / columns; its stride-2 1x1 shortcut runs on the

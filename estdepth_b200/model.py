@@ -113,18 +113,23 @@ class _Workspace(object):
 
 class DepthNetHybrid(nn.Module):
     def __init__(self, ndepths=64, depth_min=0.01, depth_max=10.0, resnet=50, IF_EST_transformer=True,
-                 align_corners=False, fix_stale_pose=False, precision="3xf16r2", feature_precision="3xf16", geometry="torch",
+                 align_corners=False, fix_stale_pose=False, precision="3xf16r2", feature_precision="3xf16", geometry="auto",
                  merged_pre2=True):
         """First five arguments: hybrid_models/model_hybrid.py:15-16.  Extra, keyword-only in practice:
 
         align_corners   grid_sample semantics of the warps: False = torch >= 1.3 (what the reference computes when run
                         today, and what the oracle pins); True = the torch 1.2 it was written for (quirk Q1).
         fix_stale_pose  opt-in fix of quirk Q4 (return the current target's pose with the hidden state).
-        geometry        how the camera matrices of the two warps are derived: "torch" (default) = with the reference's own fp32
-                        torch.inverse / matmul sequence on the GPU (a few dozen tiny launches per window, no host sync), so
-                        that the kernels' sampling coordinates equal the reference's bit for bit; "fp64" = one fp64 kernel
-                        per pair (estd_homography_setup / estd_volume_warp_setup): more accurate matrices, but a coordinate
-                        within an ulp of the sampling range may then fall on the other side of quirk Q10's cut.
+        geometry        how the camera matrices of the two warps are derived.  "auto" (default): camera parameters given as
+                        HOST tensors -> the reference's own fp32 torch.inverse / matmul sequence on the host (bit-identical
+                        to the reference run on the CPU; the small tables are uploaded); given as CUDA tensors (what the
+                        eval drivers pass) -> two launches of the library's fp64 geometry kernels per window
+                        (estd_homography_table / estd_volume_warp_table), rounded once.  "torch": the reference's op
+                        sequence on whatever device the parameters live on (~90 tiny launches per window on the GPU: the
+                        reference's own GPU arithmetic).  "fp64": always the kernels.  Matrices from different LUs differ
+                        in the last bit; a sampling coordinate within an ulp of the sampling range may then fall on the
+                        other side of quirk Q10's cut (about one voxel in ten million) -- the reference shows the same
+                        difference between its own CPU and GPU runs.
         precision       arithmetic of the 3-D convolutions: "3xf16" / "3xtf32" = error-compensated two-term splits on the
                         tcgen05 tensor cores (fp32-class accuracy; "3xf16" moves half the operand bytes and needs
                         |activation| <= 65504, which is checked), "3xf16r" = the 3xf16 arithmetic on the plane-ring
@@ -142,8 +147,8 @@ class DepthNetHybrid(nn.Module):
         self.IF_EST_transformer = bool(IF_EST_transformer)
         self.align_corners = bool(align_corners)
         self.fix_stale_pose = bool(fix_stale_pose)
-        if geometry not in ("torch", "fp64"):
-            raise ValueError("geometry must be 'torch' or 'fp64'")
+        if geometry not in ("auto", "torch", "fp64"):
+            raise ValueError("geometry must be 'auto', 'torch' or 'fp64'")
         self.geometry = geometry
         # feature_precision: "3xf16" = the 3x3 convolutions of the matching-feature net on the tensor cores (fp32-class
         # accuracy), "fp32" = the whole 2-D net on cuDNN's strict-fp32 kernels
@@ -430,10 +435,10 @@ class DepthNetHybrid(nn.Module):
 
         # Camera parameters may live on the host: the 4x4 / 3x3 algebra is then done with the reference's torch ops ON THE HOST
         # -- bit-identical to the reference run on the CPU (how the parity fixtures were made) -- and only the small tables are
-        # uploaded.  With CUDA poses (what the eval drivers pass after tocuda) the same ops run on the GPU, i.e. the
-        # reference's own GPU arithmetic; its LU differs from LAPACK's in the last bit, which is enough to move a sampling
-        # coordinate across quirk Q10's cut for about one voxel in ten million.
-        host_geometry = self.geometry == "torch" and not cam_poses.is_cuda and not cam_intr.is_cuda
+        # uploaded.  With CUDA parameters (what the eval drivers pass after tocuda) the library's fp64 kernels derive every
+        # pair's matrices in one launch per warp kind ("auto"), or the reference's own op sequence runs on the GPU ("torch").
+        host_geometry = self.geometry in ("auto", "torch") and not cam_poses.is_cuda and not cam_intr.is_cuda
+        kernel_geometry = self.geometry == "fp64" or (self.geometry == "auto" and not host_geometry)
         K4_src = self.scale_cam_intr(cam_intr.to(torch.float32), 0.25).contiguous()
         poses_src = cam_poses.to(torch.float32).contiguous()
         K4, poses = _upload(K4_src, dev), _upload(poses_src, dev)
@@ -482,7 +487,13 @@ class DepthNetHybrid(nn.Module):
                 warp_tables = [[_upload(tab, dev) for tab in ops.volume_warp_tables_torch(
                     [poses_src[b, t + 1] for t in range(T)] + [p[b].to(torch.float32).contiguous() for p in memory_poses],
                     T, K4_src[b])] for b in range(B)]
-        elif self.geometry == "torch":
+        elif kernel_geometry:
+            homo_tables = [ops.homography_table(poses[b], K4[b], pairs) for b in range(B)]
+            if memory_poses is not None:
+                warp_tables = [ops.volume_warp_tables(
+                    [poses[b, t + 1] for t in range(T)] + [_upload(p[b].to(torch.float32), dev) for p in memory_poses],
+                    T, K4[b]) for b in range(B)]
+        else:
             side = self._side_stream(dev)
             side.wait_event(inputs_ready)
             with torch.cuda.stream(side):
@@ -519,7 +530,7 @@ class DepthNetHybrid(nn.Module):
                     cam_poses=cam_poses, K4=K4, semantic_vs=semantic_vs, skip_half=maps[0], depth3=depth3,
                     init_prob=init_prob, depth_values=depth_values, warp_tables=warp_tables,
                     warp_tables_memory=None if (memory_poses is None or warp_tables is None) else len(memory_poses),
-                    host_geometry=host_geometry, poses_host=poses_src if host_geometry else None,
+                    host_geometry=host_geometry, kernel_geometry=kernel_geometry, poses_host=poses_src if host_geometry else None,
                     K4_host=K4_src if host_geometry else None)
 
     def _fuse_tail(self, prep, pre_costs=None, pre_cam_poses=None):
@@ -545,12 +556,14 @@ class DepthNetHybrid(nn.Module):
                 values += [self._state_to_vol4(v, b) for v in pre_costs["values"]]
                 keys += [self._state_to_vol4(k, b) for k in pre_costs["keys"]]
             tables = None
-            if use_est and self.geometry == "torch":
+            if use_est:
                 if prep.get("warp_tables") is not None and prep.get("warp_tables_memory") == pre_num:
-                    tables = prep["warp_tables"][b]                  # derived on the side stream during prepare()
+                    tables = prep["warp_tables"][b]                  # derived during prepare()
                 elif prep.get("host_geometry") and all(not p.is_cuda for p in pre_cam_poses):
                     host_poses = [prep["poses_host"][b, t + 1] for t in range(T)] + [p[b].to(torch.float32).contiguous() for p in pre_cam_poses]
                     tables = [_upload(tab, dev) for tab in ops.volume_warp_tables_torch(host_poses, T, prep["K4_host"][b])]
+                elif prep.get("kernel_geometry"):
+                    tables = ops.volume_warp_tables(all_poses, T, K4[b])
                 else:
                     tables = ops.volume_warp_tables_torch(all_poses, T, K4[b])
             for i in range(T):

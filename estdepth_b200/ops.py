@@ -149,6 +149,33 @@ def volume_warp_setup(pose_i, pose_j, cam_intr, out=None):
     return out
 
 
+def homography_table(poses, K4, pairs, out=None):
+    """[rot | trans] of every (reference view, source view) pair in ONE launch (fp64 algebra, rounded once):
+    poses [V,4,4], K4 [3,3] device tensors, pairs = [(ref, src), ...] -> [len(pairs), 12]."""
+    n = len(pairs)
+    out = torch.empty(n, 12, device=poses.device, dtype=torch.float32) if out is None else out
+    flat = (ctypes.c_int * (2 * n))(*[int(i) for pr in pairs for i in pr])
+    t = _pb()
+    check(_lib.get().estd_homography_table(_ptr(poses), poses.shape[0], _ptr(K4), flat, n, _ptr(out), _stream()), "estd_homography_table")
+    _pe(t, "geometry_setup")
+    return out
+
+
+def volume_warp_tables(all_poses, n_targets, K4):
+    """[Kinv | Minv (3x4) | K] for every (target i < n_targets, source j != i) pair of ``all_poses`` (list of [4,4] device
+    tensors) in ONE launch -> list (per target) of [len(all_poses) - 1, 30], sources in list order."""
+    n = len(all_poses)
+    pairs = [(i, j) for i in range(n_targets) for j in range(n) if j != i]
+    m = len(pairs)
+    out = torch.empty(m, 30, device=K4.device, dtype=torch.float32)
+    ptrs = (ctypes.c_void_p * n)(*[_ptr(p).value for p in all_poses])
+    flat = (ctypes.c_int * (2 * m))(*[int(i) for pr in pairs for i in pr])
+    t = _pb()
+    check(_lib.get().estd_volume_warp_table(ptrs, n, _ptr(K4), flat, m, _ptr(out), _stream()), "estd_volume_warp_table")
+    _pe(t, "geometry_setup")
+    return [out[i * (n - 1):(i + 1) * (n - 1)] for i in range(n_targets)]
+
+
 _INV_MIN_BATCH = 8
 
 
@@ -242,12 +269,14 @@ def warp_cost(ref_mix, src_mix, homo12, depth_values, out=None, align_corners=Fa
 class PackedConv(object):
     """Folded, packed parameters of one 3x3x3 layer (see packing.pack_conv3d)."""
     __slots__ = ("weight", "scale", "shift", "cin_chunks", "cout_pad", "out_chunks", "act_split", "act_lo", "act_hi",
-                 "cin", "cout", "weight_tc", "cout_pad_tc", "weight_f16", "scale_f16", "weight_ring", "weight_ring2", "scale_ring", "_desc")
+                 "cin", "cout", "weight_tc", "cout_pad_tc", "weight_f16", "scale_f16", "weight_ring", "weight_ring2", "scale_ring", "_desc",
+                 "precision")
 
     def __init__(self, weight, scale, shift, cin_chunks, cout_pad, out_chunks, act_split, act_lo, act_hi,
                  cin=None, cout=None, weight_tc=None, cout_pad_tc=None):
         self.weight, self.scale, self.shift = weight, scale, shift
         self._desc = None                                              # per-(arithmetic, mode) descriptor templates (_conv_desc)
+        self.precision = None                                          # per-layer arithmetic override (None: the caller's choice)
         self.weight_tc, self.cout_pad_tc = weight_tc, cout_pad_tc      # tcgen05 packings (packing.attach_tc)
         self.weight_f16, self.scale_f16 = None, None
         self.weight_ring = None                                        # plane-ring packing (packing.pack_weight_ring)
@@ -398,7 +427,7 @@ def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, pr
 
 
 def conv3d_num_ctas(pc, D, H, W, precision=None):
-    precision = _precision(pc, precision)
+    precision = _precision(pc, pc.precision or precision)
     d = ConvDesc()
     d.precision = PRECISION[precision]
     d.in0_chunks, d.in1_chunks = pc.cin_chunks, 0
@@ -415,7 +444,7 @@ def conv3d(pc, in0, out0, in1=None, out1=None, res0=None, res1=None, post_scale=
 
     precision: "fp32" (exact, CUDA cores) | "3xtf32" | "3xf16" (tcgen05 tensor cores, error-compensated splits) |
     None = DEFAULT_PRECISION."""
-    precision = _precision(pc, precision)
+    precision = _precision(pc, pc.precision or precision)
     d = _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision)
     t = _pb()
     check(_lib.get().estd_conv3d(ctypes.byref(d), _stream()), "estd_conv3d")

@@ -66,6 +66,9 @@ ESTD_API const char* estd_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 ESTD_API unsigned long long estd_launch_count(void);
 
+#define ESTD_MAX_GEOMETRY_PAIRS 64
+#define ESTD_MAX_GEOMETRY_POSES 16
+
 /* ---- geometry set-up (device-side 3x3 / 4x4 algebra; replaces the ~60 torch.inverse/matmul calls per
  *      window: model_hybrid.py:74-88, homo_utils.py:469-471, :51, :258, hybrid_depth_decoder.py:235) ---- */
 
@@ -75,6 +78,12 @@ ESTD_API unsigned long long estd_launch_count(void);
 ESTD_API int estd_homography_setup(const float* ref_pose, const float* src_pose, const float* cam_intr,
                           float* out12, void* stream);
 
+/* The same for every (reference view, source view) pair of a window in ONE launch (model_hybrid.py:74-88 loops over the
+ * sources of every target).  poses: device [n_views][4][4]; pairs: HOST array [n_pairs][2] = (ref view, src view);
+ * out: device [n_pairs][12].  n_pairs <= ESTD_MAX_GEOMETRY_PAIRS. */
+ESTD_API int estd_homography_table(const float* poses, int n_views, const float* cam_intr, const int* pairs, int n_pairs,
+                          float* out, void* stream);
+
 /* Same, from the two 4x4 projection matrices the reference's homo_warping receives
  * (utils/homo_utils.py:458,469): M = src_proj * ref_proj^-1. */
 ESTD_API int estd_homography_from_proj(const float* src_proj, const float* ref_proj, float* out12, void* stream);
@@ -83,6 +92,13 @@ ESTD_API int estd_homography_from_proj(const float* src_proj, const float* ref_p
  * (hybrid_depth_decoder.py:235 + homo_utils.py:51,258; quirk Q7).  pose_i = target, pose_j = source. */
 ESTD_API int estd_volume_warp_setup(const float* pose_i, const float* pose_j, const float* cam_intr,
                            float* out30, void* stream);
+
+/* The same for every (target, source) pair of an EST fusion step in ONE launch (hybrid_depth_decoder.py:226-243 loops over
+ * the other volumes of every target).  pose_ptrs: HOST array of n_poses device pointers to [4][4] poses (the window's
+ * targets, then the memory's); pairs: HOST array [n_pairs][2] = (target pose index, source pose index); out: device
+ * [n_pairs][30].  n_poses <= ESTD_MAX_GEOMETRY_POSES, n_pairs <= ESTD_MAX_GEOMETRY_PAIRS. */
+ESTD_API int estd_volume_warp_table(const float* const* pose_ptrs, int n_poses, const float* cam_intr, const int* pairs,
+                           int n_pairs, float* out, void* stream);
 
 /* ---- K1: fused plane-sweep warp -> cost-volume input  (replaces homo_warping, utils/homo_utils.py:458-504,
  *      + ref_volume repeat / cat / pre0 conv+BN, hybrid_models/model_hybrid.py:76,90-94) ---- */

@@ -61,8 +61,12 @@ def test_k2_delta_filter_is_a_zero_filled_shift(precision):
     want[:, 1:, :-1] = x[:, :-1, 1:]
     if precision == "fp32":
         assert torch.equal(y, want)
-    else:                                          # two-term splits reproduce fp32 inputs to 2^-21 relative
-        assert (y - want).abs().max().item() <= 2.0 ** -20 * x.abs().max().item()
+    else:
+        # two-term splits reproduce fp32 inputs to 2^-21 relative.  The truncation-bias compensation (csrc/common.cuh) assumes
+        # that every MMA of the filter's footprint adds something; a one-tap filter adds zeros in all the others, so the output is
+        # over-corrected by at most n_mma * 0.272 * 2^-24 (n_mma = 162 on the ring schedules, 54 on the output-stationary one)
+        n_mma = 162 if precision.startswith("3xf16r") else 54
+        assert (y - want).abs().max().item() <= (2.0 ** -20 + n_mma * 0.272 * 2.0 ** -24) * x.abs().max().item()
 
 
 def test_k2_linearity_and_kernel_agreement():

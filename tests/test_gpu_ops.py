@@ -60,6 +60,34 @@ def test_layout_roundtrip():
     assert torch.equal(sv[0, ..., 0], s) and sv[0, ..., 1:].abs().max() == 0
 
 
+def test_batched_geometry_tables_equal_the_per_pair_kernels_and_the_reference_ops():
+    """estd_homography_table / estd_volume_warp_table (one launch per window / fusion step) == the per-pair kernels bit for
+    bit, and agree with the reference's fp32 torch op sequence (model_hybrid.py:74-88, homo_utils.py:469-471, :51, :258,
+    hybrid_depth_decoder.py:235) to fp32 round-off."""
+    poses = synth.camera_track(5).to(DEV)
+    K4 = synth.intrinsics(480, 640).clone()
+    K4[:2] *= 0.25
+    K4 = K4.to(DEV)
+    pairs = [(t + 1, s) for t in range(3) for s in (t, t + 2)]
+    table = ops.homography_table(poses, K4, pairs)
+    for i, (r, s) in enumerate(pairs):
+        assert torch.equal(table[i], ops.homography_setup(poses[r].contiguous(), poses[s].contiguous(), K4))
+    want = ops.homography_table_torch(poses.cpu(), K4.cpu(), pairs)
+    assert (table.cpu() - want).abs().max().item() < 2e-5 * want.abs().max().item()
+    memory = [synth.camera_track(1, start=7)[0].to(DEV), synth.camera_track(1, start=9)[0].to(DEV)]
+    all_poses = [poses[t + 1] for t in range(3)] + memory
+    tabs = ops.volume_warp_tables(all_poses, 3, K4)
+    ref = ops.volume_warp_tables_torch([p.cpu() for p in all_poses], 3, K4.cpu())
+    for i in range(3):
+        others = [j for j in range(5) if j != i]
+        assert tabs[i].shape == (4, 30)
+        for n, j in enumerate(others):
+            assert torch.equal(tabs[i][n], ops.volume_warp_setup(all_poses[i].contiguous(), all_poses[j].contiguous(), K4))
+        assert (tabs[i].cpu() - ref[i]).abs().max().item() < 2e-5 * ref[i].abs().max().item()
+    with pytest.raises(RuntimeError, match="out of range"):
+        ops.homography_table(poses, K4, [(1, 7)])
+
+
 def test_premix_matches_matmul():
     g = torch.Generator().manual_seed(2)
     fea = torch.randn(32, 30, 40, generator=g)
