@@ -461,7 +461,8 @@ def extras_multi_gpu(model, dev, args, rank, world):
     lo, hi = sharding.clip_steps(n_frames, 3, world, rank)
     for s in range(lo, hi):
         frames_cached(s)
-    pipe = sharding.EstmClipPipeline(model, window=3, memory_size=2)
+    # every local step may be prepared ahead of the predecessor's memory (9 x 157 MB of key / value volumes at N = 2)
+    pipe = sharding.EstmClipPipeline(model, window=3, memory_size=2, max_ahead=n_frames)
 
     def run_pipe():
         (a, b), results = pipe.run(n_frames, frames_cached, (1, 16, D, H // 4, W // 4), dev)

@@ -28,6 +28,8 @@ class ConvDesc(ctypes.Structure):
         ("out1", c_void_p), ("out1_chunks", ctypes.c_int),
         ("gn_partials", c_void_p),
         ("D", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int),
+        ("in0_split", ctypes.c_int), ("in1_split", ctypes.c_int), ("res_split", ctypes.c_int), ("out_split", ctypes.c_int),
+        ("head_w", c_void_p), ("head_b", c_void_p), ("head_out", c_void_p),
     ]
 
 

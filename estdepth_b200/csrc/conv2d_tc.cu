@@ -70,6 +70,7 @@ struct Params {
     int* status;
     ConvEpilogue ep;
     int in0_chunks, nks;
+    int in0_split, in1_split;                   // the input segments are pre-split (vol4s): the splitter warps pass them through
     int D, H, W;                                // D = number of maps in the stack
     int tiles_h, tiles_w, n_units;
 };
@@ -183,7 +184,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             if (warp == FIRST_SPLIT_WARP) mbar_wait_polls(&full[s], (uint32_t)((it / STAGES) & 1));
             named_barrier(2, SPLIT_THREADS);
             unsigned char* area = smem + (size_t)s * S::STAGE_BYTES;
-            for (int i = t; i < 2 * HALO_VOX; i += SPLIT_THREADS) {
+            const bool presplit = (4 * (it % nks) < p.in0_chunks) ? (p.in0_split != 0) : (p.in1_split != 0);
+            for (int i = t; !presplit && i < 2 * HALO_VOX; i += SPLIT_THREADS) {
                 const int pair = i / HALO_VOX, v = i - pair * HALO_VOX;
                 float4* c0 = reinterpret_cast<float4*>(area + (size_t)pair * 2 * S::KGROUP_BYTES) + v;
                 float4* c1 = c0 + HALO_VOX;
@@ -230,6 +232,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                     r0[j] = (ep.res0 && valid) ? ldg4(ep.res0 + ((size_t)ch * vox + pos) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
+            float amax = 0.0f;
             load_res(0);
             const float mult = s_scale[cbase];                     // uniform within a slice: the per-channel multiplier is folded into the weights
             // truncation-bias compensation (common.cuh): the large-product accumulator received one MMA per k-step for every
@@ -249,10 +252,19 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                 tmem_ld16(t0 + (uint32_t)c0, a);
                 tmem_ld16(t0 + (uint32_t)(COUT + c0), b);
                 tmem_ld_wait();
+                if (ep.res0 && ep.res_split) {                     // vol4s residual: chunks (0,1) = hi / lo of 8 channels, (2,3) of the next 8
+                    float t[16];
+                    join8(r0[0], r0[1], t); join8(r0[2], r0[3], t + 8);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) r0[j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
+                }
+                float o[16];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int c = cbase + c0 + 4 * j;
                     const int ch = c >> 2;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) o[4 * j + i] = 0.0f;
                     if (!ok || ch >= ep.out_chunks) continue;
                     const int act = (c < ep.act_split) ? ep.act_lo : ep.act_hi;
                     float v[4];
@@ -275,18 +287,31 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 #pragma unroll
                         for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.0f);
                     }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) o[4 * j + i] = v[i] * ep.post_scale;
+                    if (ep.out_split) continue;
                     const size_t off = ((size_t)ch * vox + pos) * 4;
                     float* dst = (ch < ep.out0_chunks) ? ep.out0 + off : ep.out1 + (off - (size_t)ep.out0_chunks * vox * 4);
-#ifndef ESTD_EXP_NOSTORE     // timing experiment only
-                    st4(dst, make_float4(v[0] * ep.post_scale, v[1] * ep.post_scale, v[2] * ep.post_scale, v[3] * ep.post_scale));
-#else
-                    if (v[0] == 1.2345e30f) st4(dst, make_float4(v[0] * ep.post_scale, v[1] * ep.post_scale, v[2] * ep.post_scale, v[3] * ep.post_scale));
-#endif
+                    st4(dst, make_float4(o[4 * j + 0], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+                }
+                if (ep.out_split) {
+                    // vol4s: x_hi of 8 channels -> chunk c/4, x_lo -> the next chunk
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const int ch = ((cbase + c0) >> 2) + 2 * g;
+                        if (!ok || ch >= ep.out_chunks) continue;
+                        uint4 hi, lo;
+                        split8(o + 8 * g, hi, lo, amax);
+                        float* dst = ep.out0 + ((size_t)ch * vox + pos) * 4;
+                        *reinterpret_cast<uint4*>(dst) = hi;
+                        *reinterpret_cast<uint4*>(dst + vox * 4) = lo;
+                    }
                 }
                 if (c0 + 16 < COUT) load_res(c0 + 16);
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);
+            if (ep.out_split && !(amax <= 65504.0f) && ep.status) atomicOr(ep.status, 1);
         }
     }
 
@@ -320,6 +345,7 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
     p.status = d->status;
     fill_epilogue(&p.ep, d);
     p.in0_chunks = d->in0_chunks;
+    p.in0_split = d->in0_split; p.in1_split = d->in1_split;
     p.nks = (cin_chunks + 3) / 4;
     p.D = d->D; p.H = d->H; p.W = d->W;
     p.tiles_h = tiles_h; p.tiles_w = tiles_w; p.n_units = (int)n_units;

@@ -283,13 +283,20 @@ static int dispatch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_o
     const int cin_chunks = d->in0_chunks + d->in1_chunks;
     ESTD_REQUIRE(d->D > 0 && d->H > 0 && d->W > 0, "estd_conv3d: bad volume %dx%dx%d", d->D, d->H, d->W);
     if (!count_only) {
-        ESTD_REQUIRE(d->in0 && (d->weight || d->weight_tc) && d->scale && d->shift && d->out0, "estd_conv3d: null pointer");
+        ESTD_REQUIRE(d->in0 && (d->weight || d->weight_tc) && d->scale && d->shift && (d->out0 || d->head_out), "estd_conv3d: null pointer");
+        const bool ring = !d->planar && (d->precision == ESTD_PREC_3XF16_RING2 || d->precision == ESTD_PREC_3XF16_RING);
+        ESTD_REQUIRE(!(d->in0_split || d->in1_split || d->res_split || d->out_split) || ring || d->planar,
+                     "estd_conv3d: pre-split (vol4s) tensors are implemented for the plane-ring and planar kernels only");
+        ESTD_REQUIRE(!d->out_split || (!d->out1 && (d->out0_chunks % 2) == 0 && d->out0), "estd_conv3d: a pre-split output is one tensor with an even number of chunks");
+        ESTD_REQUIRE((!d->in0_split || (d->in0_chunks % 2) == 0) && (!d->in1_split || (d->in1_chunks % 2) == 0), "estd_conv3d: pre-split inputs hold an even number of chunks");
+        ESTD_REQUIRE(!d->head_out || (ring && d->cout_pad == 16 && d->head_w && d->head_b && !d->out_split && !d->out1),
+                     "estd_conv3d: the fused logit head needs a plane-ring kernel with cout_pad 16, head_w and head_b");
         ESTD_REQUIRE(d->in0_chunks > 0 && d->in1_chunks >= 0 && (d->in1_chunks == 0 || d->in1), "estd_conv3d: bad input segments");
         ESTD_REQUIRE(d->out0_chunks > 0 && d->out1_chunks >= 0 && (d->out1_chunks == 0 || d->out1), "estd_conv3d: bad output segments");
         ESTD_REQUIRE((d->out0_chunks + d->out1_chunks) * 4 <= d->cout_pad, "estd_conv3d: outputs exceed cout_pad");
         ESTD_REQUIRE(d->act_split >= 0 && (d->act_split % 8) == 0, "estd_conv3d: act_split must be a multiple of 8");
         ESTD_REQUIRE(d->planar || (d->act_lo < ESTD_ACT_ADD_RELU && d->act_hi < ESTD_ACT_ADD_RELU), "estd_conv3d: ESTD_ACT_ADD_RELU / ESTD_ACT_SIGMOID are implemented for planar convolutions only");
-        ESTD_REQUIRE(aligned16(d->in0) && aligned16(d->out0) && (!d->weight || aligned16(d->weight)) && (!d->in1 || aligned16(d->in1)) &&
+        ESTD_REQUIRE(aligned16(d->in0) && (!d->out0 || aligned16(d->out0)) && (!d->weight || aligned16(d->weight)) && (!d->in1 || aligned16(d->in1)) &&
                      (!d->out1 || aligned16(d->out1)) && (!d->res0 || aligned16(d->res0)) && (!d->res1 || aligned16(d->res1)),
                      "estd_conv3d: tensors must be 16-byte aligned");
         ESTD_REQUIRE((d->W * 16) % 16 == 0 && d->W * 4 <= (1 << 30), "estd_conv3d: W too large");

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <utility>
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace estd {
@@ -62,6 +63,9 @@ struct ConvEpilogue {
     int out0_chunks, out_chunks;
     int act_split, act_lo, act_hi;
     float post_scale;
+    int res_split, out_split;                   // vol4s residuals / output (include/estdepth_b200.h)
+    int* status;                                // fp16 range flag (out_split)
+    const float* head_w; const float* head_b; float* head_out;      // fused 1x1x1 logit head
 };
 
 inline void fill_epilogue(ConvEpilogue* e, const estd_conv3d_desc* d) {
@@ -72,6 +76,37 @@ inline void fill_epilogue(ConvEpilogue* e, const estd_conv3d_desc* d) {
     e->out0_chunks = d->out0_chunks; e->out_chunks = d->out0_chunks + d->out1_chunks;
     e->act_split = d->act_split; e->act_lo = d->act_lo; e->act_hi = d->act_hi;
     e->post_scale = d->post_scale;
+    e->res_split = d->res_split; e->out_split = d->out_split;
+    e->status = d->status;
+    e->head_w = d->head_w; e->head_b = d->head_b; e->head_out = d->head_out;
+}
+
+// ---- vol4s helpers: 8 channels of one voxel = 16 B of x_hi (8 x fp16) in chunk 2g + 16 B of x_lo in chunk 2g+1 ----
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo, float& amax) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a = v[2 * i], b = v[2 * i + 1];
+        amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
+        const __half2 hh = __floats2half2_rn(a, b);
+        const float2 f = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(a - f.x, b - f.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// x_hi + x_lo of 8 channels (exact in fp32: 22 significant bits)
+__device__ __forceinline__ void join8(const float4& hi4, const float4& lo4, float* out) {
+    const uint32_t h[4] = {__float_as_uint(hi4.x), __float_as_uint(hi4.y), __float_as_uint(hi4.z), __float_as_uint(hi4.w)};
+    const uint32_t l[4] = {__float_as_uint(lo4.x), __float_as_uint(lo4.y), __float_as_uint(lo4.z), __float_as_uint(lo4.w)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&l[i]));
+        out[2 * i] = a.x + b.x; out[2 * i + 1] = a.y + b.y;
+    }
 }
 
 // 16 consecutive output channels [c0, c0+16) of one voxel: affine -> activation -> residuals -> scale -> 4 x 16-byte stores.

@@ -70,6 +70,7 @@ struct Params {
     int* status;
     ConvEpilogue ep;
     int in0_chunks;
+    int in0_split, in1_split;                   // the input segments are pre-split (vol4s): the splitter warps pass them through
     int D, H, W;
     int tiles_h, tiles_w;
     int total;                                  // column pairs * D  (flat (column pair, plane) index space)
@@ -256,7 +257,8 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
                 if (warp == FIRST_SPLIT_WARP) mbar_wait_polls(&full[s], (uint32_t)((it / STAGES) & 1));
                 named_barrier(2, SPLIT_THREADS);
                 unsigned char* area = smem + (size_t)s * S::STAGE_BYTES;
-                for (int i = t; i < 2 * HALO_VOX; i += SPLIT_THREADS) {
+                const bool presplit = (4 * (st % NKS) < p.in0_chunks) ? (p.in0_split != 0) : (p.in1_split != 0);
+                for (int i = t; !presplit && i < 2 * HALO_VOX; i += SPLIT_THREADS) {
                     const int pair = i / HALO_VOX, v = i - pair * HALO_VOX;
                     float4* c0 = reinterpret_cast<float4*>(area + (size_t)pair * 2 * S::KGROUP_BYTES) + v;   // channels 8p..8p+3
                     float4* c1 = c0 + HALO_VOX;                                                                // channels 8p+4..8p+7
@@ -368,6 +370,7 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
     p.status = d->status;
     fill_epilogue(&p.ep, d);
     p.in0_chunks = d->in0_chunks;
+    p.in0_split = d->in0_split; p.in1_split = d->in1_split;
     p.D = d->D; p.H = d->H; p.W = d->W;
     p.tiles_h = tiles_h; p.tiles_w = tiles_w; p.total = (int)total;
     auto kern = conv3d_ring2_kernel<S>;

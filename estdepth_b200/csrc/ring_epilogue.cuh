@@ -34,6 +34,7 @@ __device__ __forceinline__ void ring_drain_slot(const ConvEpilogue& ep, const fl
     tc_fence_before();
     hand_back();
 
+    float amax = 0.0f;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int c0 = 16 * b;
@@ -47,6 +48,12 @@ __device__ __forceinline__ void ring_drain_slot(const ConvEpilogue& ep, const fl
             for (int j = 0; j < 4; ++j) {
                 const int ch = (c0 >> 2) + j;
                 r[j] = (ok && ch < ep.out_chunks) ? ldg4(ep.res0 + ((size_t)ch * vox + pos) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (ep.res_split) {                                    // vol4s: chunks (0,1) = hi / lo of channels c0..c0+7, (2,3) of c0+8..c0+15
+                float t[16];
+                join8(r[0], r[1], t); join8(r[2], r[3], t + 8);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) r[j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
             }
         } else {
 #pragma unroll
@@ -73,6 +80,12 @@ __device__ __forceinline__ void ring_drain_slot(const ConvEpilogue& ep, const fl
                 const int ch = (c0 >> 2) + j;
                 r[j] = (ok && ch < ep.out_chunks) ? ldg4(ep.res1 + ((size_t)ch * vox + pos) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            if (ep.res_split) {
+                float t[16];
+                join8(r[0], r[1], t); join8(r[2], r[3], t + 8);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) r[j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) { v[4 * j + 0] += r[j].x; v[4 * j + 1] += r[j].y; v[4 * j + 2] += r[j].z; v[4 * j + 3] += r[j].w; }
         }
@@ -81,7 +94,6 @@ __device__ __forceinline__ void ring_drain_slot(const ConvEpilogue& ep, const fl
         for (int j = 0; j < 4; ++j) {
             const int c = c0 + 4 * j;
             const int ch = c >> 2;
-            if (!ok || ch >= ep.out_chunks) continue;
             const int grp = (c < ep.act_split) ? 0 : 1;
             float s4 = 0.f, q4 = 0.f;
 #pragma unroll
@@ -90,16 +102,40 @@ __device__ __forceinline__ void ring_drain_slot(const ConvEpilogue& ep, const fl
                 s4 += v[4 * j + k];
                 q4 = fmaf(v[4 * j + k], v[4 * j + k], q4);
             }
+            if (!ok || ch >= ep.out_chunks) continue;
             if (grp == 0) { ts[0] += s4; tq[0] += q4; } else { ts[1] += s4; tq[1] += q4; }
+            if (ep.out_split || !ep.out0) continue;
             const size_t off = ((size_t)ch * vox + pos) * 4;
             float* dst = (ch < ep.out0_chunks) ? ep.out0 + off : ep.out1 + (off - (size_t)ep.out0_chunks * vox * 4);
             st4(dst, make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        }
+        if (ep.out_split) {
+            // vol4s: x_hi of channels c0..c0+7 -> chunk c0/4, x_lo -> chunk c0/4 + 1; c0+8..c0+15 -> the next two chunks
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const int ch = (c0 >> 2) + 2 * g;
+                if (!ok || ch >= ep.out_chunks) continue;
+                uint4 hi, lo;
+                split8(v + 8 * g, hi, lo, amax);
+                float* dst = ep.out0 + ((size_t)ch * vox + pos) * 4;
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + vox * 4) = lo;
+            }
+        }
+        if constexpr (COUT == 16) {
+            if (ep.head_out && ok) {                               // fused 1x1x1 logit head over the 16 finished channels
+                float logit = __ldg(ep.head_b);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) logit = fmaf(__ldg(ep.head_w + k), v[k], logit);
+                ep.head_out[pos] = logit;
+            }
         }
         if (want_gn) {
             gs[0] += (double)ts[0]; gq[0] += (double)tq[0];
             gs[1] += (double)ts[1]; gq[1] += (double)tq[1];
         }
     }
+    if (ep.out_split && !(amax <= 65504.0f) && ep.status) atomicOr(ep.status, 1);
 }
 
 }  // namespace tc

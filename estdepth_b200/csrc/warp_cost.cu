@@ -168,6 +168,9 @@ __device__ __forceinline__ Taps2 plane_sweep_taps(const float (&hm)[12], float f
 // History (profiles/README.md): v1 one voxel per thread, one plane per block -> L2-bandwidth bound (L1 hit 42 %);
 // a persistent one-plane-at-a-time variant was slower (fewer loads in flight); the kernel is L1-pipe bound (ncu:
 // l1tex 68 % of peak, 6 x 16 B through the L1 pipe per 16 B stored).
+// (A variant that wrote x0 pre-split -- vol4s, so that pre1 could skip its in-place hi/lo split -- was measured and dropped:
+// the results of an even chunk have to wait in registers for the odd chunk that completes their 8-channel group, the kernel
+// spills at its 64-register budget and runs at 69 us instead of 41 us, against 5 us saved in the consumer.)
 template <int ALIGN, int KP>
 __global__ void __launch_bounds__(256, 4) warp_cost_kernel(const float* __restrict__ ref_mix, const float* __restrict__ src_mix,
                                                            const float* __restrict__ homo12,

@@ -127,14 +127,41 @@ def _pack3x3(conv, bn, act, device, any_stride=False):
     return packing.pack_conv2d(w, s, b, act, device, cout_slice=64 if cout > 32 else 32 if cout > 16 else 16)
 
 
-def _run3x3(pcs, x4, out4=None, res4=None, dilation=1, in1=None, taps=9, post_scale=1.0):
-    """One packed planar layer over vol4 maps [C/4, N, H, W, 4] (+ optional second input segment = torch.cat on channels)."""
+SPLIT_ACTIVATIONS = _os.environ.get("ESTD_SPLIT_ACT", "1") != "0"
+
+
+def _is_split(t):
+    """True when a vol4 tensor holds PRE-SPLIT activations (vol4s, include/estdepth_b200.h: chunk pairs = x_hi | x_lo of 8
+    channels as fp16).  The form is a tag on the tensor object; every helper below that makes a new tensor from a tagged
+    one copies the tag."""
+    return t is not None and bool(getattr(t, "_estd_split", False))
+
+
+def _tag(t, split):
+    t._estd_split = bool(split)
+    return t
+
+
+def _run3x3(pcs, x4, out4=None, res4=None, dilation=1, in1=None, taps=9, post_scale=1.0, out_split=True):
+    """One packed planar layer over vol4 maps [C/4, N, H, W, 4] (+ optional second input segment = torch.cat on channels).
+
+    Activations between planar layers travel PRE-SPLIT (``out_split``, the default): the producer's epilogue writes the fp16
+    x_hi | x_lo pair the consumer's tensor-core operands need, so the consumer skips its in-place split (a tenth of a stage's
+    shared-memory traffic: 29 -> 26 us for 64->64 at 120x160x5, 87 -> 77 us for 128->128).  Inputs may be in either form (their
+    tag tells); layers whose output is read by something else than a planar layer pass ``out_split=False``."""
     from . import ops
     pc = pcs[0]
+    out_split = bool(out_split) and SPLIT_ACTIVATIONS and pc.out_chunks % 2 == 0
     if out4 is None:
         out4 = torch.empty(pc.out_chunks, x4.shape[1], x4.shape[2], x4.shape[3], 4, device=x4.device, dtype=torch.float32)
-    ops.conv_planar(pc, x4, out4, res0=res4, dilation=dilation, in1=in1, taps=taps, post_scale=post_scale)
-    return out4
+    ops.conv_planar(pc, x4, out4, res0=res4, dilation=dilation, in1=in1, taps=taps, post_scale=post_scale,
+                    in_split=(_is_split(x4), _is_split(in1)), res_split=_is_split(res4), out_split=out_split)
+    return _tag(out4, out_split)
+
+
+def _sub2(x4):
+    """Every other row and column of vol4 maps (what a stride-2 layer keeps of its stride-1 result); form-agnostic."""
+    return _tag(x4[:, :, ::2, ::2, :].contiguous(), _is_split(x4))
 
 
 def _as_vol4(t):
@@ -151,7 +178,9 @@ def _as_vol4(t):
 
 def _as_nchw(t):
     from . import ops
-    return ops.vol4_to_nchw(t) if t.dim() == 5 else t
+    if t.dim() != 5:
+        return t
+    return ops.vol4_to_nchw(ops.from_split(t) if _is_split(t) else t)
 
 
 def _channels(t):
@@ -161,7 +190,7 @@ def _channels(t):
 def _up2_vol4(x4):
     """nearest x2 upsampling of vol4 maps (hybrid_depth_decoder.py:11-14)."""
     c, n, h, w, _ = x4.shape
-    return x4[:, :, :, None, :, None, :].expand(c, n, h, 2, w, 2, 4).reshape(c, n, 2 * h, 2 * w, 4)
+    return _tag(x4[:, :, :, None, :, None, :].expand(c, n, h, 2, w, 2, 4).reshape(c, n, 2 * h, 2 * w, 4), _is_split(x4))
 
 
 def _conv_bn(cin, cout, k, stride, pad, dilation):
@@ -251,16 +280,14 @@ class MatchingFeatureNet(nn.Module):
         return self._tc_packed
 
     @staticmethod
-    def _conv_tc(pcs, x4, out4, res4=None, dilation=1, taps=9):
+    def _conv_tc(pcs, x4, out4, res4=None, dilation=1, taps=9, out_split=True):
         """Runs a packed planar layer (3x3, or 1x1 with taps=1) from vol4 maps into out4."""
-        from . import ops
-        ops.conv_planar(pcs[0], x4, out4, res0=res4, dilation=dilation, taps=taps)
-        return out4
+        return _run3x3(pcs, x4, out4, res4=res4, dilation=dilation, taps=taps, out_split=out_split)
 
     def forward_tc(self, x):
-        """Same arithmetic as ``forward`` with the stride-1 3x3 convolutions of layer2/3/4 and the 320->128 fuse conv
-        (538 + 70 of the net's 679 GFLOP at 480x640) on the tcgen05 tensor cores (fp16 two-term split, fp32-class
-        accuracy) with BN / ReLU / residual add fused into their epilogues; activations stay in vol4 between them."""
+        """Same arithmetic as ``forward`` with every stride-1 3x3 / 1x1 convolution (600 of the net's 679 GFLOP at 480x640) on
+        the tcgen05 tensor cores (fp16 two-term split, fp32-class accuracy) with BN / ReLU / residual add fused into their
+        epilogues; activations stay in vol4 between them, pre-split (vol4s) wherever the reader is another planar layer."""
         from . import ops
         P = self._packed(x.device)
         x = _folded(x, self.firstconv[0][0], self.firstconv[0][1], relu=True)   # 3->32 stride-2 stem conv: cuDNN
@@ -271,36 +298,35 @@ class MatchingFeatureNet(nn.Module):
         for i in range(len(self.layer1)):
             self._conv_tc(P[("layer1", i, 1)], cur, tmp)
             cur = self._conv_tc(P[("layer1", i, 2)], tmp, half(), cur)
-        blk = self.layer2[0]
         H, W = (Hh + 1) // 2, (Wh + 1) // 2
         dev = x.device
 
         def vol(chunks):
             return torch.empty(chunks, N, H, W, 4, device=dev, dtype=torch.float32)
 
-        cat = vol(80)                                               # [raw 64 | skip 128 | branch4..1 32 each]
+        # [raw 64 | skip 128 | branch4..1 32 each]: fp32 throughout (the SPP branches and the pooling read / write it too)
+        cat = vol(80)
         # layer2 block 0: the stride-2 3x3 runs at stride 1 and keeps the even rows / columns; the stride-2 1x1 shortcut
         # runs on the subsampled input
-        y = self._conv_tc(P[("layer2", 0, 1)], cur, torch.empty(16, N, Hh, Wh, 4, device=dev))[:, :, ::2, ::2, :].contiguous()
-        shortcut = self._conv_tc(P[("layer2", 0, "down")], cur[:, :, ::2, ::2, :].contiguous(), vol(16), taps=1)
+        y = _sub2(self._conv_tc(P[("layer2", 0, 1)], cur, torch.empty(16, N, Hh, Wh, 4, device=dev)))
+        shortcut = self._conv_tc(P[("layer2", 0, "down")], _sub2(cur), vol(16), taps=1)
         cur = self._conv_tc(P[("layer2", 0, 2)], y, vol(16), shortcut)
         tmp = vol(16)
         n2 = len(self.layer2)
         for i in range(1, n2):
             self._conv_tc(P[("layer2", i, 1)], cur, tmp)
-            nxt = cat[0:16] if i == n2 - 1 else vol(16)
-            cur = self._conv_tc(P[("layer2", i, 2)], tmp, nxt, cur)
+            last = i == n2 - 1
+            cur = self._conv_tc(P[("layer2", i, 2)], tmp, cat[0:16] if last else vol(16), cur, out_split=not last)
         raw = cur
-        # layer3: block 0 changes the width (64 -> 128) and projects the shortcut with a 1x1 conv (cuDNN)
-        blk = self.layer3[0]
+        # layer3: block 0 changes the width (64 -> 128) and projects the shortcut with a 1x1 conv
         shortcut = self._conv_tc(P[("layer3", 0, "down")], raw, vol(32), taps=1)
         tmp = self._conv_tc(P[("layer3", 0, 1)], raw, vol(32))
         cur = self._conv_tc(P[("layer3", 0, 2)], tmp, vol(32), shortcut)
         stages = [("layer3", i, 1) for i in range(1, len(self.layer3))] + [("layer4", i, 2) for i in range(len(self.layer4))]
         for k, (name, i, dil) in enumerate(stages):
             self._conv_tc(P[(name, i, 1)], cur, tmp, dilation=dil)
-            nxt = cat[16:48] if k == len(stages) - 1 else vol(32)
-            cur = self._conv_tc(P[(name, i, 2)], tmp, nxt, cur, dilation=dil)
+            last = k == len(stages) - 1
+            cur = self._conv_tc(P[(name, i, 2)], tmp, cat[16:48] if last else vol(32), cur, dilation=dil, out_split=not last)
         deep = ops.vol4_to_nchw(cur)                                # SPP pooling / 1x1 / bilinear resize: torch
         pooled = None
         for slot, idx in enumerate((4, 3, 2, 1)):
@@ -317,7 +343,7 @@ class MatchingFeatureNet(nn.Module):
             torch.backends.cuda.matmul.allow_tf32 = tf32
             ops.upsample_bilinear_vol4(y, cat[48 + 8 * slot:56 + 8 * slot], bias=bf, relu=True)
         fused = self._conv_tc(P["fuse"], cat, vol(32))
-        return ops.vol4_to_nchw(self._conv_tc(P["last"], fused, vol(8), taps=1))
+        return ops.vol4_to_nchw(self._conv_tc(P["last"], fused, vol(8), taps=1, out_split=False))
 
     def forward(self, x):
         if x.is_cuda and getattr(self, "tensor_cores", False):
@@ -401,17 +427,17 @@ class ContextEncoder(nn.Module):
             if blk.downsample is None:
                 identity4 = x4
             else:
-                xs = x4 if blk.downsample[0].stride == (1, 1) else x4[:, :, ::2, ::2, :].contiguous()
+                xs = x4 if blk.downsample[0].stride == (1, 1) else _sub2(x4)
                 identity4 = _run3x3(pd, xs, taps=1)
             if kind == "bottleneck":
                 y4 = _run3x3(p2, _run3x3(p1, x4, taps=1))
                 if strided:
-                    y4 = y4[:, :, ::2, ::2, :].contiguous()
+                    y4 = _sub2(y4)
                 x4 = _run3x3(p3, y4, res4=identity4, taps=1)
             else:
                 y4 = _run3x3(p1, x4)
                 if strided:
-                    y4 = y4[:, :, ::2, ::2, :].contiguous()
+                    y4 = _sub2(y4)
                 x4 = _run3x3(p2, y4, res4=identity4)
         return x4
 
@@ -526,7 +552,7 @@ class ContextDecoder2D(nn.Module):
             x = _run3x3(P["upconv_3_0"], x)
             x = _run3x3(P["upconv_3_1"], _up2_vol4(x), in1=_as_vol4(maps[2]))
             x = _run3x3(P["upconv_2_0"], x)
-            x = _run3x3(P["upconv_2_1"], _up2_vol4(x), in1=_as_vol4(maps[1]))
+            x = _run3x3(P["upconv_2_1"], _up2_vol4(x), in1=_as_vol4(maps[1]), out_split=False)    # read by vol4_to_nchw / refine
             out = ops.vol4_to_nchw(x)
             out._estd_vol4 = x                  # refine() takes the vol4 copy (saves a layout pass)
             return out
@@ -547,10 +573,10 @@ class ContextDecoder2D(nn.Module):
             # whole refinement on the planar tcgen05 kernel: cat -> second input segment, sigmoid * depth_max in the epilogue
             x = _run3x3(P["upconv_1_0"], _as_vol4(semantic_vs), in1=ops.nchw_to_vol4(F.relu(fused_logits)))
             x = _run3x3(P["upconv_1_1"], _up2_vol4(x), in1=ops.nchw_to_vol4(skip_half.contiguous()))
-            d1 = _run3x3(P["dispconv_1"], x, post_scale=self.depth_max)                  # [1 chunk, N, H/2, W/2, 4]
+            d1 = _run3x3(P["dispconv_1"], x, post_scale=self.depth_max, out_split=False)  # [1 chunk, N, H/2, W/2, 4]
             depth_half = _up2(d1[0, ..., 0].unsqueeze(1))
             x = _run3x3(P["upconv_0_1"], _up2_vol4(_run3x3(P["upconv_0_0"], x)))
-            depth_full = _run3x3(P["dispconv_0"], x, post_scale=self.depth_max)[0, ..., 0].unsqueeze(1).contiguous()
+            depth_full = _run3x3(P["dispconv_0"], x, post_scale=self.depth_max, out_split=False)[0, ..., 0].unsqueeze(1).contiguous()
             return depth_half, depth_full
         self._log_cudnn("refinement", semantic_vs)
         x = self.upconv_1_0(torch.cat([semantic_vs, F.relu(fused_logits)], dim=1))

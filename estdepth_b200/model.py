@@ -99,7 +99,7 @@ class _Workspace(object):
             return torch.empty(chunks, D, H, W, 4, device=device, dtype=torch.float32)
         self.key = (str(device), D, H, W)
         self.x0, self.y, self.cost, self.a, self.b = vol(8), vol(8), vol(8), vol(8), vol(8)
-        self.sem, self.z = vol(1), vol(9)
+        self.sem, self.z = vol(1), vol(10)          # z: 36 channels = 9 chunks; 10 when it is kept pre-split (vol4s)
         self.hid = vol(4)
         self.h, self.rh, self.o = vol(4), vol(4), vol(4)
         self.f = vol(8)
@@ -162,6 +162,8 @@ class DepthNetHybrid(nn.Module):
         self.merged_pre2 = bool(merged_pre2)
         # overlap_context: context encoder / decoder on a second stream beside the matching-feature net (see prepare)
         self.overlap_context = int(os.environ.get("ESTD_OVERLAP_CONTEXT", "2"))    # 0 off, 1 join after the feature nets, 2 join at dres2
+        self.split_activations = os.environ.get("ESTD_SPLIT_ACT", "1") != "0"      # see _ring
+        self.fused_head = os.environ.get("ESTD_FUSED_HEAD", "1") != "0"
         self._ctx_done = None
 
         self.matchingFeature = MatchingFeatureNet()
@@ -273,6 +275,26 @@ class DepthNetHybrid(nn.Module):
     def _conv(self, pc, *args, **kwargs):
         return ops.conv3d(pc, *args, precision=self.precision, **kwargs)
 
+    def _ring(self, L):
+        """True when every 3-D layer runs on a plane-ring kernel: the conv-to-conv activations of the 3-D path are then kept
+        PRE-SPLIT (vol4s: the producer's epilogue writes x_hi | x_lo, the consumer skips its in-place split) and the 1x1x1 logit
+        heads are fused into the head convolutions' epilogues.  ESTD_SPLIT_ACT=0 / ESTD_FUSED_HEAD=0 turn the two off."""
+        return self.precision in ("3xf16r", "3xf16r2") and all(
+            v.precision is None and v.weight_ring is not None for v in L.values() if isinstance(v, ops.PackedConv))
+
+    def _head(self, L, ws, which, volume, depth_values, logits_out, depth_out, prob_out):
+        """stereo_head{0,1} (3x3x3 conv + BN + ReLU, then Conv3d(16, 1, 1)) + nearest x4 + depthlayer
+        (hybrid_depth_decoder.py:104-112, 202-209, 259-260)."""
+        name = "head%d" % which
+        if self._ring(L) and self.fused_head:
+            # the 16-channel hidden volume never reaches memory: the logit is a dot product in the convolution's epilogue
+            self._conv(L[name], volume, None, head=(L[name + "_w"], L[name + "_b"], logits_out))
+            ops.head_softargmin(depth_values, logits_in=logits_out, depth_out=depth_out, prob_out=prob_out, up=4)
+        else:
+            self._conv(L[name], volume, ws.hid)
+            ops.head_softargmin(depth_values, hidden=ws.hid, head_w=L[name + "_w"], head_b=L[name + "_b"],
+                                logits_out=logits_out, depth_out=depth_out, prob_out=prob_out, up=4)
+
     def scale_cam_intr(self, cam_intr, scale):
         out = cam_intr.clone()
         out[:, :2, :] *= scale
@@ -287,45 +309,50 @@ class DepthNetHybrid(nn.Module):
         (SURVEY.md Appendix A.1): the second pre1 adds y_a in its epilogue (after its ReLU) and ONE pre2 with the doubled
         offset runs per target -- 3 instead of 4 convolutions, same value up to fp32 summation order."""
         homo = [self._homo_table[2 * t + n] if self._homo_table is not None else None for n in (0, 1)]
+        # conv-to-conv activations are kept pre-split (vol4s, see _ring): pre1's output and the cost volume.  x0 stays fp32 (a
+        # K1 that writes it pre-split spills: measured 69 us against 41 us) and so do the tensors that are residuals.
+        sp = self._ring(L) and self.split_activations
+        s0 = (sp, False)
         if self.merged_pre2:
             assert out is not ws.x0 and out is not ws.a
             h = homo[0] if homo[0] is not None else ops.homography_setup(poses[t + 1], poses[t], K4, ws.homo)
             ops.warp_cost(ref_mix[t + 1], src_mix[t], h, depth_values, ws.x0, self.align_corners)
-            self._conv(L["pre1"], ws.x0, ws.y)
+            self._conv(L["pre1"], ws.x0, ws.y)                                              # y is only ever a residual: fp32
             h = homo[1] if homo[1] is not None else ops.homography_setup(poses[t + 1], poses[t + 2], K4, ws.homo)
             ops.warp_cost(ref_mix[t + 1], src_mix[t + 2], h, depth_values, ws.b, self.align_corners)
-            self._conv(L["pre1"], ws.b, ws.a, res0=ws.y)                                    # relu(bn(conv(x0_b))) + y_a
-            self._conv(L["pre2_pair"], ws.a, out, res0=ws.x0, res1=ws.b, post_scale=0.5)
+            self._conv(L["pre1"], ws.b, ws.a, res0=ws.y, out_split=sp)                      # relu(bn(conv(x0_b))) + y_a
+            self._conv(L["pre2_pair"], ws.a, out, res0=ws.x0, res1=ws.b, post_scale=0.5, in_split=s0, out_split=sp)
             return out
         for n, s in enumerate((t, t + 2)):
             h = homo[n] if homo[n] is not None else ops.homography_setup(poses[t + 1], poses[s], K4, ws.homo)
             ops.warp_cost(ref_mix[t + 1], src_mix[s], h, depth_values, ws.x0, self.align_corners)
-            self._conv(L["pre1"], ws.x0, ws.y)
-            if n == 0:      # cost = x0 + pre2(pre1(x0))
-                self._conv(L["pre2"], ws.y, ws.cost, res0=ws.x0)
+            self._conv(L["pre1"], ws.x0, ws.y, out_split=sp)
+            if n == 0:      # cost = x0 + pre2(pre1(x0))   (fp32: it is a residual of the second application)
+                self._conv(L["pre2"], ws.y, ws.cost, res0=ws.x0, in_split=s0)
             else:           # cost = (cost + x0 + pre2(pre1(x0))) / 2
-                self._conv(L["pre2"], ws.y, out, res0=ws.x0, res1=ws.cost, post_scale=0.5)
+                self._conv(L["pre2"], ws.y, out, res0=ws.x0, res1=ws.cost, post_scale=0.5, in_split=s0, out_split=sp)
         return out
 
     def _matching(self, L, ws, cost, semantic_vs_t, depth_values, logits_out, depth_out, prob_out):
         """dres0..2, value/key heads, stereo_head0 + soft-argmin (hybrid_depth_decoder.py:187-209)."""
         dev = cost.device
         _, D, H, W, _ = cost.shape
-        self._conv(L["dres0.0"], cost, ws.a)
-        self._conv(L["dres0.1"], ws.a, ws.b)
-        self._conv(L["dres1.0"], ws.b, ws.a)
-        self._conv(L["dres1.1"], ws.a, ws.b)
+        sp = self._ring(L) and self.split_activations          # the cost volume arrives pre-split then (see _cost_volume)
+        s0 = (sp, False)
+        self._conv(L["dres0.0"], cost, ws.a, in_split=s0, out_split=sp)
+        self._conv(L["dres0.1"], ws.a, ws.b, in_split=s0, out_split=sp)
+        self._conv(L["dres1.0"], ws.b, ws.a, in_split=s0, out_split=sp)
+        self._conv(L["dres1.1"], ws.a, ws.b, in_split=s0, out_split=sp)
         if self._ctx_done is not None:
             torch.cuda.current_stream(dev).wait_event(self._ctx_done)
             self._ctx_done = None
         ops.scalar_to_vol4(semantic_vs_t, ws.sem)
-        self._conv(L["dres2"], ws.b, ws.z, in1=ws.sem)
+        z = ws.z if sp else ws.z[:9]
+        self._conv(L["dres2"], ws.b, z, in1=ws.sem, in_split=s0, out_split=sp)             # the context chunk stays fp32
         value = torch.empty(4, D, H, W, 4, device=dev, dtype=torch.float32)
         key = torch.empty(4, D, H, W, 4, device=dev, dtype=torch.float32)
-        self._conv(L["value_key"], ws.z, value, out1=key)
-        self._conv(L["head0"], value, ws.hid)
-        ops.head_softargmin(depth_values, hidden=ws.hid, head_w=L["head0_w"], head_b=L["head0_b"],
-                            logits_out=logits_out, depth_out=depth_out, prob_out=prob_out, up=4)
+        self._conv(L["value_key"], z, value, out1=key, in_split=s0)
+        self._head(L, ws, 0, value, depth_values, logits_out, depth_out, prob_out)
         return value, key
 
     def _fuse(self, L, ws, key_i, value_i, src_keys, src_values, pose_i, src_poses, K4, depth_values, warp30=None):
@@ -573,10 +600,7 @@ class DepthNetHybrid(nn.Module):
                                        all_poses[i], [all_poses[j] for j in others], K4[b], depth_values,
                                        warp30=None if tables is None else tables[i])
                     values[i] = fused                                             # quirk Q5 (:253)
-                self._conv(L["head1"], values[i], ws.hid)
-                ops.head_softargmin(depth_values, hidden=ws.hid, head_w=L["head1_w"], head_b=L["head1_b"],
-                                    logits_out=fused_logits[b * T + i], depth_out=depth2[b, i, 0],
-                                    prob_out=fused_prob[b, i, 0], up=4)
+                self._head(L, ws, 1, values[i], depth_values, fused_logits[b * T + i], depth2[b, i, 0], fused_prob[b, i, 0])
             ops.vol4_to_ncdhw(keys[T - 1], state_key[b])
             ops.vol4_to_ncdhw(values[T - 1], state_value[b])
             state_key._estd_vol4[b], state_value._estd_vol4[b] = keys[T - 1], values[T - 1]

@@ -398,7 +398,12 @@ def _desc_template(pc, precision, planar, dilation, device):
     return bytes(d)
 
 
-def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision, planar=0, dilation=1):
+def _even(n):
+    return (n + 1) // 2 * 2
+
+
+def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision, planar=0, dilation=1,
+               in_split=(False, False), res_split=False, out_split=False, head=None):
     chunks0, D, H, W, _ = in0.shape
     key = (precision, planar, dilation, in0.device.index)
     cache = pc._desc
@@ -411,15 +416,32 @@ def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, pr
     d.in0, d.in0_chunks = _act_ptr(in0), chunks0
     if in1 is not None:
         d.in1, d.in1_chunks = _act_ptr(in1), in1.shape[0]
-    if d.in0_chunks + d.in1_chunks != pc.cin_chunks:
-        raise RuntimeError("conv3d: layer packed for %d input chunks, got %d" % (pc.cin_chunks, d.in0_chunks + d.in1_chunks))
+    # a pre-split (vol4s) tensor has an even number of chunks: a 36-channel tensor occupies 10
+    want_in = _even(pc.cin_chunks) if (in_split[0] and in1 is None) else pc.cin_chunks
+    if d.in0_chunks + d.in1_chunks != want_in:
+        raise RuntimeError("conv3d: layer packed for %d input chunks, got %d" % (want_in, d.in0_chunks + d.in1_chunks))
+    if any(in_split) or res_split or out_split or head is not None:
+        if precision not in ("3xf16r", "3xf16r2") and not planar:
+            raise RuntimeError("conv3d: pre-split tensors / the fused logit head need the plane-ring kernels, not %r" % (precision,))
+        if (in_split[0] and chunks0 % 2) or (in1 is not None and in_split[1] and in1.shape[0] % 2) or (out_split and out1 is not None):
+            raise RuntimeError("conv3d: pre-split tensors hold an even number of chunks; a split output has one segment")
+        d.in0_split, d.in1_split, d.res_split, d.out_split = int(in_split[0]), int(in_split[1]), int(res_split), int(out_split)
     d.res0, d.res1 = _act_ptr(res0), _act_ptr(res1)
     d.post_scale = post_scale
-    d.out0, d.out0_chunks = _act_ptr(out0), out0.shape[0]
+    if out0 is not None:
+        d.out0, d.out0_chunks = _act_ptr(out0), out0.shape[0]
+    else:
+        d.out0_chunks = pc.out_chunks
     if out1 is not None:
         d.out1, d.out1_chunks = _act_ptr(out1), out1.shape[0]
-    if d.out0_chunks + d.out1_chunks != pc.out_chunks:
+    if d.out0_chunks + d.out1_chunks != (_even(pc.out_chunks) if out_split else pc.out_chunks):
         raise RuntimeError("conv3d: layer produces %d chunks, outputs hold %d" % (pc.out_chunks, d.out0_chunks + d.out1_chunks))
+    if head is not None:
+        if planar or pc.cout_pad_tc != 16 or gn_partials is not None:
+            raise RuntimeError("conv3d: the fused logit head needs a 16-channel 3x3x3 layer")
+        d.head_w, d.head_b, d.head_out = _act_ptr(head[0]), _act_ptr(head[1]), _act_ptr(head[2])
+    elif out0 is None:
+        raise RuntimeError("conv3d: no output")
     if gn_partials is not None:
         d.gn_partials = _act_ptr(gn_partials, torch.float64)
     d.D, d.H, d.W = D, H, W
@@ -439,13 +461,18 @@ def conv3d_num_ctas(pc, D, H, W, precision=None):
     return n
 
 
-def conv3d(pc, in0, out0, in1=None, out1=None, res0=None, res1=None, post_scale=1.0, gn_partials=None, precision=None):
+def conv3d(pc, in0, out0, in1=None, out1=None, res0=None, res1=None, post_scale=1.0, gn_partials=None, precision=None,
+           in_split=(False, False), res_split=False, out_split=False, head=None):
     """3x3x3 conv + folded affine + activation (+ residuals, x post_scale) over vol4 tensors; returns out0.
 
     precision: "fp32" (exact, CUDA cores) | "3xtf32" | "3xf16" (tcgen05 tensor cores, error-compensated splits) |
-    None = DEFAULT_PRECISION."""
+    "3xf16r" / "3xf16r2" (the same arithmetic on the plane-ring schedules) | None = DEFAULT_PRECISION.
+    Plane-ring kernels only: ``in_split`` = (in0, in1) are pre-split (vol4s, ``to_split``), ``res_split`` = the residuals
+    are, ``out_split`` = write out0 pre-split; ``head`` = (weight [16], bias [1], logits_out [D,H,W]): the 1x1x1 logit head
+    fused into the epilogue of a 16-channel layer (out0 may then be None)."""
     precision = _precision(pc, pc.precision or precision)
-    d = _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision)
+    d = _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision,
+                   in_split=in_split, res_split=res_split, out_split=out_split, head=head)
     t = _pb()
     check(_lib.get().estd_conv3d(ctypes.byref(d), _stream()), "estd_conv3d")
     vox = float(d.D) * d.H * d.W
@@ -453,15 +480,42 @@ def conv3d(pc, in0, out0, in1=None, out1=None, res0=None, res1=None, post_scale=
     return out0
 
 
-def conv_planar(pc, in0, out0, res0=None, dilation=1, in1=None, taps=9, post_scale=1.0):
+def conv_planar(pc, in0, out0, res0=None, dilation=1, in1=None, taps=9, post_scale=1.0,
+                in_split=(False, False), res_split=False, out_split=False):
     """2-D 3x3 (taps=9; stride 1, padding = dilation) or 1x1 (taps=1) convolution over a stack of N maps held as vol4
-    [C/4,N,H,W,4], with folded affine + activation (+ residual), on the tensor cores (fp16 two-term split).  Returns out0."""
-    d = _conv_desc(pc, in0, in1, out0, None, res0, None, post_scale, None, "3xf16", planar=1 if taps == 9 else 2, dilation=dilation)
+    [C/4,N,H,W,4], with folded affine + activation (+ residual), on the tensor cores (fp16 two-term split).  Returns out0.
+    ``in_split`` / ``res_split`` / ``out_split``: pre-split (vol4s) tensors, as for ``conv3d``."""
+    d = _conv_desc(pc, in0, in1, out0, None, res0, None, post_scale, None, "3xf16", planar=1 if taps == 9 else 2, dilation=dilation,
+                   in_split=in_split, res_split=res_split, out_split=out_split)
     t = _pb()
     check(_lib.get().estd_conv3d(ctypes.byref(d), _stream()), "estd_conv3d(planar)")
     vox = float(d.D) * d.H * d.W
     _pe(t, "conv2d_3xf16", 2.0 * taps * pc.cin * pc.cout * vox, 4.0 * vox * (pc.cin + pc.cout))
     return out0
+
+
+def to_split(vol4):
+    """vol4 -> vol4s with torch ops (tests, one-off conversions): chunks (2g, 2g+1) <- (fp16(x), fp16(x - fp16(x))) of channels
+    8g..8g+7, bit-identical to what the kernels' splitter warps / split epilogues produce.  The chunk count is padded to even."""
+    chunks = vol4.shape[0]
+    if chunks % 2:
+        vol4 = torch.cat([vol4, torch.zeros_like(vol4[:1])], 0)
+        chunks += 1
+    x = vol4.reshape(chunks // 2, 2, *vol4.shape[1:-1], 4)                    # [g, half, ..., 4]
+    x = torch.cat([x[:, 0], x[:, 1]], dim=-1)                                 # [g, ..., 8 channels]
+    hi = x.to(torch.float16)
+    lo = (x - hi.to(torch.float32)).to(torch.float16)
+    out = torch.stack([hi, lo], dim=1)                                        # [g, 2, ..., 8] fp16
+    return out.reshape(chunks, *vol4.shape[1:-1], 8).contiguous().view(torch.float32)
+
+
+def from_split(vol4s):
+    """vol4s -> vol4 (x_hi + x_lo)."""
+    chunks = vol4s.shape[0]
+    h = vol4s.contiguous().view(torch.float16).reshape(chunks // 2, 2, *vol4s.shape[1:-1], 8).to(torch.float32)
+    x = h[:, 0] + h[:, 1]                                                     # [g, ..., 8]
+    x = torch.stack([x[..., :4], x[..., 4:]], dim=1)                          # [g, 2, ..., 4]
+    return x.reshape(chunks, *vol4s.shape[1:-1], 4).contiguous()
 
 
 def nchw_to_vol4(x, out=None):

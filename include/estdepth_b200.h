@@ -120,6 +120,7 @@ ESTD_API int estd_warp_cost(const float* ref_mix_map4, const float* src_mix_map4
                    const float* depth_values, float* x0_vol4, int C, int D, int H, int W,
                    int align_corners, void* stream);
 
+
 /* ---- K2: 3x3x3 convolution, stride 1, pad 1, folded BN/bias + activation + residuals
  *      (replaces every convbn*_3d / nn.Conv3d(k=3): networks/layers_op.py:16-39, model_hybrid.py:59-60,94-95,
  *       hybrid_depth_decoder.py:84-112,190-200,256,377, transformer/epipolar_transformer.py:21,26) ---- */
@@ -148,6 +149,18 @@ typedef struct estd_conv3d_desc {
     float* out1; int out1_chunks;         /* optional second output tensor for the remaining chunks      */
     double* gn_partials;                  /* optional [n_ctas][2][2] (sum,sumsq) per channel group {[0,act_split),[act_split,..)} */
     int D, H, W;
+    /* PRE-SPLIT activations ("vol4s"; plane-ring and planar tensor-core kernels only).  Same shape, strides and bytes as vol4,
+     * but every pair of chunks (2g, 2g+1) holds channels 8g..8g+7 as 8 x fp16 x_hi = fp16(x) in chunk 2g and 8 x fp16
+     * x_lo = fp16(x - x_hi) in chunk 2g+1 -- exactly what the kernels' splitter warps turn an fp32 tile into in shared memory.
+     * A producer that writes this form (out_split) saves its consumer the in-place split (a tenth of the shared-memory
+     * traffic of a stage); chunk counts of such tensors are even (a 36-channel tensor has 10 chunks).  Flags are 0 / 1. */
+    int in0_split, in1_split;             /* the input segments are vol4s                                                  */
+    int res_split;                        /* res0 / res1 are vol4s (read as x_hi + x_lo)                                    */
+    int out_split;                        /* out0 is written as vol4s (out1 must be NULL); |value| > 65504 raises `status`  */
+    /* fused 1x1x1 logit head (hybrid_depth_decoder.py:104-112: Conv3d(16, 1, 1, bias=True) after the 16-channel head
+     * convolution; plane-ring kernels with cout_pad 16 only): head_out[d][h][w] = sum_c head_w[c] * y[c] + head_b[0] of the
+     * finished 16 channels y.  With head_out set, out0 may be NULL (the 16-channel volume is then never written). */
+    const float* head_w; const float* head_b; float* head_out;
 } estd_conv3d_desc;
 
 /* number of CTAs estd_conv3d will launch for this shape == rows of gn_partials the caller must provide */

@@ -501,3 +501,91 @@ def test_align_corners_flag_changes_sampling():
     assert maxdiff(got, want) < 2e-4
     got_false = ops.homo_warping(x["fea"].to(DEV), sp.to(DEV), rp.to(DEV), x["depth_values"].view(1, D).to(DEV))
     assert maxdiff(got_false, want) > 1e-2
+
+
+# ------------------------------------------------------------------------------------------- pre-split activations (vol4s)
+@pytest.mark.parametrize("precision", ["3xf16r", "3xf16r2"])
+@pytest.mark.parametrize("cin_chunks,cout,cout_pad", [(8, 32, 32), (9, 33, 48), (4, 16, 16)])
+def test_conv3d_presplit_tensors_equal_fp32_tensors(precision, cin_chunks, cout, cout_pad):
+    """A producer that writes x_hi | x_lo (out_split) and a consumer that reads it (in_split, res_split) compute exactly what the
+    fp32-tensor launch computes: the tensor core sees the same operands, only the stored form differs (22 significant bits)."""
+    g = torch.Generator().manual_seed(11)
+    D, H, W = 5, 21, 40
+    cin = 4 * cin_chunks
+    x = torch.randn(cin, D, H, W, generator=g)
+    if cin_chunks == 9:
+        x[33:] = 0                                                 # the canonical 36-channel tensor: 33 real channels + 3 zero pads
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) / (cin * 27) ** 0.5
+    order = list(range(cout)) + [-1] * (cout_pad - cout)
+    out_chunks = (cout + 3) // 4
+    pc = packing.attach_tc(ops.PackedConv(packing.pack_weight(w, list(range(cin)), order), torch.ones(cout_pad), torch.zeros(cout_pad),
+                                          cin_chunks, cout_pad, out_chunks, cout_pad, "relu", "relu")).to(DEV)
+    res = torch.randn(4 * out_chunks, D, H, W, generator=g)
+    x4, r4 = to_vol4(x).to(DEV), to_vol4(res).to(DEV)
+    plain = ops.conv3d(pc, x4, torch.empty(out_chunks, D, H, W, 4, device=DEV), res0=r4, res1=r4, post_scale=0.5, precision=precision)
+    xs, rs = ops.to_split(x4), ops.to_split(r4)
+    n_out = (out_chunks + 1) // 2 * 2
+    split = ops.conv3d(pc, xs, torch.full((n_out, D, H, W, 4), float("nan"), device=DEV), res0=rs, res1=rs, post_scale=0.5,
+                       precision=precision, in_split=(True, False), res_split=True, out_split=True)
+    got = ops.from_split(split)[:out_chunks]
+    assert torch.isfinite(got).all()
+    scale = plain.abs().max().item()
+    assert (got - plain).abs().max().item() <= 2.0 ** -20 * scale          # 22-bit storage of the output and of the residuals
+    # split input + fp32 output: bit-identical to the all-fp32 launch when there is no residual
+    a = ops.conv3d(pc, x4, torch.empty(out_chunks, D, H, W, 4, device=DEV), precision=precision)
+    b = ops.conv3d(pc, xs, torch.empty(out_chunks, D, H, W, 4, device=DEV), precision=precision, in_split=(True, False))
+    assert torch.equal(a, b)
+    ops.check_status(torch.device(DEV))
+
+
+def test_conv3d_presplit_rejected_by_other_kernels():
+    pc = packing.attach_tc(ops.PackedConv(packing.pack_weight(torch.randn(32, 32, 3, 3, 3) / 30, list(range(32)), list(range(32))),
+                                          torch.ones(32), torch.zeros(32), 8, 32, 8, 32, "none", "none")).to(DEV)
+    x = torch.randn(8, 4, 16, 32, 4, device=DEV)
+    for precision in ("fp32", "3xf16", "3xtf32"):
+        with pytest.raises(RuntimeError, match="plane-ring"):
+            ops.conv3d(pc, x, torch.empty_like(x), precision=precision, in_split=(True, False))
+
+
+def test_conv_planar_presplit_tensors_equal_fp32_tensors():
+    g = torch.Generator().manual_seed(4)
+    N, H, W, cin, cout = 2, 37, 50, 64, 128
+    x = torch.randn(N, cin, H, W, generator=g).relu()
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    res = torch.randn(N, cout, H, W, generator=g)
+    pc = packing.pack_conv2d(w, torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) / 3, "add_relu", DEV)[0]
+    x4, r4 = ops.nchw_to_vol4(x.to(DEV)), ops.nchw_to_vol4(res.to(DEV))
+    plain = ops.conv_planar(pc, x4, torch.empty(cout // 4, N, H, W, 4, device=DEV), res0=r4)
+    split = ops.conv_planar(pc, ops.to_split(x4), torch.full((cout // 4, N, H, W, 4), float("nan"), device=DEV), res0=ops.to_split(r4),
+                            in_split=(True, False), res_split=True, out_split=True)
+    got = ops.from_split(split)
+    assert torch.isfinite(got).all()
+    assert (got - plain).abs().max().item() <= 2.0 ** -20 * max(1.0, plain.abs().max().item())
+    mixed = ops.conv_planar(pc, ops.to_split(x4), torch.empty(cout // 4, N, H, W, 4, device=DEV), res0=r4, in_split=(True, False))
+    assert torch.equal(mixed, plain)
+
+
+@pytest.mark.parametrize("precision", ["3xf16r", "3xf16r2"])
+def test_fused_logit_head_equals_head_conv_then_1x1x1(precision):
+    """stereo_head: Conv3d(16,16,3)+BN+ReLU then Conv3d(16,1,1,bias) (hybrid_depth_decoder.py:104-112): the logit computed in the
+    convolution's epilogue equals the two-kernel path (hidden volume + head_softargmin's own dot product)."""
+    g = torch.Generator().manual_seed(6)
+    D, H, W = 9, 24, 40
+    x = to_vol4(torch.randn(16, D, H, W, generator=g)).to(DEV)
+    w = torch.randn(16, 16, 3, 3, 3, generator=g) / (16 * 27) ** 0.5
+    pc = packing.attach_tc(ops.PackedConv(packing.pack_weight(w, list(range(16)), list(range(16))), torch.rand(16, generator=g) + 0.5,
+                                          torch.randn(16, generator=g) / 3, 4, 16, 4, 16, "relu", "relu")).to(DEV)
+    hw, hb = (3.0 * torch.randn(16, generator=g)).to(DEV), torch.randn(1, generator=g).to(DEV)
+    dv = (torch.arange(D, dtype=torch.float32) * (9.9 / (D - 1)) + 0.1).to(DEV)
+    hidden = ops.conv3d(pc, x, torch.empty_like(x), precision=precision)
+    logits_a = torch.empty(D, H, W, device=DEV)
+    depth_a, prob_a = torch.empty(4 * H, 4 * W, device=DEV), torch.empty(4 * H, 4 * W, device=DEV)
+    ops.head_softargmin(dv, hidden=hidden, head_w=hw, head_b=hb, logits_out=logits_a, depth_out=depth_a, prob_out=prob_a, up=4)
+    logits_b = torch.full((D, H, W), float("nan"), device=DEV)
+    ops.conv3d(pc, x, None, precision=precision, head=(hw, hb, logits_b))
+    depth_b, prob_b = torch.empty_like(depth_a), torch.empty_like(prob_a)
+    ops.head_softargmin(dv, logits_in=logits_b, depth_out=depth_b, prob_out=prob_b, up=4)
+    want = (from_vol4(hidden.cpu()) * hw.cpu().view(16, 1, 1, 1)).sum(0) + hb.cpu()
+    assert (logits_b.cpu() - want).abs().max().item() < 2e-5
+    assert (logits_b - logits_a).abs().max().item() < 2e-5
+    assert (depth_b - depth_a).abs().max().item() < 1e-4 and (prob_b - prob_a).abs().max().item() < 1e-5
