@@ -30,6 +30,7 @@ class ConvDesc(ctypes.Structure):
         ("D", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int),
         ("in0_split", ctypes.c_int), ("in1_split", ctypes.c_int), ("res_split", ctypes.c_int), ("out_split", ctypes.c_int),
         ("head_w", c_void_p), ("head_b", c_void_p), ("head_out", c_void_p),
+        ("out_up2", ctypes.c_int),
     ]
 
 

@@ -223,6 +223,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             const int h = h0 + mh, w = w0 + 8 * mt + mw;
             const bool ok = (h < p.H) && (w < p.W);
             const size_t pos = ((size_t)d * p.H + h) * p.W + w;
+            // output addressing: the same map, or its nearest x2 up-sampled version [2H][2W]
+            const size_t ovox = ep.out_up2 ? 4 * vox : vox;
+            const size_t opos = ep.out_up2 ? ((size_t)d * 2 * p.H + 2 * h) * (2 * p.W) + 2 * w : pos;
+            const size_t orow = (size_t)2 * p.W * 4;               // floats per row of the up-sampled map
             float4 r0[4];
             auto load_res = [&](int c0) {
 #pragma unroll
@@ -290,9 +294,15 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 4; ++i) o[4 * j + i] = v[i] * ep.post_scale;
                     if (ep.out_split) continue;
+                    const float4 o4 = make_float4(o[4 * j + 0], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    if (ep.out_up2) {                                // nearest x2: the pixel's 2 x 2 block of the [2H][2W] map
+                        float* dst = ep.out0 + ((size_t)ch * ovox + opos) * 4;
+                        st4(dst, o4); st4(dst + 4, o4); st4(dst + orow, o4); st4(dst + orow + 4, o4);
+                        continue;
+                    }
                     const size_t off = ((size_t)ch * vox + pos) * 4;
                     float* dst = (ch < ep.out0_chunks) ? ep.out0 + off : ep.out1 + (off - (size_t)ep.out0_chunks * vox * 4);
-                    st4(dst, make_float4(o[4 * j + 0], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+                    st4(dst, o4);
                 }
                 if (ep.out_split) {
                     // vol4s: x_hi of 8 channels -> chunk c/4, x_lo -> the next chunk
@@ -302,9 +312,16 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                         if (!ok || ch >= ep.out_chunks) continue;
                         uint4 hi, lo;
                         split8(o + 8 * g, hi, lo, amax);
-                        float* dst = ep.out0 + ((size_t)ch * vox + pos) * 4;
-                        *reinterpret_cast<uint4*>(dst) = hi;
-                        *reinterpret_cast<uint4*>(dst + vox * 4) = lo;
+                        float* dst = ep.out0 + ((size_t)ch * ovox + opos) * 4;
+                        uint4* dh = reinterpret_cast<uint4*>(dst);
+                        uint4* dl = reinterpret_cast<uint4*>(dst + ovox * 4);
+                        *dh = hi; *dl = lo;
+                        if (ep.out_up2) {
+                            dh[1] = hi; dl[1] = lo;
+                            uint4* dh2 = reinterpret_cast<uint4*>(dst + orow);
+                            uint4* dl2 = reinterpret_cast<uint4*>(dst + ovox * 4 + orow);
+                            dh2[0] = hi; dh2[1] = hi; dl2[0] = lo; dl2[1] = lo;
+                        }
                     }
                 }
                 if (c0 + 16 < COUT) load_res(c0 + 16);
@@ -333,6 +350,7 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
     ESTD_REQUIRE(d->weight_tc && aligned16(d->weight_tc), "estd_conv3d(planar): needs a 16-byte aligned weight_tc");
     ESTD_REQUIRE(d->in1_chunks == 0 || (d->in0_chunks % 4) == 0, "estd_conv3d(planar): first input segment must hold a multiple of 4 chunks");
     ESTD_REQUIRE(!d->gn_partials && !d->res1, "estd_conv3d(planar): GroupNorm partial sums / second residual are not implemented for planar convolutions");
+    ESTD_REQUIRE(!d->out_up2 || !d->out1, "estd_conv3d(planar): an up-sampled output is one tensor");
     CUtensorMap map0, map1;
     int rc = make_vol4_tensor_map(&map0, d->in0, d->in0_chunks, d->D, d->H, d->W, S::HALO_W * 4, S::HALO_H, 1, 4);
     if (rc) return rc;

@@ -289,6 +289,7 @@ static int dispatch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_o
                      "estd_conv3d: pre-split (vol4s) tensors are implemented for the plane-ring and planar kernels only");
         ESTD_REQUIRE(!d->out_split || (!d->out1 && (d->out0_chunks % 2) == 0 && d->out0), "estd_conv3d: a pre-split output is one tensor with an even number of chunks");
         ESTD_REQUIRE((!d->in0_split || (d->in0_chunks % 2) == 0) && (!d->in1_split || (d->in1_chunks % 2) == 0), "estd_conv3d: pre-split inputs hold an even number of chunks");
+        ESTD_REQUIRE(!d->out_up2 || d->planar, "estd_conv3d: out_up2 is implemented for planar convolutions only");
         ESTD_REQUIRE(!d->head_out || (ring && d->cout_pad == 16 && d->head_w && d->head_b && !d->out_split && !d->out1),
                      "estd_conv3d: the fused logit head needs a plane-ring kernel with cout_pad 16, head_w and head_b");
         ESTD_REQUIRE(d->in0_chunks > 0 && d->in1_chunks >= 0 && (d->in1_chunks == 0 || d->in1), "estd_conv3d: bad input segments");

@@ -66,6 +66,7 @@ struct ConvEpilogue {
     int res_split, out_split;                   // vol4s residuals / output (include/estdepth_b200.h)
     int* status;                                // fp16 range flag (out_split)
     const float* head_w; const float* head_b; float* head_out;      // fused 1x1x1 logit head
+    int out_up2;                                                    // planar: nearest x2 up-sampled output
 };
 
 inline void fill_epilogue(ConvEpilogue* e, const estd_conv3d_desc* d) {
@@ -79,6 +80,7 @@ inline void fill_epilogue(ConvEpilogue* e, const estd_conv3d_desc* d) {
     e->res_split = d->res_split; e->out_split = d->out_split;
     e->status = d->status;
     e->head_w = d->head_w; e->head_b = d->head_b; e->head_out = d->head_out;
+    e->out_up2 = d->out_up2;
 }
 
 // ---- vol4s helpers: 8 channels of one voxel = 16 B of x_hi (8 x fp16) in chunk 2g + 16 B of x_lo in chunk 2g+1 ----

@@ -142,20 +142,23 @@ def _tag(t, split):
     return t
 
 
-def _run3x3(pcs, x4, out4=None, res4=None, dilation=1, in1=None, taps=9, post_scale=1.0, out_split=True):
+def _run3x3(pcs, x4, out4=None, res4=None, dilation=1, in1=None, taps=9, post_scale=1.0, out_split=True, up2=False):
     """One packed planar layer over vol4 maps [C/4, N, H, W, 4] (+ optional second input segment = torch.cat on channels).
 
     Activations between planar layers travel PRE-SPLIT (``out_split``, the default): the producer's epilogue writes the fp16
     x_hi | x_lo pair the consumer's tensor-core operands need, so the consumer skips its in-place split (a tenth of a stage's
     shared-memory traffic: 29 -> 26 us for 64->64 at 120x160x5, 87 -> 77 us for 128->128).  Inputs may be in either form (their
-    tag tells); layers whose output is read by something else than a planar layer pass ``out_split=False``."""
+    tag tells); layers whose output is read by something else than a planar layer pass ``out_split=False``.
+    ``up2``: the result is returned nearest-neighbour x2 up-sampled (hybrid_depth_decoder.py:11-14), written that way by the
+    layer's own epilogue instead of by a separate copy."""
     from . import ops
     pc = pcs[0]
     out_split = bool(out_split) and SPLIT_ACTIVATIONS and pc.out_chunks % 2 == 0
     if out4 is None:
-        out4 = torch.empty(pc.out_chunks, x4.shape[1], x4.shape[2], x4.shape[3], 4, device=x4.device, dtype=torch.float32)
+        f = 2 if up2 else 1
+        out4 = torch.empty(pc.out_chunks, x4.shape[1], f * x4.shape[2], f * x4.shape[3], 4, device=x4.device, dtype=torch.float32)
     ops.conv_planar(pc, x4, out4, res0=res4, dilation=dilation, in1=in1, taps=taps, post_scale=post_scale,
-                    in_split=(_is_split(x4), _is_split(in1)), res_split=_is_split(res4), out_split=out_split)
+                    in_split=(_is_split(x4), _is_split(in1)), res_split=_is_split(res4), out_split=out_split, out_up2=up2)
     return _tag(out4, out_split)
 
 
@@ -185,12 +188,6 @@ def _as_nchw(t):
 
 def _channels(t):
     return t.shape[0] * 4 if t.dim() == 5 else t.shape[1]
-
-
-def _up2_vol4(x4):
-    """nearest x2 upsampling of vol4 maps (hybrid_depth_decoder.py:11-14)."""
-    c, n, h, w, _ = x4.shape
-    return _tag(x4[:, :, :, None, :, None, :].expand(c, n, h, 2, w, 2, 4).reshape(c, n, 2 * h, 2 * w, 4), _is_split(x4))
 
 
 def _conv_bn(cin, cout, k, stride, pad, dilation):
@@ -547,12 +544,13 @@ class ContextDecoder2D(nn.Module):
         P = self._use_tc(maps[4], ("upconv_4_0", "upconv_4_1", "upconv_3_0", "upconv_3_1", "upconv_2_0", "upconv_2_1"))
         if P is not None and all(_channels(m) % 16 == 0 for m in maps[1:]):
             # same layers, planar tcgen05 kernel: torch.cat becomes a second input segment, activations stay in vol4
-            x = _run3x3(P["upconv_4_0"], _as_vol4(maps[4]))
-            x = _run3x3(P["upconv_4_1"], _up2_vol4(x), in1=_as_vol4(maps[3]))
-            x = _run3x3(P["upconv_3_0"], x)
-            x = _run3x3(P["upconv_3_1"], _up2_vol4(x), in1=_as_vol4(maps[2]))
-            x = _run3x3(P["upconv_2_0"], x)
-            x = _run3x3(P["upconv_2_1"], _up2_vol4(x), in1=_as_vol4(maps[1]), out_split=False)    # read by vol4_to_nchw / refine
+            # `upsample` (nearest x2) of upconv_N_0's output is written by that layer's epilogue (up2): no separate copy
+            x = _run3x3(P["upconv_4_0"], _as_vol4(maps[4]), up2=True)
+            x = _run3x3(P["upconv_4_1"], x, in1=_as_vol4(maps[3]))
+            x = _run3x3(P["upconv_3_0"], x, up2=True)
+            x = _run3x3(P["upconv_3_1"], x, in1=_as_vol4(maps[2]))
+            x = _run3x3(P["upconv_2_0"], x, up2=True)
+            x = _run3x3(P["upconv_2_1"], x, in1=_as_vol4(maps[1]), out_split=False)    # read by vol4_to_nchw / refine
             out = ops.vol4_to_nchw(x)
             out._estd_vol4 = x                  # refine() takes the vol4 copy (saves a layout pass)
             return out
@@ -571,11 +569,11 @@ class ContextDecoder2D(nn.Module):
         P = self._use_tc(semantic_vs, ("upconv_1_0", "upconv_1_1", "upconv_0_0", "upconv_0_1", "dispconv_1", "dispconv_0"))
         if P is not None and semantic_vs.shape[1] % 16 == 0 and skip_half.shape[1] % 16 == 0:
             # whole refinement on the planar tcgen05 kernel: cat -> second input segment, sigmoid * depth_max in the epilogue
-            x = _run3x3(P["upconv_1_0"], _as_vol4(semantic_vs), in1=ops.nchw_to_vol4(F.relu(fused_logits)))
-            x = _run3x3(P["upconv_1_1"], _up2_vol4(x), in1=ops.nchw_to_vol4(skip_half.contiguous()))
+            x = _run3x3(P["upconv_1_0"], _as_vol4(semantic_vs), in1=ops.nchw_to_vol4(F.relu(fused_logits)), up2=True)
+            x = _run3x3(P["upconv_1_1"], x, in1=ops.nchw_to_vol4(skip_half.contiguous()))
             d1 = _run3x3(P["dispconv_1"], x, post_scale=self.depth_max, out_split=False)  # [1 chunk, N, H/2, W/2, 4]
             depth_half = _up2(d1[0, ..., 0].unsqueeze(1))
-            x = _run3x3(P["upconv_0_1"], _up2_vol4(_run3x3(P["upconv_0_0"], x)))
+            x = _run3x3(P["upconv_0_1"], _run3x3(P["upconv_0_0"], x, up2=True))
             depth_full = _run3x3(P["dispconv_0"], x, post_scale=self.depth_max, out_split=False)[0, ..., 0].unsqueeze(1).contiguous()
             return depth_half, depth_full
         self._log_cudnn("refinement", semantic_vs)

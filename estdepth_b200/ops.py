@@ -403,7 +403,7 @@ def _even(n):
 
 
 def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, precision, planar=0, dilation=1,
-               in_split=(False, False), res_split=False, out_split=False, head=None):
+               in_split=(False, False), res_split=False, out_split=False, head=None, out_up2=False):
     chunks0, D, H, W, _ = in0.shape
     key = (precision, planar, dilation, in0.device.index)
     cache = pc._desc
@@ -436,6 +436,10 @@ def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, pr
         d.out1, d.out1_chunks = _act_ptr(out1), out1.shape[0]
     if d.out0_chunks + d.out1_chunks != (_even(pc.out_chunks) if out_split else pc.out_chunks):
         raise RuntimeError("conv3d: layer produces %d chunks, outputs hold %d" % (pc.out_chunks, d.out0_chunks + d.out1_chunks))
+    if out_up2:
+        if not planar or out1 is not None or tuple(out0.shape[1:]) != (D, 2 * H, 2 * W, 4):
+            raise RuntimeError("conv: an up-sampled output needs a planar layer and one [chunks, N, 2H, 2W, 4] tensor")
+        d.out_up2 = 1
     if head is not None:
         if planar or pc.cout_pad_tc != 16 or gn_partials is not None:
             raise RuntimeError("conv3d: the fused logit head needs a 16-channel 3x3x3 layer")
@@ -481,12 +485,13 @@ def conv3d(pc, in0, out0, in1=None, out1=None, res0=None, res1=None, post_scale=
 
 
 def conv_planar(pc, in0, out0, res0=None, dilation=1, in1=None, taps=9, post_scale=1.0,
-                in_split=(False, False), res_split=False, out_split=False):
+                in_split=(False, False), res_split=False, out_split=False, out_up2=False):
     """2-D 3x3 (taps=9; stride 1, padding = dilation) or 1x1 (taps=1) convolution over a stack of N maps held as vol4
     [C/4,N,H,W,4], with folded affine + activation (+ residual), on the tensor cores (fp16 two-term split).  Returns out0.
-    ``in_split`` / ``res_split`` / ``out_split``: pre-split (vol4s) tensors, as for ``conv3d``."""
+    ``in_split`` / ``res_split`` / ``out_split``: pre-split (vol4s) tensors, as for ``conv3d``; ``out_up2``: out0 is
+    [C/4,N,2H,2W,4] and receives the result nearest-neighbour x2 up-sampled."""
     d = _conv_desc(pc, in0, in1, out0, None, res0, None, post_scale, None, "3xf16", planar=1 if taps == 9 else 2, dilation=dilation,
-                   in_split=in_split, res_split=res_split, out_split=out_split)
+                   in_split=in_split, res_split=res_split, out_split=out_split, out_up2=out_up2)
     t = _pb()
     check(_lib.get().estd_conv3d(ctypes.byref(d), _stream()), "estd_conv3d(planar)")
     vox = float(d.D) * d.H * d.W

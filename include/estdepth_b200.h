@@ -161,6 +161,10 @@ typedef struct estd_conv3d_desc {
      * convolution; plane-ring kernels with cout_pad 16 only): head_out[d][h][w] = sum_c head_w[c] * y[c] + head_b[0] of the
      * finished 16 channels y.  With head_out set, out0 may be NULL (the 16-channel volume is then never written). */
     const float* head_w; const float* head_b; float* head_out;
+    /* planar kernels only: write the result nearest-neighbour x2 up-sampled (hybrid_depth_decoder.py:11-14 `upsample`, applied
+     * to the output of upconv_4_0 / 3_0 / 2_0 / 1_0 / 0_0 before the next layer): out0 is [chunks][D][2H][2W][4] and every
+     * pixel is stored to its 2 x 2 block -- the up-sampled map is never produced by a separate copy. */
+    int out_up2;
 } estd_conv3d_desc;
 
 /* number of CTAs estd_conv3d will launch for this shape == rows of gn_partials the caller must provide */

@@ -236,15 +236,17 @@ def plane_sweep_grid(src_proj, ref_proj, depth_values, H, W, homo12=None):
     return xn, yn
 
 
-def homo_warp(src_fea, src_proj, ref_proj, depth_values, sampler="aten", homo12=None):
-    """utils/homo_utils.py:458-504.  src_fea [1,C,H,W] -> [1,C,D,H,W]."""
+def homo_warp(src_fea, src_proj, ref_proj, depth_values, sampler="aten", homo12=None, align_corners=False):
+    """utils/homo_utils.py:458-504.  src_fea [1,C,H,W] -> [1,C,D,H,W].  ``align_corners``: the grid_sample convention; False =
+    what the reference computes under torch >= 1.3 (and what the fixtures pin), True = the torch 1.2 it was written for (Q1)."""
     _, C, H, W = src_fea.shape
     D = depth_values.numel()
     xn, yn = plane_sweep_grid(src_proj[0], ref_proj[0], depth_values.reshape(-1), H, W, homo12)
     if sampler == "aten":
         grid = torch.stack((xn, yn), dim=2).view(1, D * H, W, 2)
-        out = F.grid_sample(src_fea, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+        out = F.grid_sample(src_fea, grid, mode="bilinear", padding_mode="zeros", align_corners=align_corners)
         return out.view(1, C, D, H, W)
+    assert not align_corners, "the explicit sampler restates align_corners=False only"
     return bilinear_zeros(src_fea[0], xn.view(D, H, W), yn.view(D, H, W)).unsqueeze(0)
 
 
@@ -278,14 +280,15 @@ def volume_warp_grid(rel_pose, cam_intr, depth_values, D, H, W, depth_min, depth
     return xn, yn, zn
 
 
-def warp_volume(vol, rel_pose, cam_intr, depth_values, depth_min, depth_interval, sampler="aten", table30=None):
+def warp_volume(vol, rel_pose, cam_intr, depth_values, depth_min, depth_interval, sampler="aten", table30=None, align_corners=False):
     """utils/homo_utils.py:240-279, zeros padding.  vol [1,C,D,H,W] -> same shape."""
     _, C, D, H, W = vol.shape
     xn, yn, zn = volume_warp_grid(rel_pose[0], cam_intr[0], depth_values.reshape(-1), D, H, W, depth_min, depth_interval,
                                   table30)
     if sampler == "aten":
         grid = torch.stack((xn, yn, zn), dim=2).view(1, D, H, W, 3)
-        return F.grid_sample(vol, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+        return F.grid_sample(vol, grid, mode="bilinear", padding_mode="zeros", align_corners=align_corners)
+    assert not align_corners, "the explicit sampler restates align_corners=False only"
     return trilinear_zeros(vol[0], xn.view(D, H, W), yn.view(D, H, W), zn.view(D, H, W)).unsqueeze(0)
 
 
@@ -293,7 +296,7 @@ def warp_volume(vol, rel_pose, cam_intr, depth_values, depth_min, depth_interval
 # cost volume (row a4/a6), matching net (a8), soft-argmin (a9), EST fusion (a11)
 # ----------------------------------------------------------------------------------------------
 
-def cost_volume(sd, feats, poses, cam_intr, depth_values, sampler="aten", taps=None, homo=None):
+def cost_volume(sd, feats, poses, cam_intr, depth_values, sampler="aten", taps=None, homo=None, align_corners=False):
     """hybrid_models/model_hybrid.py:62-102.  feats: 3 maps [1,32,H,W]; poses [1,3,4,4]; middle = target.
     ``homo`` (test hook): [2, 12] precomputed [rot | trans] of the two sources (see plane_sweep_grid)."""
     ref = feats[1]
@@ -306,7 +309,7 @@ def cost_volume(sd, feats, poses, cam_intr, depth_values, sampler="aten", taps=N
         src_proj, ref_proj = src_ext.clone(), ref_ext.clone()
         src_proj[:, :3, :4] = cam_intr @ src_ext[:, :3, :4]
         ref_proj[:, :3, :4] = cam_intr @ ref_ext[:, :3, :4]
-        warped = homo_warp(feats[v], src_proj, ref_proj, depth_values, sampler, None if homo is None else homo[v // 2])
+        warped = homo_warp(feats[v], src_proj, ref_proj, depth_values, sampler, None if homo is None else homo[v // 2], align_corners)
         x = _cb3(torch.cat([ref_volume, warped], 1), sd, "pre0")
         if taps is not None:
             taps.setdefault("x0", []).append(x)
@@ -385,7 +388,8 @@ def depth_planes(cfg):
     return torch.arange(0, cfg["ndepths"]).to(torch.float32) * interval + cfg["depth_min"], interval
 
 
-def forward(sd, cfg, imgs, cam_poses, cam_intr, pre_costs=None, pre_cam_poses=None, sampler="aten", taps=None, geometry=None):
+def forward(sd, cfg, imgs, cam_poses, cam_intr, pre_costs=None, pre_cam_poses=None, sampler="aten", taps=None, geometry=None,
+            align_corners=False):
     """``DepthNetHybrid.forward(..., mode='val')`` (model_hybrid.py:110-184 + hybrid_depth_decoder.py:138-432).
 
     cfg = dict(ndepths, depth_min, depth_max, resnet, est=True).  imgs [1,V,3,H,W] in 0..255,
@@ -396,6 +400,7 @@ def forward(sd, cfg, imgs, cam_poses, cam_intr, pre_costs=None, pre_cam_poses=No
     matrices of the two warps computed elsewhere (layout of estdepth_b200.ops.homography_table_torch /
     volume_warp_tables_torch), used instead of this function's own ``torch.inverse`` products; everything downstream
     of the matrices is unchanged.  Lets a test hand the CPU oracle the matrices a GPU's LU produced.
+    ``align_corners``: grid_sample convention of both warps (quirk Q1); False = the reference as it runs today.
     """
     assert imgs.shape[0] == 1, "the reference (and this oracle) run at B=1 (quirk Q16)"
     imgs = 2 * (imgs / 255.) - 1.
@@ -411,7 +416,7 @@ def forward(sd, cfg, imgs, cam_poses, cam_intr, pre_costs=None, pre_cam_poses=No
     K4[:, :2, :] *= 0.25                                                      # scale_cam_intr :104-108
     depth_values, interval = depth_planes(cfg)
     cvs = [cost_volume(sd, feats[t:t + 3], cam_poses[:, t:t + 3], K4, depth_values, sampler, taps,
-                       None if geometry is None else geometry["homo"][2 * t:2 * t + 2]) for t in range(T)]
+                       None if geometry is None else geometry["homo"][2 * t:2 * t + 2], align_corners) for t in range(T)]
     poses = [cam_poses[:, t + 1] for t in range(T)]
     if taps is not None:
         taps["features"] = feats
@@ -444,8 +449,8 @@ def forward(sd, cfg, imgs, cam_poses, cam_intr, pre_costs=None, pre_cam_poses=No
                     continue
                 rel = poses[j] @ torch.inverse(poses[i])                         # quirk Q7 (:235)
                 tab = None if geometry is None else geometry["warp"][i][len(wk)]
-                wk.append(warp_volume(keys[j], rel, K4, depth_values, cfg["depth_min"], interval, sampler, tab))
-                wv.append(warp_volume(values[j], rel, K4, depth_values, cfg["depth_min"], interval, sampler, tab))
+                wk.append(warp_volume(keys[j], rel, K4, depth_values, cfg["depth_min"], interval, sampler, tab, align_corners))
+                wv.append(warp_volume(values[j], rel, K4, depth_values, cfg["depth_min"], interval, sampler, tab, align_corners))
             fused = est_fuse(sd, keys[i], wk, values[i], wv)
             if taps is not None:
                 taps.setdefault("h", []).append(est_attention(keys[i], wk, wv))

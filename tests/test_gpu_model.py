@@ -219,3 +219,31 @@ def test_merged_pre2_equals_two_pre2_convolutions():
             d = float((out_m[key] - out_s[key]).abs().max())
             assert d < (2e-4 if key[0] == "depth" else 5e-5), (key, d)
         assert float((state_m["values"][0] - state_s["values"][0]).abs().max()) < 1e-4
+
+
+def test_as_trained_align_corners_mode_end_to_end():
+    """Quirk Q1 / SURVEY 8f rank 4: the reference was written for torch 1.2, where grid_sample was corner-aligned; a real
+    checkpoint reproduces the paper's accuracy only in that mode.  ``DepthNetHybrid(align_corners=True)`` against the oracle
+    with both warps switched to align_corners=True, both Joint windows (plane-sweep warp and EST volume warp), same gates."""
+    torch.backends.cudnn.allow_tf32 = False
+    model, sd = synth_model_and_state(18, 32)
+    model.align_corners = True
+    model.cuda()
+    cfg = cfg_of(18, 32)
+    state = pstate = ostate = opstate = None
+    worst = {}
+    for start in (0, 3):
+        imgs, poses, K, sample = synth.synth_inputs(5, 128, 160, seed=0, start=start)
+        outputs, state, pstate = model(imgs.cuda(), poses, K, sample, state, pstate, mode="val")
+        with torch.no_grad():
+            want, ostate, opstate = orc.forward(sd, cfg, imgs, poses, K, ostate, opstate, align_corners=True)
+            plain = orc.forward(sd, cfg, imgs, poses, K, None, None)[0] if start == 0 else None
+        for key, val in outputs.items():
+            d = (val.cpu() - want[key]).abs().max().item()
+            tag = "depth%d" % key[2] if key[0] == "depth" else key[0]
+            worst[tag] = max(worst.get(tag, 0.0), d)
+            assert d < (DEPTH_TOL if key[0] == "depth" else 2e-4), (start, key, d)
+        if plain is not None:       # the two conventions really differ (by far more than the gate)
+            assert (want[("depth", 1, 2)] - plain[("depth", 1, 2)]).abs().max().item() > 10 * DEPTH_TOL
+        assert (state["values"][0].cpu() - ostate["values"][0]).abs().max().item() < STATE_TOL
+    print("align_corners=True end to end vs oracle(align_corners=True):", {k: "%.1e" % v for k, v in sorted(worst.items())})

@@ -565,6 +565,25 @@ def test_conv_planar_presplit_tensors_equal_fp32_tensors():
     assert torch.equal(mixed, plain)
 
 
+@pytest.mark.parametrize("split", [False, True])
+def test_conv_planar_upsampled_output_equals_nearest_interpolate(split):
+    """`upsample` of hybrid_depth_decoder.py:11-14 (F.interpolate(scale_factor=2, mode="nearest")) written by the producing
+    layer's epilogue: bit-identical to the plain output replicated 2 x 2, in fp32 and in pre-split form."""
+    g = torch.Generator().manual_seed(8)
+    N, H, W, cin, cout = 3, 15, 20, 64, 64
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    pc = packing.pack_conv2d(w, torch.ones(cout), torch.randn(cout, generator=g) / 3, "relu", DEV)[0]
+    x4 = ops.nchw_to_vol4(x.to(DEV))
+    plain = ops.conv_planar(pc, x4, torch.empty(cout // 4, N, H, W, 4, device=DEV), out_split=split)
+    up = ops.conv_planar(pc, x4, torch.full((cout // 4, N, 2 * H, 2 * W, 4), float("nan"), device=DEV), out_split=split, out_up2=True)
+    want = plain[:, :, :, None, :, None, :].expand(-1, -1, -1, 2, -1, 2, -1).reshape(cout // 4, N, 2 * H, 2 * W, 4)
+    assert torch.equal(up, want)
+    if not split:
+        ref = F.interpolate(ops.vol4_to_nchw(plain), scale_factor=2, mode="nearest")
+        assert torch.equal(ops.vol4_to_nchw(up), ref)
+
+
 @pytest.mark.parametrize("precision", ["3xf16r", "3xf16r2"])
 def test_fused_logit_head_equals_head_conv_then_1x1x1(precision):
     """stereo_head: Conv3d(16,16,3)+BN+ReLU then Conv3d(16,1,1,bias) (hybrid_depth_decoder.py:104-112): the logit computed in the
