@@ -294,7 +294,7 @@ static int dispatch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_o
                      "estd_conv3d: the fused logit head needs a plane-ring kernel with cout_pad 16, head_w and head_b");
         ESTD_REQUIRE(d->in0_chunks > 0 && d->in1_chunks >= 0 && (d->in1_chunks == 0 || d->in1), "estd_conv3d: bad input segments");
         ESTD_REQUIRE(d->out0_chunks > 0 && d->out1_chunks >= 0 && (d->out1_chunks == 0 || d->out1), "estd_conv3d: bad output segments");
-        ESTD_REQUIRE((d->out0_chunks + d->out1_chunks) * 4 <= d->cout_pad, "estd_conv3d: outputs exceed cout_pad");
+        ESTD_REQUIRE((d->out0_chunks + d->out1_chunks) * 4 <= (d->cout_pad + 15) / 16 * 16, "estd_conv3d: outputs exceed cout_pad");
         ESTD_REQUIRE(d->act_split >= 0 && (d->act_split % 8) == 0, "estd_conv3d: act_split must be a multiple of 8");
         ESTD_REQUIRE(d->planar || (d->act_lo < ESTD_ACT_ADD_RELU && d->act_hi < ESTD_ACT_ADD_RELU), "estd_conv3d: ESTD_ACT_ADD_RELU / ESTD_ACT_SIGMOID are implemented for planar convolutions only");
         ESTD_REQUIRE(aligned16(d->in0) && (!d->out0 || aligned16(d->out0)) && (!d->weight || aligned16(d->weight)) && (!d->in1 || aligned16(d->in1)) &&

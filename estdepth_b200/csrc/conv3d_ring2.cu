@@ -39,7 +39,10 @@ struct Shape {
     static constexpr int HALO_H = TILE_H + 2, HALO_W = TILE_W + 2, HALO_VOX = HALO_H * HALO_W;
     static constexpr int KGROUP_BYTES = HALO_VOX * 16;
     static constexpr int A_BYTES = 4 * KGROUP_BYTES;
-    static constexpr int N3 = 3 * COUT;                           // N of the MMA = accumulator columns of one M tile
+    // N of the MMA = accumulator columns of one M tile: three slots of COUT columns each, rounded up to the MMA's granularity
+    // (COUT = 33: 99 -> 112; the 13 extra columns belong to zero weight rows and are never read)
+    static constexpr int N3 = (3 * COUT + 15) / 16 * 16;
+    static constexpr int SHIFT_N = (COUT + 15) / 16 * 16;         // per-channel offsets kept in shared memory
     static constexpr int NH = N3 / 2;                             // weight rows held by one CTA of the pair
     static constexpr int W_PART_BYTES = 2 * NH * 16;              // [2 K-groups][NH rows][16 B] of w_hi (or w_lo)
     static constexpr int W_TAP_BYTES = 2 * W_PART_BYTES;
@@ -51,7 +54,7 @@ struct Shape {
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;
     static_assert(COLS <= 512, "ring accumulators must fit TMEM");
     static_assert(SMEM + 2048 <= 227 * 1024, "stages must fit shared memory");
-    static_assert(COUT % 16 == 0 && COUT <= 48 && N3 <= 256 && N3 % 16 == 0 && (MT == 2 || MT == 4), "bad shape");
+    static_assert(COUT % 16 <= 1 && COUT <= 48 && N3 <= 256 && N3 % 16 == 0 && (MT == 2 || MT == 4), "bad shape");
 };
 
 
@@ -106,7 +109,7 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
     uint64_t* acc_empty = acc_full + 2;     // [2 halves] (rank 0's copy is used) both CTAs have drained and zeroed the slot
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
     __shared__ double s_red[EPI_WARPS][4];
-    __shared__ __align__(16) float s_shift[COUT];                    // per-channel offset; the per-channel multiplier is folded into the weights
+    __shared__ __align__(16) float s_shift[S::SHIFT_N];              // per-channel offset; the per-channel multiplier is folded into the weights
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = cluster_ctarank();
@@ -118,7 +121,7 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc2(tmem_base_smem, S::TMEM_COLS);
-    if (warp == 3) for (int i = lane; i < COUT; i += 32) s_shift[i] = p.ep.shift[i];
+    if (warp == 3) for (int i = lane; i < S::SHIFT_N; i += 32) s_shift[i] = p.ep.shift[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -405,6 +408,7 @@ int dispatch_ring2(const estd_conv3d_desc* d, cudaStream_t stream, bool count_on
     ESTD_REQUIRE(!d->planar && (d->dilation == 0 || d->dilation == 1), "estd_conv3d(ring2): 3x3x3, dilation 1 only");
 #define ESTD_RING2(NKS, COUT, MT) if (nks == NKS && d->cout_pad == COUT) return launch<Shape<NKS, COUT, MT>>(d, stream, count_only, n_ctas)
     ESTD_RING2(2, 32, 4); ESTD_RING2(3, 32, 4); ESTD_RING2(1, 16, 4); ESTD_RING2(2, 16, 4); ESTD_RING2(3, 48, 2);
+    ESTD_RING2(3, 33, 4);         // dres2 (36 -> 33 channels): 33-column slots, N = 112, so that 4 M tiles fit TMEM (448 columns)
 #undef ESTD_RING2
     return fail(ESTD_EUNSUPPORTED, "estd_conv3d(ring2): no kernel for %d input chunks -> cout_pad %d", cin_chunks, d->cout_pad);
 }

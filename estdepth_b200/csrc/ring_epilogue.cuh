@@ -12,8 +12,19 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
                  ::"r"(taddr), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// one 32-bit column (the 33rd channel of a 33-channel slot)
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_st1_zero(uint32_t taddr) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(0u) : "memory");
+}
 
-// The accumulator slot at TMEM address t0 (COUT columns, this thread's lane = its voxel) is complete.
+// The accumulator slot at TMEM address t0 (COUT columns, this thread's lane = its voxel) is complete.  COUT is a multiple of 16,
+// or a multiple of 16 plus ONE (the 33-channel layer dres2, hybrid_depth_decoder.py:90: its slots are 33 columns wide so that
+// the three of them fit N = 112 instead of 3 x 48 = 144).
 //   1. TMEM -> registers, zero the slot, hand it back to the MMA issuer (hand_back());
 //   2. only then: * mult + shift -> activation -> residuals -> post_scale -> GroupNorm partial sums -> 16-byte stores.
 // The order matters: the issuer needs the slot back within the time the tensor core spends on the other half tile, and every
@@ -24,12 +35,17 @@ __device__ __forceinline__ void ring_drain_slot(const ConvEpilogue& ep, const fl
                                                 size_t pos, size_t vox, bool want_gn, double (&gs)[2], double (&gq)[2],
                                                 HandBack&& hand_back) {
     constexpr int NB = COUT / 16;
+    constexpr bool XTRA = (COUT % 16) != 0;
+    static_assert(COUT % 16 <= 1, "a slot holds a multiple of 16 channels, plus at most one");
     float acc[NB][16];
+    float accx = 0.0f;
 #pragma unroll
     for (int b = 0; b < NB; ++b) tmem_ld16(t0 + (uint32_t)(16 * b), acc[b]);
+    if constexpr (XTRA) accx = tmem_ld1(t0 + (uint32_t)(16 * NB));
     tmem_ld_wait();
 #pragma unroll
     for (int b = 0; b < NB; ++b) tmem_st16_zero(t0 + (uint32_t)(16 * b));
+    if constexpr (XTRA) tmem_st1_zero(t0 + (uint32_t)(16 * NB));
     tmem_st_wait();
     tc_fence_before();
     hand_back();
@@ -133,6 +149,37 @@ __device__ __forceinline__ void ring_drain_slot(const ConvEpilogue& ep, const fl
         if (want_gn) {
             gs[0] += (double)ts[0]; gq[0] += (double)tq[0];
             gs[1] += (double)ts[1]; gq[1] += (double)tq[1];
+        }
+    }
+    if constexpr (XTRA) {
+        // the one channel beyond the 16-channel blocks: c = 16 * NB, first element of chunk c / 4 (the rest of that chunk is padding)
+        constexpr int c = 16 * NB;
+        const int ch = c >> 2;
+        const int act = (c < ep.act_split) ? ep.act_lo : ep.act_hi;
+        float v = fmaf(accx, mult, s_shift[c]);
+        if (act == ESTD_ACT_RELU) v = fmaxf(v, 0.0f); else if (act == ESTD_ACT_TANH) v = tanhf(v);
+        if (ok && ch < ep.out_chunks) {
+            const size_t off = ((size_t)ch * vox + pos) * 4;
+            if (ep.res0) {
+                if (ep.res_split) { float t[8]; join8(ldg4(ep.res0 + off), ldg4(ep.res0 + off + vox * 4), t); v += t[0]; }
+                else v += __ldg(ep.res0 + off);
+            }
+            if (ep.res1) {
+                if (ep.res_split) { float t[8]; join8(ldg4(ep.res1 + off), ldg4(ep.res1 + off + vox * 4), t); v += t[0]; }
+                else v += __ldg(ep.res1 + off);
+            }
+            v *= ep.post_scale;
+            if (want_gn) { const int grp = (c < ep.act_split) ? 0 : 1; gs[grp] += (double)v; gq[grp] += (double)v * (double)v; }
+            if (ep.out_split) {
+                const float v8[8] = {v, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                uint4 hi, lo;
+                split8(v8, hi, lo, amax);
+                *reinterpret_cast<uint4*>(ep.out0 + off) = hi;
+                *reinterpret_cast<uint4*>(ep.out0 + off + vox * 4) = lo;
+            } else if (ep.out0) {
+                float* dst = (ch < ep.out0_chunks) ? ep.out0 + off : ep.out1 + (off - (size_t)ep.out0_chunks * vox * 4);
+                st4(dst, make_float4(v, 0.f, 0.f, 0.f));
+            }
         }
     }
     if (ep.out_split && !(amax <= 65504.0f) && ep.status) atomicOr(ep.status, 1);

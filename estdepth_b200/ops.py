@@ -270,13 +270,14 @@ class PackedConv(object):
     """Folded, packed parameters of one 3x3x3 layer (see packing.pack_conv3d)."""
     __slots__ = ("weight", "scale", "shift", "cin_chunks", "cout_pad", "out_chunks", "act_split", "act_lo", "act_hi",
                  "cin", "cout", "weight_tc", "cout_pad_tc", "weight_f16", "scale_f16", "weight_ring", "weight_ring2", "scale_ring", "_desc",
-                 "precision")
+                 "precision", "cout_pad_ring2")
 
     def __init__(self, weight, scale, shift, cin_chunks, cout_pad, out_chunks, act_split, act_lo, act_hi,
                  cin=None, cout=None, weight_tc=None, cout_pad_tc=None):
         self.weight, self.scale, self.shift = weight, scale, shift
         self._desc = None                                              # per-(arithmetic, mode) descriptor templates (_conv_desc)
         self.precision = None                                          # per-layer arithmetic override (None: the caller's choice)
+        self.cout_pad_ring2 = None                                     # columns per ring slot of a narrow layer's CTA-pair packing
         self.weight_tc, self.cout_pad_tc = weight_tc, cout_pad_tc      # tcgen05 packings (packing.attach_tc)
         self.weight_f16, self.scale_f16 = None, None
         self.weight_ring = None                                        # plane-ring packing (packing.pack_weight_ring)
@@ -393,6 +394,8 @@ def _desc_template(pc, precision, planar, dilation, device):
     ring = precision in ("3xf16r", "3xf16r2")
     d.scale, d.shift = _ptr(pc.scale_ring if ring else pc.scale_f16 if f16 else pc.scale), _ptr(pc.shift)
     d.cout_pad = pc.cout_pad_tc if tc else pc.cout_pad
+    if precision == "3xf16r2" and pc.cout_pad_ring2 is not None:
+        d.cout_pad = pc.cout_pad_ring2
     d.status = _ptr(status_flag(device), torch.int32) if f16 else None
     d.act_split, d.act_lo, d.act_hi = pc.act_split, pc.act_lo, pc.act_hi
     return bytes(d)
@@ -458,6 +461,8 @@ def conv3d_num_ctas(pc, D, H, W, precision=None):
     d.precision = PRECISION[precision]
     d.in0_chunks, d.in1_chunks = pc.cin_chunks, 0
     d.cout_pad = pc.cout_pad_tc if precision != "fp32" else pc.cout_pad
+    if precision == "3xf16r2" and pc.cout_pad_ring2 is not None:
+        d.cout_pad = pc.cout_pad_ring2
     d.D, d.H, d.W = D, H, W
     n = _lib.get().estd_conv3d_num_ctas(ctypes.byref(d))
     if n < 0:

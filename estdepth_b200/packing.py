@@ -155,7 +155,10 @@ def pack_weight_ring(packed, cout_pad_tc=None, scale=None):
 RING2_SHAPES = ((2, 32), (3, 32), (1, 16), (2, 16), (3, 48))
 
 
-def pack_weight_ring2(packed, cout_pad_tc=None, scale=None):
+RING2_COMPACT = {(3, 48): 33}    # (k-steps, cout_pad_tc) -> columns per ring slot when the layer's real width allows fewer
+
+
+def pack_weight_ring2(packed, cout_pad_tc=None, scale=None, cslot=None):
     """SIMT packing [27][cin_pad][cout_pad] -> CTA-pair ring packing of conv3d_ring2.cu,
     [7 live-tap masks][3 rotations][nks][2 CTAs][9 taps][hi,lo][2 K-groups][3*C/2 rows][8 x fp16] (float32-typed bytes)
     + the power-of-two exponent of ``pack_weight_f16``.
@@ -163,7 +166,11 @@ def pack_weight_ring2(packed, cout_pad_tc=None, scale=None):
     Rotation r orders the rows by ring slot exactly like ``pack_weight_ring`` (slot j <- depth tap (r - j + 1) mod 3);
     variant ``mask - 1`` zeroes the taps whose bit is clear in ``mask`` (bit kd: output plane z + 1 - kd belongs to the
     CTA pair's range), so that partial first / last planes issue the same full-N MMA; CTA 0 of the pair holds rows
-    [0, 3C/2), CTA 1 rows [3C/2, 3C)."""
+    [0, 3C/2), CTA 1 rows [3C/2, 3C).
+
+    ``cslot`` (default C): rows per ring slot.  A layer with fewer real output channels than its padded width packs only
+    ``cslot`` rows per slot and pads the TOTAL to a multiple of 16 -- the 33-channel layer dres2 (hybrid_depth_decoder.py:90)
+    gets N = 112 instead of 3 x 48 = 144: a fifth fewer tensor-core cycles, and 4 M tiles instead of 2 fit TMEM."""
     taps, cin_pad, cout_pad = packed.shape
     assert taps == 27
     C = tc_cout_pad(cout_pad) if cout_pad_tc is None else cout_pad_tc
@@ -184,14 +191,19 @@ def pack_weight_ring2(packed, cout_pad_tc=None, scale=None):
         return x.reshape(3, 9, nks, 2, 8, C).permute(0, 2, 1, 3, 5, 4)
 
     parts = torch.stack([arrange(hi), arrange(lo)], dim=3)                    # [kd][ks][tap9][prod][kg][C][e]
+    cslot = C if cslot is None else int(cslot)
+    assert cout_pad <= cslot <= C
+    parts = parts[:, :, :, :, :, :cslot]
     zero = torch.zeros_like(parts[0])
-    NH = 3 * C // 2
+    n_rows = (3 * cslot + 15) // 16 * 16                                      # N of the MMA
+    NH = n_rows // 2
+    pad = torch.zeros(nks, 9, 2, 2, n_rows - 3 * cslot, 8, dtype=parts.dtype, device=parts.device)
     variants = []
     for mask in range(1, 8):
         rots = []
         for r in range(3):
             slots = [parts[(r - j + 1) % 3] if (mask >> ((r - j + 1) % 3)) & 1 else zero for j in range(3)]
-            full = torch.cat(slots, dim=4)                                    # [ks][tap9][prod][kg][3C][e]
+            full = torch.cat(slots + [pad], dim=4)                            # [ks][tap9][prod][kg][N][e]
             halves = full.reshape(nks, 9, 2, 2, 2, NH, 8).permute(0, 4, 1, 2, 3, 5, 6)      # [ks][half][tap9][prod][kg][NH][e]
             rots.append(halves)
         variants.append(torch.stack(rots, dim=0))
@@ -210,7 +222,13 @@ def attach_tc(pc):
     pc.scale_f16 = (pc.scale * (2.0 ** -k)).contiguous()
     nks = (pc.weight.shape[1] + 15) // 16
     if pc.weight.shape[0] == 27 and (nks, pc.cout_pad_tc) in RING2_SHAPES:
-        pc.weight_ring2, k_ring2 = pack_weight_ring2(pc.weight, pc.cout_pad_tc, pc.scale)
+        cslot = RING2_COMPACT.get((nks, pc.cout_pad_tc))
+        if cslot is not None and pc.cout <= cslot and pc.weight.shape[2] <= cslot + 7:
+            # narrow layer: `cslot` columns per ring slot (conv3d_ring2.cu Shape<3, 33, 4>); the kernel is selected by cout_pad
+            pc.cout_pad_ring2 = cslot
+            pc.weight_ring2, k_ring2 = pack_weight_ring2(pc.weight[:, :, :cslot].contiguous(), pc.cout_pad_tc, pc.scale, cslot=cslot)
+        else:
+            pc.weight_ring2, k_ring2 = pack_weight_ring2(pc.weight, pc.cout_pad_tc, pc.scale)
     if pc.weight.shape[0] == 27 and (nks, pc.cout_pad_tc) in RING_SHAPES:
         pc.weight_ring, k_ring = pack_weight_ring(pc.weight, pc.cout_pad_tc, pc.scale)
         assert pc.weight_ring2 is None or k_ring2 == k_ring
