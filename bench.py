@@ -640,14 +640,16 @@ def run_ours(args):
     conv_name = "conv3d_" + model.precision
     dom = max(((k, v) for k, v in kernels.items() if "share_ms_per_step" in v), key=lambda kv: kv[1]["share_ms_per_step"])
     conv = kernels.get(conv_name, dom[1])
-    mma_per_flop = {"fp32": 0.0, "3xtf32": 3.0, "3xf16": 3.0, "3xf16r": 3.0, "3xf16r2": 3.0}[model.precision]
+    mma_per_flop = {"fp32": 0.0}.get(model.precision, 3.0)
     # dram__bytes_read.sum + dram__bytes_write.sum of one 32->32 launch at cfg2 size from the committed ncu --set full capture
     # (profiles/kernels_r01_final.txt): CTA-pair kernel 217.5 + 115.2 MB against 314.6 MB algorithmic (157.3 MB read + 157.3 MB
     # written; the reads carry the 18x34 / 16x32 halo, part of the output is still in L2 when the kernel ends)
     traffic = {"3xf16r2": 332.6e6, "3xf16r": 375.8e6}.get(model.precision) if args.workload == "cfg2" else None
     kname = {"3xf16r": "estd::ring::conv3d_ring_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule, fp16 two-term split)",
              "3xf16r2": "estd::ring2::conv3d_ring2_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule on CTA pairs / "
-                        "cta_group::2, fp16 two-term split)"}.get(model.precision, "estd conv3d kernel (%s)" % model.precision)
+                        "cta_group::2, fp16 two-term split)",
+             "3xf16r2d": "estd::ring2::conv3d_ring2_kernel, two accumulators per ring slot (3x3x3 implicit GEMM on tcgen05, plane-ring "
+                         "schedule on CTA pairs / cta_group::2, fp16 two-term split)"}.get(model.precision, "estd conv3d kernel (%s)" % model.precision)
     achieved = conv.get("TFLOPps") or 0.0
     roofline = {"kernel": kname if conv_name in kernels else dom[0], "bound": "tensor",
                 "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
@@ -689,7 +691,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=None, choices=["fp32", "3xtf32", "3xf16", "3xf16r", "3xf16r2"], help="conv3d arithmetic (default: the model's)")
+    ap.add_argument("--precision", default=None, choices=["fp32", "3xtf32", "3xf16", "3xf16r", "3xf16r2", "3xf16r2d"], help="conv3d arithmetic (default: the model's)")
     ap.add_argument("--geometry", default=None, choices=["auto", "torch", "fp64"], help="camera-matrix derivation (default: the model's)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~1 min oracle timing on the host cores")
     ap.add_argument("--no-extras", action="store_true", help="skip the extras (cfg3 / cfg4 / cfg5 / PyTorch-CUDA baseline / clip pipeline)")

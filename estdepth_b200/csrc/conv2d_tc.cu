@@ -385,7 +385,7 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
 
 int dispatch_planar(const estd_conv3d_desc* d, cudaStream_t stream, bool count_only, int* n_ctas) {
     using namespace planar;
-    ESTD_REQUIRE(d->precision == ESTD_PREC_3XF16 || d->precision == ESTD_PREC_3XF16_RING,
+    ESTD_REQUIRE(d->precision == ESTD_PREC_3XF16 || d->precision == ESTD_PREC_3XF16_RING || d->precision == ESTD_PREC_3XF16_RING2D,
                  "estd_conv3d: planar convolutions are implemented for the fp16 split only");
     const int dil = d->dilation > 0 ? d->dilation : 1;
     const int C = d->cout_pad;

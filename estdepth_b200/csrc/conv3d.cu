@@ -284,7 +284,7 @@ static int dispatch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_o
     ESTD_REQUIRE(d->D > 0 && d->H > 0 && d->W > 0, "estd_conv3d: bad volume %dx%dx%d", d->D, d->H, d->W);
     if (!count_only) {
         ESTD_REQUIRE(d->in0 && (d->weight || d->weight_tc) && d->scale && d->shift && (d->out0 || d->head_out), "estd_conv3d: null pointer");
-        const bool ring = !d->planar && (d->precision == ESTD_PREC_3XF16_RING2 || d->precision == ESTD_PREC_3XF16_RING);
+        const bool ring = !d->planar && (d->precision == ESTD_PREC_3XF16_RING2 || d->precision == ESTD_PREC_3XF16_RING2D || d->precision == ESTD_PREC_3XF16_RING);
         ESTD_REQUIRE(!(d->in0_split || d->in1_split || d->res_split || d->out_split) || ring || d->planar,
                      "estd_conv3d: pre-split (vol4s) tensors are implemented for the plane-ring and planar kernels only");
         ESTD_REQUIRE(!d->out_split || (!d->out1 && (d->out0_chunks % 2) == 0 && d->out0), "estd_conv3d: a pre-split output is one tensor with an even number of chunks");
@@ -303,7 +303,7 @@ static int dispatch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_o
         ESTD_REQUIRE((d->W * 16) % 16 == 0 && d->W * 4 <= (1 << 30), "estd_conv3d: W too large");
     }
     if (d->planar) return dispatch_planar(d, stream, count_only, n_ctas);
-    if (d->precision == ESTD_PREC_3XF16_RING2) return dispatch_ring2(d, stream, count_only, n_ctas);
+    if (d->precision == ESTD_PREC_3XF16_RING2 || d->precision == ESTD_PREC_3XF16_RING2D) return dispatch_ring2(d, stream, count_only, n_ctas);
     if (d->precision == ESTD_PREC_3XF16_RING) return dispatch_ring(d, stream, count_only, n_ctas);
     if (d->precision == ESTD_PREC_3XTF32 || d->precision == ESTD_PREC_3XF16) return dispatch_tc(d, stream, count_only, n_ctas);
     ESTD_REQUIRE(d->precision == ESTD_PREC_FP32, "estd_conv3d: unknown precision %d", d->precision);

@@ -323,7 +323,7 @@ conv3d_ring_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                     if (e == 0) mbar_wait_polls(&acc_full[half], (uint32_t)(n_seen & 1));
                     named_barrier(3, 128 * S::MH);
                     tc_fence_after();
-                    ring_drain_slot<COUT>(ep, s_shift, mult_v, t0, ok, pos, vox, want_gn, gs, gq, [&]() { mbar_arrive(&acc_empty[half]); });
+                    ring_drain_slot<COUT, false, 0, 0, 1>(ep, s_shift, mult_v, 0.0f, t0, ok, pos, vox, want_gn, gs, gq, [&]() { mbar_arrive(&acc_empty[half]); });
                 }
             }
         }

@@ -32,9 +32,16 @@ constexpr int EPI_THREADS = EPI_WARPS * 32, SPLIT_THREADS = SPLIT_WARPS * 32;
 constexpr int THREADS = 128 + EPI_THREADS + SPLIT_THREADS;       // warps 0-3 control, 4-11 epilogue, 12-19 splitters
 constexpr int FIRST_SPLIT_WARP = 4 + EPI_WARPS;
 
-template <int NKS_, int COUT_, int MT_>
+// DUAL: two accumulators per ring slot (precision 3xf16r2d).  The tensor core adds into its fp32 accumulator with truncation;
+// with all three products of the split in one accumulator every output takes 3 x 27 x NKS truncating adds at its full
+// magnitude, and although the mean of that error is compensated (common.cuh) its spread is three times that of the
+// large products alone.  DUAL keeps the small products (x_hi w_lo, x_lo w_hi) in a second accumulator, N3 columns further, which
+// the epilogue adds in round-to-nearest: the error of a layer drops to that of the exact-fp32 kernel (profiles/trunc_probe.py),
+// at twice the TMEM columns -- 2 M tiles per CTA instead of 4 for the 32-channel layers.
+template <int NKS_, int COUT_, int MT_, bool DUAL_ = false>
 struct Shape {
     static constexpr int NKS = NKS_, COUT = COUT_, MT = MT_, MH = MT_ / 2;      // MH: M tiles per half tile
+    static constexpr bool DUAL = DUAL_;
     static constexpr int TILE_H = 16, TILE_W = 8 * MT;
     static constexpr int HALO_H = TILE_H + 2, HALO_W = TILE_W + 2, HALO_VOX = HALO_H * HALO_W;
     static constexpr int KGROUP_BYTES = HALO_VOX * 16;
@@ -48,8 +55,9 @@ struct Shape {
     static constexpr int W_TAP_BYTES = 2 * W_PART_BYTES;
     static constexpr int W_BYTES = 9 * W_TAP_BYTES;               // per CTA and stage
     static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES + 127) / 128 * 128;
-    static constexpr int STAGES = (3 * STAGE_BYTES + 2048 <= 227 * 1024) ? 3 : 2;
-    static constexpr int COLS = MT * N3;
+    static constexpr int STAGES = (DUAL && 4 * STAGE_BYTES + 2048 <= 227 * 1024) ? 4 : (3 * STAGE_BYTES + 2048 <= 227 * 1024) ? 3 : 2;
+    static constexpr int ACC_N = DUAL ? 2 * N3 : N3;             // accumulator columns of one M tile (large | small products)
+    static constexpr int COLS = MT * ACC_N;
     static constexpr int TMEM_COLS = 512;                         // the pair allocates symmetrically: everything
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;
     static_assert(COLS <= 512, "ring accumulators must fit TMEM");
@@ -215,7 +223,7 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
                                 tc_fence_after();
                             }
                             if (leader) {
-                                const uint32_t acc0 = tmem_base + (uint32_t)(half * S::MH * N3);
+                                const uint32_t acc0 = tmem_base + (uint32_t)(half * S::MH * S::ACC_N);
                                 const uint64_t a_base = (uint64_t)(half * S::MH * 8);
 #pragma unroll
                                 for (int tap = 0; tap < 9; ++tap) {
@@ -225,7 +233,8 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
 #pragma unroll
                                         for (int m2 = 0; m2 < S::MH; ++m2) {
                                             const uint64_t a_off = a_base + (uint64_t)((tap / 3) * HALO_W + 8 * m2 + (tap % 3));
-                                            const uint32_t acc = acc0 + (uint32_t)(m2 * N3);
+                                            // DUAL: x_hi w_hi -> the large accumulator, the two small products -> the one N3 columns further
+                                            const uint32_t acc = acc0 + (uint32_t)(m2 * S::ACC_N + ((S::DUAL && prod != 0) ? N3 : 0));
                                             umma2_f16(acc, (prod == 2 ? a_lo_desc : a_hi_desc) + a_off, (prod == 1 ? w_lo_desc : w_hi_desc) + b_off, idesc, 1u);
                                         }
                                     }
@@ -288,7 +297,12 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
         if (bad && p.status) atomicOr(p.status, 1);
     } else if (warp >= 4) {
         // ===================== epilogue (own column, own TMEM) =====================
-        const int e = warp - 4, q = e & 3, m2 = e >> 2;
+        // 4 M tiles per column (MH = 2): all eight warps drain half 0, then half 1 (warps 4-7 the first M tile of the half, warps
+        // 8-11 the second).  2 M tiles (MH = 1): a half is ONE M tile, and each group of four warps owns one half for good --
+        // with both groups on the same half, the loads / stores of a drain (residuals!) would have to finish within the 27 MMAs
+        // of the other half before the next drain could start (measured: 239 us instead of 202 us for a 32->32 layer with a
+        // residual); owning a half gives every drain a whole plane's worth of MMAs to hide behind.
+        const int e = warp - 4, q = e & 3, g2 = e >> 2;
         const int m = q * 32 + lane;
         const int mh = m >> 3, mw = m & 7;
         double gs[2] = {0.0, 0.0}, gq[2] = {0.0, 0.0};
@@ -297,7 +311,7 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
         const bool want_gn = ep.gn_partials != nullptr;
         const float mult = __ldg(ep.scale);                      // uniform: 2^-k of the fp16 weight scaling (pack_weight_ring)
         int n_seen = 0;
-        int f = (m2 < S::MH) ? f_begin : f_end;
+        int f = f_begin;
         Segment sg;
         while (next_segment(f, f_end, p.D, sg)) {
             int h0, w0;
@@ -306,22 +320,31 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
             for (int z = sg.z0; z < sg.z1; ++z, ++n_seen) {
                 const int slot = z % 3;
 #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    const int mt = S::MH * half + m2;
+                for (int hh = 0; hh < 2; ++hh) {
+                    // MH == 2: hh = 0, 1 are the two halves, M tile = MH * half + g2.  MH == 1: one iteration, half = M tile = g2.
+                    const int half = (S::MH == 1) ? g2 : hh;
+                    if (S::MH == 1 && hh > 0) break;
+                    const int mt = (S::MH == 1) ? g2 : S::MH * half + g2;
                     const int w = w0 + 8 * mt + mw;
                     const bool ok = (h < p.H) && (w < p.W);
                     const size_t pos = ((size_t)z * p.H + h) * p.W + w;
-                    // truncation-bias compensation (common.cuh): this voxel's slot received 3 products x NKS k-steps for every
-                    // filter tap that lies inside the volume
-                    const float mult_v = mult * (1.0f + kTruncBiasPerMma * (float)(3 * NKS * taps_inside(z, p.D, 1) * taps_inside(h, p.H, 1) * taps_inside(w, p.W, 1)));
-                    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N3 + slot * COUT);
-                    if (e == 0) mbar_wait_polls(&acc_full[half], (uint32_t)(n_seen & 1));
-                    named_barrier(3, 128 * S::MH);
+                    // truncation-bias compensation (common.cuh): NKS k-steps for every filter tap that lies inside the volume, times
+                    // the products that share the accumulator (3; DUAL: only x_hi w_hi)
+                    const float comp = kTruncBiasPerMma * (float)((S::DUAL ? 1 : 3) * NKS * taps_inside(z, p.D, 1) * taps_inside(h, p.H, 1) * taps_inside(w, p.W, 1));
+                    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * S::ACC_N + slot * COUT);
+                    // who synchronises: MH == 2 all eight epilogue warps (barriers 3 / 5); MH == 1 the four warps of this group (3 / 5 and 6 / 7)
+                    const int n_sync = (S::MH == 1) ? 128 : EPI_THREADS;
+                    const int bar_full = (S::MH == 1 && g2 == 1) ? 6 : 3, bar_back = (S::MH == 1 && g2 == 1) ? 7 : 5;
+                    const bool leader = (S::MH == 1) ? (q == 0) : (e == 0);
+                    if (leader) mbar_wait_polls(&acc_full[half], (uint32_t)(n_seen & 1));
+                    named_barrier(bar_full, n_sync);
                     tc_fence_after();
-                    ring_drain_slot<COUT>(ep, s_shift, mult_v, t0, ok, pos, vox, want_gn, gs, gq, [&]() {
-                        named_barrier(5, 128 * S::MH);                                   // this CTA's slot is drained and zeroed ...
-                        if (e == 0 && lane == 0) mbar_arrive_remote(&acc_empty[half], 0);   // ... one arrival per CTA on the issuer's barrier
-                    });
+                    auto hand_back = [&]() {
+                        named_barrier(bar_back, n_sync);                                     // this CTA's slot is drained and zeroed ...
+                        if (leader && lane == 0) mbar_arrive_remote(&acc_empty[half], 0);    // ... one arrival per CTA on the issuer's barrier
+                    };
+                    const float mult_v = S::DUAL ? mult : mult * (1.0f + comp);
+                    ring_drain_slot<COUT, S::DUAL, N3, 0, 1>(ep, s_shift, mult_v, comp, t0, ok, pos, vox, want_gn, gs, gq, hand_back);
                 }
             }
         }
@@ -406,6 +429,13 @@ int dispatch_ring2(const estd_conv3d_desc* d, cudaStream_t stream, bool count_on
     const int cin_chunks = d->in0_chunks + d->in1_chunks;
     const int nks = (cin_chunks + 3) / 4;                         // 16 channels per stage
     ESTD_REQUIRE(!d->planar && (d->dilation == 0 || d->dilation == 1), "estd_conv3d(ring2): 3x3x3, dilation 1 only");
+    if (d->precision == ESTD_PREC_3XF16_RING2D) {
+        // two accumulators per slot: 2 * MT * N3 <= 512 columns
+#define ESTD_RING2D(NKS, COUT, MT) if (nks == NKS && d->cout_pad == COUT) return launch<Shape<NKS, COUT, MT, true>>(d, stream, count_only, n_ctas)
+        ESTD_RING2D(2, 32, 2); ESTD_RING2D(3, 32, 2); ESTD_RING2D(1, 16, 4); ESTD_RING2D(2, 16, 4); ESTD_RING2D(3, 33, 2);
+#undef ESTD_RING2D
+        return fail(ESTD_EUNSUPPORTED, "estd_conv3d(ring2, dual accumulators): no kernel for %d input chunks -> cout_pad %d", cin_chunks, d->cout_pad);
+    }
 #define ESTD_RING2(NKS, COUT, MT) if (nks == NKS && d->cout_pad == COUT) return launch<Shape<NKS, COUT, MT>>(d, stream, count_only, n_ctas)
     ESTD_RING2(2, 32, 4); ESTD_RING2(3, 32, 4); ESTD_RING2(1, 16, 4); ESTD_RING2(2, 16, 4); ESTD_RING2(3, 48, 2);
     ESTD_RING2(3, 33, 4);         // dres2 (36 -> 33 channels): 33-column slots, N = 112, so that 4 M tiles fit TMEM (448 columns)

@@ -30,31 +30,61 @@ __device__ __forceinline__ void tmem_st1_zero(uint32_t taddr) {
 // The order matters: the issuer needs the slot back within the time the tensor core spends on the other half tile, and every
 // load/store of step 2 queues behind the tensor core's operand fetches on the saturated l1tex data pipe (measured: ~1900
 // cycles per 16 channels, profiles/README.md) -- with the stores on the critical path the issuer waited a third of the time.
-template <int COUT, class HandBack>
-__device__ __forceinline__ void ring_drain_slot(const ConvEpilogue& ep, const float* s_shift, float mult, uint32_t t0, bool ok,
+//
+// DUAL (conv3d_ring2.cu, precision 3xf16r2d): the slot is a PAIR of accumulators -- the large products x_hi w_hi at t0, the small
+// ones (x_hi w_lo + x_lo w_hi) SMALL_OFF columns further -- added here in fp32 round-to-nearest; only the large one carries a
+// truncation bias worth compensating (`comp` = n_mma * kTruncBiasPerMma; the single-accumulator kernels fold it into `mult`).
+// B0 / BSTEP: this thread drains the 16-channel blocks B0, B0 + BSTEP, ... of the slot (two warps can share one M tile); the
+// extra 33rd channel belongs to the thread with B0 == 0.
+template <int COUT, bool DUAL, int SMALL_OFF, int B0, int BSTEP, class HandBack>
+__device__ __forceinline__ void ring_drain_slot(const ConvEpilogue& ep, const float* s_shift, float mult, float comp, uint32_t t0, bool ok,
                                                 size_t pos, size_t vox, bool want_gn, double (&gs)[2], double (&gq)[2],
                                                 HandBack&& hand_back) {
-    constexpr int NB = COUT / 16;
-    constexpr bool XTRA = (COUT % 16) != 0;
+    constexpr int NB_ALL = COUT / 16;
+    constexpr int NB = (NB_ALL - B0 + BSTEP - 1) / BSTEP;          // blocks of this thread
+    constexpr bool XTRA = (COUT % 16) != 0 && B0 == 0;
     static_assert(COUT % 16 <= 1, "a slot holds a multiple of 16 channels, plus at most one");
-    float acc[NB][16];
-    float accx = 0.0f;
+    float acc[NB > 0 ? NB : 1][16];
+    float sm[(DUAL && NB > 0) ? NB : 1][16];
+    float accx = 0.0f, smx = 0.0f;
+    // every TMEM load of the slot is issued before the one wait: the hand-back below is on the MMA issuer's critical path
 #pragma unroll
-    for (int b = 0; b < NB; ++b) tmem_ld16(t0 + (uint32_t)(16 * b), acc[b]);
-    if constexpr (XTRA) accx = tmem_ld1(t0 + (uint32_t)(16 * NB));
+    for (int i = 0; i < NB; ++i) {
+        tmem_ld16(t0 + (uint32_t)(16 * (B0 + i * BSTEP)), acc[i]);
+        if constexpr (DUAL) tmem_ld16(t0 + (uint32_t)(SMALL_OFF + 16 * (B0 + i * BSTEP)), sm[i]);
+    }
+    if constexpr (XTRA) {
+        accx = tmem_ld1(t0 + (uint32_t)(16 * NB_ALL));
+        if constexpr (DUAL) smx = tmem_ld1(t0 + (uint32_t)(SMALL_OFF + 16 * NB_ALL));
+    }
     tmem_ld_wait();
 #pragma unroll
-    for (int b = 0; b < NB; ++b) tmem_st16_zero(t0 + (uint32_t)(16 * b));
-    if constexpr (XTRA) tmem_st1_zero(t0 + (uint32_t)(16 * NB));
+    for (int i = 0; i < NB; ++i) {
+        tmem_st16_zero(t0 + (uint32_t)(16 * (B0 + i * BSTEP)));
+        if constexpr (DUAL) tmem_st16_zero(t0 + (uint32_t)(SMALL_OFF + 16 * (B0 + i * BSTEP)));
+    }
+    if constexpr (XTRA) {
+        tmem_st1_zero(t0 + (uint32_t)(16 * NB_ALL));
+        if constexpr (DUAL) tmem_st1_zero(t0 + (uint32_t)(SMALL_OFF + 16 * NB_ALL));
+    }
     tmem_st_wait();
     tc_fence_before();
     hand_back();
 
+    if constexpr (DUAL) {
+        // large-product accumulator: undo its truncation bias, then add the small products (held apart so that their 2 x n adds
+        // do not truncate at the large sum's magnitude)
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[i][k] = fmaf(acc[i][k], comp, acc[i][k]) + sm[i][k];
+        if constexpr (XTRA) accx = fmaf(accx, comp, accx) + smx;
+    }
     float amax = 0.0f;
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        const int c0 = 16 * b;
-        float (&v)[16] = acc[b];                                   // finished in place: the kernel is at the register limit of its 640 threads
+    for (int i = 0; i < NB; ++i) {
+        const int c0 = 16 * (B0 + i * BSTEP);
+        float (&v)[16] = acc[i];                                   // finished in place: the kernel is at the register limit of its 640 threads
         // what the block needs from memory is requested in batches (offsets + first residual, then the second residual)
         float4 sh[4], r[4];
 #pragma unroll
@@ -153,7 +183,7 @@ __device__ __forceinline__ void ring_drain_slot(const ConvEpilogue& ep, const fl
     }
     if constexpr (XTRA) {
         // the one channel beyond the 16-channel blocks: c = 16 * NB, first element of chunk c / 4 (the rest of that chunk is padding)
-        constexpr int c = 16 * NB;
+        constexpr int c = 16 * NB_ALL;
         const int ch = c >> 2;
         const int act = (c < ep.act_split) ? ep.act_lo : ep.act_hi;
         float v = fmaf(accx, mult, s_shift[c]);

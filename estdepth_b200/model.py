@@ -113,7 +113,7 @@ class _Workspace(object):
 
 class DepthNetHybrid(nn.Module):
     def __init__(self, ndepths=64, depth_min=0.01, depth_max=10.0, resnet=50, IF_EST_transformer=True,
-                 align_corners=False, fix_stale_pose=False, precision="3xf16r2", feature_precision="3xf16", geometry="auto",
+                 align_corners=False, fix_stale_pose=False, precision="3xf16r2d", feature_precision="3xf16", geometry="auto",
                  merged_pre2=True):
         """First five arguments: hybrid_models/model_hybrid.py:15-16.  Extra, keyword-only in practice:
 
@@ -133,7 +133,8 @@ class DepthNetHybrid(nn.Module):
         precision       arithmetic of the 3-D convolutions: "3xf16" / "3xtf32" = error-compensated two-term splits on the
                         tcgen05 tensor cores (fp32-class accuracy; "3xf16" moves half the operand bytes and needs
                         |activation| <= 65504, which is checked), "3xf16r" = the 3xf16 arithmetic on the plane-ring
-                        schedule, "3xf16r2" (default) = the same on CTA pairs (cta_group::2) where specialised,
+                        schedule, "3xf16r2" = the same on CTA pairs (cta_group::2), "3xf16r2d" = the CTA-pair ring with the
+                        small products of the split in a second accumulator per slot (the accuracy of the exact kernel),
                         "fp32" = exact fp32 on the CUDA cores.
         """
         super().__init__()
@@ -279,8 +280,18 @@ class DepthNetHybrid(nn.Module):
         """True when every 3-D layer runs on a plane-ring kernel: the conv-to-conv activations of the 3-D path are then kept
         PRE-SPLIT (vol4s: the producer's epilogue writes x_hi | x_lo, the consumer skips its in-place split) and the 1x1x1 logit
         heads are fused into the head convolutions' epilogues.  ESTD_SPLIT_ACT=0 / ESTD_FUSED_HEAD=0 turn the two off."""
-        return self.precision in ("3xf16r", "3xf16r2") and all(
-            v.precision is None and v.weight_ring is not None for v in L.values() if isinstance(v, ops.PackedConv))
+        return self.precision in ops.RING_PRECISIONS and all(
+            (v.precision is None or v.precision in ops.RING_PRECISIONS) and v.weight_ring is not None
+            for v in L.values() if isinstance(v, ops.PackedConv))
+
+    def _split3d(self, L):
+        """Pre-split (vol4s) conv-to-conv activations on the 3-D path: a gain for the single-accumulator CTA-pair kernels (4 M
+        tiles per CTA: 169 -> 164 us per 32->32 layer), a loss for the two-accumulator ones (2 M tiles: 173 -> 181 us,
+        profiles/bench_split_r02.txt), which therefore keep fp32 tensors.  ESTD_SPLIT_ACT3D=0|1 forces it."""
+        if not (self._ring(L) and self.split_activations):
+            return False
+        forced = os.environ.get("ESTD_SPLIT_ACT3D")
+        return (forced != "0") if forced is not None else self.precision != "3xf16r2d"
 
     def _head(self, L, ws, which, volume, depth_values, logits_out, depth_out, prob_out):
         """stereo_head{0,1} (3x3x3 conv + BN + ReLU, then Conv3d(16, 1, 1)) + nearest x4 + depthlayer
@@ -311,7 +322,7 @@ class DepthNetHybrid(nn.Module):
         homo = [self._homo_table[2 * t + n] if self._homo_table is not None else None for n in (0, 1)]
         # conv-to-conv activations are kept pre-split (vol4s, see _ring): pre1's output and the cost volume.  x0 stays fp32 (a
         # K1 that writes it pre-split spills: measured 69 us against 41 us) and so do the tensors that are residuals.
-        sp = self._ring(L) and self.split_activations
+        sp = self._split3d(L)
         s0 = (sp, False)
         if self.merged_pre2:
             assert out is not ws.x0 and out is not ws.a
@@ -337,7 +348,7 @@ class DepthNetHybrid(nn.Module):
         """dres0..2, value/key heads, stereo_head0 + soft-argmin (hybrid_depth_decoder.py:187-209)."""
         dev = cost.device
         _, D, H, W, _ = cost.shape
-        sp = self._ring(L) and self.split_activations          # the cost volume arrives pre-split then (see _cost_volume)
+        sp = self._split3d(L)                                   # the cost volume arrives pre-split then (see _cost_volume)
         s0 = (sp, False)
         self._conv(L["dres0.0"], cost, ws.a, in_split=s0, out_split=sp)
         self._conv(L["dres0.1"], ws.a, ws.b, in_split=s0, out_split=sp)
@@ -419,7 +430,7 @@ class DepthNetHybrid(nn.Module):
         """fp16 range flag of EARLIER launches, examined without draining the GPU (ops.check_status_async): called at the start
         of ``prepare`` and of ``fuse`` so that callers of the split API (the clip pipeline) are covered too.  The check is
         late by design -- a violation in the last call of a run is only caught by ``check()``."""
-        if self.precision in ("3xf16", "3xf16r", "3xf16r2") or self.feature_precision == "3xf16":
+        if self.precision in ("3xf16",) + ops.RING_PRECISIONS or self.feature_precision == "3xf16":
             ops.check_status_async(device)
 
     def check(self, device=None):

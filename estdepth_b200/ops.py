@@ -19,7 +19,8 @@ from . import _lib
 from ._lib import ConvDesc, check
 
 ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2, "add_relu": 3, "sigmoid": 4}
-PRECISION = {"fp32": 0, "3xtf32": 1, "3xf16": 2, "3xf16r": 3, "3xf16r2": 4}
+PRECISION = {"fp32": 0, "3xtf32": 1, "3xf16": 2, "3xf16r": 3, "3xf16r2": 4, "3xf16r2d": 5}
+RING_PRECISIONS = ("3xf16r", "3xf16r2", "3xf16r2d")
 MAX_SOURCES = 8
 # default arithmetic of conv3d: "fp32" = exact CUDA-core kernel, "3xtf32" / "3xf16" = error-compensated splits on tcgen05,
 # "3xf16r" = the 3xf16 arithmetic on the plane-ring schedule (conv3d_ring.cu) for the layers it is specialised for, the
@@ -313,6 +314,8 @@ def _precision(pc, precision):
     precision = DEFAULT_PRECISION if precision is None else precision
     if precision not in PRECISION:
         raise RuntimeError("conv3d: unknown precision %r" % (precision,))
+    if precision == "3xf16r2d" and (pc.weight_ring2 is None or (pc.cout_pad_tc == 48 and pc.cout_pad_ring2 is None)):
+        precision = "3xf16r2"          # two accumulators per slot do not fit TMEM for this shape
     if precision == "3xf16r2" and pc.weight_ring2 is None:
         precision = "3xf16r"           # same arithmetic and schedule on single CTAs: no CTA-pair specialisation for this shape
     if precision == "3xf16r" and pc.weight_ring is None:
@@ -388,13 +391,13 @@ def _desc_template(pc, precision, planar, dilation, device):
     d.planar, d.dilation = int(planar), int(dilation)
     tc = precision != "fp32"
     d.weight = _ptr(pc.weight)
-    f16 = precision in ("3xf16", "3xf16r", "3xf16r2")
-    d.weight_tc = _ptr(pc.weight_ring2 if precision == "3xf16r2" else pc.weight_ring if precision == "3xf16r"
+    f16 = precision in ("3xf16",) + RING_PRECISIONS
+    d.weight_tc = _ptr(pc.weight_ring2 if precision in ("3xf16r2", "3xf16r2d") else pc.weight_ring if precision == "3xf16r"
                        else pc.weight_f16 if precision == "3xf16" else pc.weight_tc)
-    ring = precision in ("3xf16r", "3xf16r2")
+    ring = precision in RING_PRECISIONS
     d.scale, d.shift = _ptr(pc.scale_ring if ring else pc.scale_f16 if f16 else pc.scale), _ptr(pc.shift)
     d.cout_pad = pc.cout_pad_tc if tc else pc.cout_pad
-    if precision == "3xf16r2" and pc.cout_pad_ring2 is not None:
+    if precision in ("3xf16r2", "3xf16r2d") and pc.cout_pad_ring2 is not None:
         d.cout_pad = pc.cout_pad_ring2
     d.status = _ptr(status_flag(device), torch.int32) if f16 else None
     d.act_split, d.act_lo, d.act_hi = pc.act_split, pc.act_lo, pc.act_hi
@@ -424,7 +427,7 @@ def _conv_desc(pc, in0, in1, out0, out1, res0, res1, post_scale, gn_partials, pr
     if d.in0_chunks + d.in1_chunks != want_in:
         raise RuntimeError("conv3d: layer packed for %d input chunks, got %d" % (want_in, d.in0_chunks + d.in1_chunks))
     if any(in_split) or res_split or out_split or head is not None:
-        if precision not in ("3xf16r", "3xf16r2") and not planar:
+        if precision not in RING_PRECISIONS and not planar:
             raise RuntimeError("conv3d: pre-split tensors / the fused logit head need the plane-ring kernels, not %r" % (precision,))
         if (in_split[0] and chunks0 % 2) or (in1 is not None and in_split[1] and in1.shape[0] % 2) or (out_split and out1 is not None):
             raise RuntimeError("conv3d: pre-split tensors hold an even number of chunks; a split output has one segment")
@@ -461,7 +464,7 @@ def conv3d_num_ctas(pc, D, H, W, precision=None):
     d.precision = PRECISION[precision]
     d.in0_chunks, d.in1_chunks = pc.cin_chunks, 0
     d.cout_pad = pc.cout_pad_tc if precision != "fp32" else pc.cout_pad
-    if precision == "3xf16r2" and pc.cout_pad_ring2 is not None:
+    if precision in ("3xf16r2", "3xf16r2d") and pc.cout_pad_ring2 is not None:
         d.cout_pad = pc.cout_pad_ring2
     d.D, d.H, d.W = D, H, W
     n = _lib.get().estd_conv3d_num_ctas(ctypes.byref(d))

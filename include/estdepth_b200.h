@@ -60,6 +60,10 @@ extern "C" {
 #define ESTD_PREC_3XF16_RING2 4     /* ESTD_PREC_3XF16_RING on CTA pairs (tcgen05 cta_group::2, conv3d_ring2.cu): M = 256 per MMA, each CTA of
                                        the cluster holds half of the weight rows; `weight_tc` = packing [7 masks][3 rotations][nks][2 CTAs]
                                        [9][hi,lo][2][3*cout_pad/2 rows][16 B]; same shapes as ESTD_PREC_3XF16_RING */
+#define ESTD_PREC_3XF16_RING2D 5    /* ESTD_PREC_3XF16_RING2 with TWO accumulators per ring slot: the small products of the split
+                                       (x_hi w_lo + x_lo w_hi) accumulate apart from x_hi w_hi and are added in the epilogue.  Same
+                                       weight packing; 2 instead of 4 M tiles per CTA for the 32-channel layers (TMEM holds 512
+                                       columns); error of a layer = that of the exact-fp32 kernel.  cout_pad 16 / 32 / 33 */
 
 ESTD_API int estd_version(void);
 ESTD_API const char* estd_last_error(void);

@@ -40,6 +40,12 @@ for cin, cout, pad in ((32, 32, 32), (16, 16, 16), (36, 33, 48)):
         print("ring2 %2d->%2d %-15s %7.1f us" % (cin, cout, name, t))
     t = timeit(lambda i: ops.conv3d(pc, x, outs[i % 2][:oc], res0=res, precision="3xf16r2"))
     print("ring2 %2d->%2d fp32 + residual    %7.1f us" % (cin, cout, t))
+    for name, kw, xin, nout in (("fp32 -> fp32", {}, x, oc), ("split -> fp32", dict(in_split=(True, False)), xs, oc),
+                                ("fp32 -> split", dict(out_split=True), x, (oc + 1) // 2 * 2), ("split -> split", dict(in_split=(True, False), out_split=True), xs, (oc + 1) // 2 * 2)):
+        t = timeit(lambda i: ops.conv3d(pc, xin, outs[i % 2][:nout], precision="3xf16r2d", **kw))
+        print("ring2 DUAL %2d->%2d %-15s %7.1f us" % (cin, cout, name, t))
+    t = timeit(lambda i: ops.conv3d(pc, x, outs[i % 2][:oc], res0=res, precision="3xf16r2d"))
+    print("ring2 DUAL %2d->%2d fp32 + residual    %7.1f us" % (cin, cout, t))
 
 N, H2, W2 = 5, 120, 160
 for cin, cout in ((64, 64), (128, 128)):

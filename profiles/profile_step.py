@@ -18,7 +18,7 @@ V, H, W, D, resnet = {"cfg2": (5, 480, 640, 64, 50), "cfg1": (5, 128, 160, 32, 1
 torch.backends.cudnn.benchmark = True
 torch.backends.cudnn.allow_tf32 = False
 dev = torch.device("cuda:0")
-model = DepthNetHybrid(ndepths=D, depth_min=0.1, depth_max=10.0, resnet=resnet, precision=(sys.argv[2] if len(sys.argv) > 2 else "3xf16r2"))
+model = DepthNetHybrid(ndepths=D, depth_min=0.1, depth_max=10.0, resnet=resnet, precision=(sys.argv[2] if len(sys.argv) > 2 else "3xf16r2d"))
 model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=0))
 model.eval().to(dev)
 w1 = synth.synth_inputs(V, H, W, seed=0, start=0)

@@ -48,7 +48,7 @@ def conv3d_probe():
             pc = packing.attach_tc(ops.PackedConv(pw, torch.ones(cout), torch.zeros(cout), cin // 4, cout, cout // 4, cout, "none", "none")).to(dev)
             xin = to_vol4(x).to(dev)
             print(" %d->%d %s" % (cin, cout, kind))
-            for prec in ("fp32", "3xf16", "3xf16r", "3xf16r2"):
+            for prec in ("fp32", "3xf16", "3xf16r", "3xf16r2", "3xf16r2d"):
                 out = torch.empty(cout // 4, D, H, W, 4, device=dev)
                 ops.conv3d(pc, xin, out, precision=prec)
                 stats(prec, from_vol4(out), ref)
@@ -76,7 +76,7 @@ def attribution():
     print("== cfg2 (480x640, D=64, R50) vs the reference fixture: worst |depth diff| by configuration")
     from oracle.make_golden import subsample
     gold = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "joint_r50_d64_480x640_g3.npz"))
-    for prec, psm_tc, ctx_tc in (("3xf16r2", True, True), ("3xf16r2", False, True), ("3xf16r2", True, False), ("3xf16r2", False, False),
+    for prec, psm_tc, ctx_tc in (("3xf16r2d", True, True), ("3xf16r2d", False, False), ("3xf16r2", True, True), ("3xf16r2", False, True), ("3xf16r2", True, False), ("3xf16r2", False, False),
                                  ("3xf16", True, True), ("3xf16", False, False), ("fp32", True, True), ("fp32", False, False)):
         model = DepthNetHybrid(ndepths=64, depth_min=0.1, depth_max=10.0, resnet=50, precision=prec)
         model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=0))

@@ -48,7 +48,7 @@ def test_k1_identity_pose_and_linearity():
     assert 0.01 < frac_zero < 0.5          # near planes leave the source image (quirk Q10), far planes do not
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16", "3xf16r", "3xf16r2"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16", "3xf16r", "3xf16r2", "3xf16r2d"])
 def test_k2_delta_filter_is_a_zero_filled_shift(precision):
     x = _vol(8, 1)
     w = torch.zeros(32, 32, 3, 3, 3)
@@ -65,7 +65,7 @@ def test_k2_delta_filter_is_a_zero_filled_shift(precision):
         # two-term splits reproduce fp32 inputs to 2^-21 relative.  The truncation-bias compensation (csrc/common.cuh) assumes
         # that every MMA of the filter's footprint adds something; a one-tap filter adds zeros in all the others, so the output is
         # over-corrected by at most n_mma * 0.272 * 2^-24 (n_mma = 162 on the ring schedules, 54 on the output-stationary one)
-        n_mma = 162 if precision.startswith("3xf16r") else 54
+        n_mma = 162 if precision in ("3xf16r", "3xf16r2") else 54
         assert (y - want).abs().max().item() <= (2.0 ** -20 + n_mma * 0.272 * 2.0 ** -24) * x.abs().max().item()
 
 
@@ -76,9 +76,9 @@ def test_k2_linearity_and_kernel_agreement():
     pc = packing.attach_tc(ops.PackedConv(packing.pack_weight(w, list(range(32)), list(range(32))).to(DEV),
                                           torch.ones(32, device=DEV), torch.zeros(32, device=DEV), 8, 32, 8, 32, "none", "none"))
     exact = ops.conv3d(pc, x, torch.empty_like(x), precision="fp32")
-    for precision in ("3xtf32", "3xf16", "3xf16r", "3xf16r2"):
+    for precision in ("3xtf32", "3xf16", "3xf16r", "3xf16r2", "3xf16r2d"):
         got = ops.conv3d(pc, x, torch.empty_like(x), precision=precision)
-        assert (got - exact).abs().max().item() < (4e-5 if precision.startswith("3xf16r") else 2e-5), precision   # outputs are O(1)
+        assert (got - exact).abs().max().item() < (4e-5 if precision in ("3xf16r", "3xf16r2") else 2e-5), precision   # outputs are O(1)
     fx = exact
     fy = ops.conv3d(pc, y, torch.empty_like(x), precision="3xf16")
     fxy = ops.conv3d(pc, 0.5 * x + 2.0 * y, torch.empty_like(x), precision="3xf16")

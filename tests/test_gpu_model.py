@@ -44,7 +44,7 @@ def _run_joint(model, height, width, starts=(0, 3)):
     return results
 
 
-@pytest.mark.parametrize("precision", ["3xf16r2", "3xf16r", "3xf16", "3xtf32", "fp32"])
+@pytest.mark.parametrize("precision", ["3xf16r2d", "3xf16r2", "3xf16r", "3xf16", "3xtf32", "fp32"])
 @pytest.mark.parametrize("resnet,ndepths,height,width,name", [
     (18, 32, 128, 160, "joint_r18_d32_128x160.npz"),
     (50, 64, 128, 128, "joint_r50_d64_128x128.npz"),
@@ -166,7 +166,7 @@ def test_fp16_range_violation_is_reported():
         ops.check_status(x.device)
     ops.check_status(x.device)                       # flag was cleared
     # the non-blocking variant forward() uses reports the violation one or two calls later, for every tensor-core schedule
-    for precision in ("3xf16r", "3xf16r2"):
+    for precision in ("3xf16r", "3xf16r2", "3xf16r2d"):
         ops.conv3d(pc, x, y, precision=precision)
         with pytest.raises(RuntimeError, match="fp16 range"):
             for _ in range(3):

@@ -188,7 +188,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16", "3xf16r", "3xf16r2"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16", "3xf16r", "3xf16r2", "3xf16r2d"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 @pytest.mark.parametrize("shape", [(5, 21, 40), (8, 32, 64)], ids=["ragged", "aligned"])
 def test_conv3d_vs_torch_cpu(case, shape, precision):
@@ -246,7 +246,7 @@ def test_conv3d_vs_torch_cpu(case, shape, precision):
         assert abs(tot[1, 1].item() - (g1 ** 2).sum().item()) < 1e-4 * (g1 ** 2).sum().item()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16", "3xf16r", "3xf16r2"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16", "3xf16r", "3xf16r2", "3xf16r2d"])
 def test_conv3d_is_bitwise_deterministic(precision):
     g = torch.Generator().manual_seed(5)
     D, H, W = 6, 24, 64
@@ -504,7 +504,7 @@ def test_align_corners_flag_changes_sampling():
 
 
 # ------------------------------------------------------------------------------------------- pre-split activations (vol4s)
-@pytest.mark.parametrize("precision", ["3xf16r", "3xf16r2"])
+@pytest.mark.parametrize("precision", ["3xf16r", "3xf16r2", "3xf16r2d"])
 @pytest.mark.parametrize("cin_chunks,cout,cout_pad", [(8, 32, 32), (9, 33, 48), (4, 16, 16)])
 def test_conv3d_presplit_tensors_equal_fp32_tensors(precision, cin_chunks, cout, cout_pad):
     """A producer that writes x_hi | x_lo (out_split) and a consumer that reads it (in_split, res_split) compute exactly what the
@@ -584,7 +584,7 @@ def test_conv_planar_upsampled_output_equals_nearest_interpolate(split):
         assert torch.equal(ops.vol4_to_nchw(up), ref)
 
 
-@pytest.mark.parametrize("precision", ["3xf16r", "3xf16r2"])
+@pytest.mark.parametrize("precision", ["3xf16r", "3xf16r2", "3xf16r2d"])
 def test_fused_logit_head_equals_head_conv_then_1x1x1(precision):
     """stereo_head: Conv3d(16,16,3)+BN+ReLU then Conv3d(16,1,1,bias) (hybrid_depth_decoder.py:104-112): the logit computed in the
     convolution's epilogue equals the two-kernel path (hidden volume + head_softargmin's own dot product)."""
