@@ -275,10 +275,11 @@ def test_cuda_poses_vs_reference_algorithm_on_the_same_gpu_cfg2():
 # ------------------------------------------------------------------------------------------- feature cache
 def test_frame_id_feature_cache_estm_cfg3():
     """ESTM at 480 x 640 with and without ``frame_ids`` (consecutive 3-frame windows share 2 frames: their matching features
-    are computed once, eval_hybrid_seq.py:169-190 recomputes them).  Same depth maps; time per step printed."""
+    are computed once, where eval_hybrid_seq.py:169-190 recomputes them).  Same depth maps bit for bit (the in-house kernels are
+    batch invariant, and so is the cuDNN stem with benchmark off); steady-state time per step printed for both and compared."""
     model, _ = _model(50, 64)
     torch.backends.cudnn.benchmark = False
-    n_frames = 10
+    n_frames = 14
     windows = [synth.synth_inputs(3, 480, 640, seed=0, start=s) for s in range(n_frames - 2)]
     windows = [(w[0].cuda(), w[1], w[2]) for w in windows]
 
@@ -287,8 +288,9 @@ def test_frame_id_feature_cache_estm_cfg3():
         model._feat_cache.clear()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
         for s, (imgs, poses, K) in enumerate(windows):
+            if s == 2:
+                e0.record()                                  # steady state: two memory volumes, every window shares two frames
             pre = sharding._flatten_memory(memory)
             out, costs, cposes = model(imgs, poses, K, None, pre[0], pre[1], mode="val",
                                        frame_ids=[s, s + 1, s + 2] if with_ids else None)
@@ -298,17 +300,25 @@ def test_frame_id_feature_cache_estm_cfg3():
             maps.append(torch.cat([out[("depth", 0, 0)], out[("depth", 0, 2)]]))
         e1.record()
         torch.cuda.synchronize()
-        return torch.cat(maps), e0.elapsed_time(e1) / len(windows)
+        return torch.cat(maps), e0.elapsed_time(e1) / (len(windows) - 2)
 
     run(False)
-    plain, ms_plain = run(False)
-    cached, ms_cached = run(True)
+    run(True)
+    times = {False: [], True: []}
+    for _ in range(3):
+        for with_ids in (False, True):
+            maps, ms = run(with_ids)
+            times[with_ids].append(ms)
+            if with_ids:
+                cached = maps
+            else:
+                plain = maps
+    ms_plain, ms_cached = min(times[False]), min(times[True])
     diff = float((plain - cached).abs().max())
-    print("frame-id feature cache, ESTM %d steps 480x640: %.2f ms/step without ids, %.2f ms/step with ids (%.1f %% less); "
-          "max |depth diff| = %.3e" % (len(windows), ms_plain, ms_cached, 100.0 * (1 - ms_cached / ms_plain), diff))
-    # the cached features were computed in a differently composed batch; the in-house kernels are batch invariant, the cuDNN
-    # stem may choose another algorithm: fp32 round-off at most
+    print("frame-id feature cache, ESTM steady state at 480x640: %.2f ms/step without ids, %.2f ms/step with ids (%.1f %% less); "
+          "max |depth diff| = %.3e" % (ms_plain, ms_cached, 100.0 * (1 - ms_cached / ms_plain), diff))
     assert diff < 1e-4, diff
+    assert ms_cached < ms_plain
 
 
 # ------------------------------------------------------------------------------------------- driver I/O
