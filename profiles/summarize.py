@@ -41,16 +41,22 @@ def launches(path):
 
 
 def raw(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """``path``: an .ncu-rep, or the CSV that ``ncu -i X.ncu-rep --page raw --csv`` printed (large reports are converted on
+    the GPU box and only the CSV is brought back)."""
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ki = hdr.index("Kernel Name")
     seen = collections.Counter()
-    print("# ncu --set full --clock-control none; first instance of each kernel")
+    every = "--all" in sys.argv
+    print("# ncu --set full --clock-control none; %s" % ("every captured launch" if every else "first instance of each kernel"))
     for r in data:
-        name = re.sub(r"\(.*", "", r[ki])[:80]
+        name = re.sub(r"\(CUtensorMap.*|\(const.*|\(float.*", "", r[ki])[:120].replace("(int)", "").replace("(bool)", "")
         seen[name] += 1
-        if seen[name] > 1:
+        if seen[name] > 1 and not every:
             continue
         print("==== " + name)
         for k in KEYS:
