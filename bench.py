@@ -549,6 +549,7 @@ def run_ours(args):
             gather(outputs)
 
     def step_e2e():
+        """One window the way the reference's drivers run it: copy in, forward, copy out, wait."""
         imgs_dev = host[0].to(dev, non_blocking=True)
         outputs, _, _ = model(imgs_dev, host[1], host[2], None, state, pstate, mode="val")
         if world > 1:
@@ -557,17 +558,44 @@ def run_ours(args):
             buf.copy_(outputs[key], non_blocking=True)
         torch.cuda.current_stream().synchronize()         # the driver consumes the maps before the next window
 
+    from estdepth_b200.io import WindowIO
+    wio = WindowIO(dev)
+    pipe = {"next": None, "prev": None}
+
+    def step_e2e_pipelined():
+        """The same window through the repository's own I/O helper (estdepth_b200.io.WindowIO): every step still copies its
+        images from pinned host memory and reads its six maps back, but the NEXT window's upload and the PREVIOUS window's
+        download overlap this window's compute; the host waits for the previous window's maps only."""
+        cur = pipe["next"] if pipe["next"] is not None else wio.upload(host[0])
+        pipe["next"] = wio.upload(host[0])                # the next window's images (the same synthetic window every step)
+        outputs, _, _ = model(wio.ready(cur), host[1], host[2], None, state, pstate, mode="val")
+        if world > 1:
+            gather(outputs)
+        pending = wio.download([outputs[key] for key in save_keys])
+        if pipe["prev"] is not None:
+            pipe["prev"].result()                         # the driver consumes the previous window's maps
+            wio.release(pipe["prev"])
+        pipe["prev"] = pending
+
+    def drain_e2e_pipelined():
+        if pipe["prev"] is not None:
+            pipe["prev"].result()
+            wio.release(pipe["prev"])
+        pipe["prev"] = pipe["next"] = None
+
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, after=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        if after is not None:
+            after()                                        # (pipelined arm: the last window's maps are read inside the region)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -591,18 +619,21 @@ def run_ours(args):
             n_warm += 1
             if n_warm >= max(3, args.warmup):
                 torch.cuda.current_stream().synchronize()      # the wait is GPU time, not enqueue time
-    for _ in range(3):                                     # both step kinds once more, so that no timed repetition is the first of its kind
+    for _ in range(3):                                     # every step kind once more, so that no timed repetition is the first of its kind
         step_e2e()
+        step_e2e_pipelined()
         step_resident()
+    drain_e2e_pipelined()
     launches0 = _lib.launch_count()
-    rep_res, rep_e2e = [], []
+    rep_res, rep_e2e, rep_serial = [], [], []
     for _ in range(REPEATS):                               # resident and end-to-end repetitions alternate
         rep_res.append(timed(step_resident, args.steps) / args.steps)
-        rep_e2e.append(timed(step_e2e, args.steps) / args.steps)
-    launches = (_lib.launch_count() - launches0) // (2 * REPEATS * args.steps)
+        rep_e2e.append(timed(step_e2e_pipelined, args.steps, after=drain_e2e_pipelined) / args.steps)
+        rep_serial.append(timed(step_e2e, args.steps) / args.steps)
+    launches = (_lib.launch_count() - launches0) // (3 * REPEATS * args.steps)
     clocks = sampler.stop() if sampler else None
     model.check()                                          # fp16-range flag of everything timed above
-    ms_resident, ms_e2e = median(rep_res), median(rep_e2e)
+    ms_resident, ms_e2e, ms_serial = median(rep_res), median(rep_e2e), median(rep_serial)
     # host issue time of a step (informational): two steps enqueued on an idle GPU without waiting
     barrier()
     t0 = time.perf_counter()
@@ -686,7 +717,13 @@ def run_ours(args):
                        "timed_region_s": sum(rep_res) * args.steps * 1e-3, "warmup_steps_run": n_warm,
                        "collective_in_step": "all_gather_into_tensor of the saved depth maps (%d B per rank)" % d2h if world > 1 else None},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
-                    "repeats_ms_per_step": rep_e2e},
+                    "repeats_ms_per_step": rep_e2e,
+                    "how": "public call model(...) with the window's images uploaded from pinned host memory and the six saved maps read back "
+                           "into pinned host memory EVERY step, through estdepth_b200.io.WindowIO: the next window's upload and the previous "
+                           "window's download overlap the current window's compute (the host waits for the previous window's maps); the "
+                           "first upload and the last download are inside the timed region",
+                    "serial": {"value": frames / (ms_serial * 1e-3), "ms_per_step": ms_serial, "repeats_ms_per_step": rep_serial,
+                               "how": "the same copies issued the way the reference's drivers do: upload, forward, download, wait -- nothing overlapped"}},
             "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "clocks": clocks, "roofline": roofline,
             "kernels": kernels, "extras": extras, "cpu_baseline": cpu_base}
     print(json.dumps(line))

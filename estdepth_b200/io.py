@@ -1,4 +1,6 @@
-"""Asynchronous depth-map writer -- the save path of the reference's eval drivers without their stalls.
+"""Driver-side I/O off the critical path: ``DepthMapWriter`` -- the save path of the reference's eval
+drivers without their stalls -- and ``WindowIO`` -- double-buffered host<->device traffic around ``forward``.
+
 
 The drivers save each map as ``np.save(path, np.float16(outputs[key].squeeze(1).cpu().numpy()))`` (eval_hybrid.py:260-264,
 282-286, 276-277, 306-307): a blocking device->host copy of fp32 data, a host-side cast and a synchronous file write per map,
@@ -92,3 +94,86 @@ class DepthMapWriter(object):
     def __exit__(self, *exc):
         self.close()
         return False
+
+
+class WindowIO(object):
+    """Host<->device traffic of a stream of windows, off the critical path.
+
+    The reference's drivers move every window to the GPU right before the forward (``tocuda(sample)``, eval_hybrid.py:231-243) and
+    read the maps back right after it (``.cpu()``, :259-286): the GPU idles during both copies.  With this helper the NEXT window's
+    images travel host->device on a copy stream while the current window computes, and a window's maps travel device->host while
+    the next one computes; the host only ever waits for maps that were requested a window ago.
+
+        io = WindowIO(device)
+        nxt = io.upload(first_window_images)                    # pinned host tensor -> device, asynchronous
+        for k, (poses, K) in enumerate(cameras):
+            cur, nxt = nxt, (io.upload(images[k + 1]) if k + 1 < n else None)
+            outputs, state, pose_state = model(io.ready(cur), poses, K, sample, state, pose_state, mode="val")
+            pending = io.download([outputs[key] for key in keys])     # asynchronous, into pinned buffers
+            if previous is not None:
+                maps = previous.result()                        # the PREVIOUS window's maps: long since on the host
+            previous = pending
+
+    Nothing here changes what is computed; it is plain stream / event plumbing over pinned buffers."""
+
+    class _Upload(object):
+        __slots__ = ("tensor", "done")
+
+    class _Download(object):
+        __slots__ = ("buffers", "done")
+
+        def result(self):
+            """The maps as pinned host tensors (waits for this download only)."""
+            self.done.synchronize()
+            return self.buffers
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.copy_in = torch.cuda.Stream(device=self.device)
+        self.copy_out = torch.cuda.Stream(device=self.device)
+        self._pool = {}            # (shape, dtype) -> free pinned buffers for downloads
+
+    def upload(self, host_tensor):
+        """Pinned host tensor -> device on the upload stream; returns a handle for ``ready``."""
+        if not host_tensor.is_pinned():
+            host_tensor = host_tensor.pin_memory()
+        up = WindowIO._Upload()
+        with torch.cuda.stream(self.copy_in):
+            up.tensor = host_tensor.to(self.device, non_blocking=True)
+            up.done = torch.cuda.Event()
+            up.done.record(self.copy_in)
+        return up
+
+    def ready(self, upload):
+        """The uploaded tensor, usable on the CURRENT stream (which is made to wait for the copy; the host does not)."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(upload.done)
+        upload.tensor.record_stream(cur)
+        return upload.tensor
+
+    def download(self, tensors):
+        """Device tensors -> pinned host buffers on the download stream, behind the work already enqueued on the current
+        stream.  Returns a handle whose ``result()`` gives the host tensors; buffers are recycled after ``release``."""
+        cur = torch.cuda.current_stream(self.device)
+        produced = torch.cuda.Event()
+        produced.record(cur)
+        self.copy_out.wait_event(produced)
+        dl = WindowIO._Download()
+        dl.buffers = []
+        with torch.cuda.stream(self.copy_out):
+            for t in tensors:
+                key = (tuple(t.shape), t.dtype)
+                free = self._pool.get(key)
+                buf = free.pop() if free else torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                buf.copy_(t, non_blocking=True)
+                t.record_stream(self.copy_out)
+                dl.buffers.append(buf)
+            dl.done = torch.cuda.Event()
+            dl.done.record(self.copy_out)
+        return dl
+
+    def release(self, download):
+        """Hands a finished download's pinned buffers back for reuse."""
+        for buf in download.buffers:
+            self._pool.setdefault((tuple(buf.shape), buf.dtype), []).append(buf)
+        download.buffers = []

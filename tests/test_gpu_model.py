@@ -247,3 +247,40 @@ def test_as_trained_align_corners_mode_end_to_end():
             assert (want[("depth", 1, 2)] - plain[("depth", 1, 2)]).abs().max().item() > 10 * DEPTH_TOL
         assert (state["values"][0].cpu() - ostate["values"][0]).abs().max().item() < STATE_TOL
     print("align_corners=True end to end vs oracle(align_corners=True):", {k: "%.1e" % v for k, v in sorted(worst.items())})
+
+
+def test_window_io_pipeline_gives_the_plain_results():
+    """estdepth_b200.io.WindowIO (next window's upload and previous window's download overlapped with the current window's
+    compute) changes nothing in what is computed: same maps, bit for bit, as upload -> forward -> .cpu() per window."""
+    from estdepth_b200.io import WindowIO
+    torch.backends.cudnn.benchmark = False
+    model, _ = synth_model_and_state(18, 32)
+    model.cuda()
+    windows = [synth.synth_inputs(5, 128, 160, seed=0, start=s) for s in (0, 3, 6, 9)]
+    keys = [("depth", t, s) for t in range(3) for s in (2, 0)]
+
+    plain, state, pstate = [], None, None
+    for imgs, poses, K, sample in windows:
+        out, state, pstate = model(imgs.cuda(), poses, K, sample, state, pstate, mode="val")
+        plain.append([out[k].cpu() for k in keys])
+
+    io = WindowIO(torch.device("cuda"))
+    host = [w[0].pin_memory() for w in windows]
+    got, state, pstate, prev = [], None, None, None
+    nxt = io.upload(host[0])
+    for k, (imgs, poses, K, sample) in enumerate(windows):
+        cur, nxt = nxt, (io.upload(host[k + 1]) if k + 1 < len(windows) else None)
+        out, state, pstate = model(io.ready(cur), poses, K, sample, state, pstate, mode="val")
+        pending = io.download([out[key] for key in keys])
+        if prev is not None:
+            got.append([b.clone() for b in prev.result()])
+            io.release(prev)
+        prev = pending
+    got.append([b.clone() for b in prev.result()])
+    assert all(b.is_pinned() for b in prev.buffers)
+    io.release(prev)
+    model.check()
+    assert len(got) == len(plain)
+    for a, b in zip(plain, got):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
