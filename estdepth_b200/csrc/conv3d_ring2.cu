@@ -52,7 +52,13 @@ struct Shape {
     static constexpr int SHIFT_N = (COUT + 15) / 16 * 16;         // per-channel offsets kept in shared memory
     static constexpr int NH = N3 / 2;                             // weight rows held by one CTA of the pair
     static constexpr int W_PART_BYTES = 2 * NH * 16;              // [2 K-groups][NH rows][16 B] of w_hi (or w_lo)
-    static constexpr int W_TAP_BYTES = 2 * W_PART_BYTES;
+    // DUAL: per tap a "merged" block [2 K-groups][N3 rows] -- rank 0 holds ALL of w_hi, rank 1 ALL of w_lo, so that ONE MMA with
+    // N = 2*N3 and A = x_hi writes x_hi w_hi into the large accumulator and x_hi w_lo into the small one next to it -- and a
+    // "third" block [2 K-groups][NH rows] with this rank's half of w_hi for A = x_lo.  Two MMAs per tap and M tile instead of
+    // three: one fetch of the A tile (32 of the ~44 shared-memory wavefronts of an MMA) is saved.
+    static constexpr int W_MERGED_BYTES = 2 * N3 * 16;
+    static constexpr int W_TAP_BYTES = DUAL ? (W_MERGED_BYTES + W_PART_BYTES) : 2 * W_PART_BYTES;
+    static_assert(!DUAL || 2 * N3 <= 256, "the merged MMA needs N = 2 * N3 <= 256");
     static constexpr int W_BYTES = 9 * W_TAP_BYTES;               // per CTA and stage
     static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES + 127) / 128 * 128;
     static constexpr int STAGES = (DUAL && 4 * STAGE_BYTES + 2048 <= 227 * 1024) ? 4 : (3 * STAGE_BYTES + 2048 <= 227 * 1024) ? 3 : 2;
@@ -78,6 +84,7 @@ __device__ long long g_ring2_epi[148 * 8];      // per CTA, epilogue warp 4: {cy
 
 struct Params {
     const float* weight_ring2;                  // [7 live-tap masks][3 rotations][NKS][2 CTAs][9 taps][hi,lo][2 K-groups][NH rows][16 bytes]
+                                                // DUAL: [...][9 taps]{[2 K-groups][N3 rows] merged, [2 K-groups][NH rows] third}[16 bytes]
     int* status;
     ConvEpilogue ep;
     int in0_chunks;
@@ -186,6 +193,7 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
         if (rank == 0) {
             const bool leader = elect_one();
             const uint32_t idesc = make_idesc2(0u, N3);
+            const uint32_t idesc_merged = make_idesc2(0u, 2 * N3);
             int it = 0, f = f_begin;
             int n_sig = 0;                                           // hand-overs issued so far (the same for both halves)
             Segment sg;
@@ -214,8 +222,11 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
                         const uint32_t a_hi = smem_u32(smem + (size_t)s * S::STAGE_BYTES);
                         const uint64_t a_hi_desc = make_desc(a_hi, 2 * S::KGROUP_BYTES, HALO_W * 16);
                         const uint64_t a_lo_desc = make_desc(a_hi + S::KGROUP_BYTES, 2 * S::KGROUP_BYTES, HALO_W * 16);
-                        const uint64_t w_hi_desc = make_desc(a_hi + A_BYTES, S::NH * 16, 128);
-                        const uint64_t w_lo_desc = make_desc(a_hi + A_BYTES + S::W_PART_BYTES, S::NH * 16, 128);
+                        // single accumulator: w_hi / w_lo halves of this rank.  DUAL: "w_hi_desc" = the merged block (N3 rows per K-group:
+                        // w_hi in rank 0, w_lo in rank 1), "w_lo_desc" = the third block (this rank's half of w_hi)
+                        const uint64_t w_hi_desc = S::DUAL ? make_desc(a_hi + A_BYTES, N3 * 16, 128) : make_desc(a_hi + A_BYTES, S::NH * 16, 128);
+                        const uint64_t w_lo_desc = S::DUAL ? make_desc(a_hi + A_BYTES + S::W_MERGED_BYTES, S::NH * 16, 128)
+                                                           : make_desc(a_hi + A_BYTES + S::W_PART_BYTES, S::NH * 16, 128);
 #pragma unroll 1
                         for (int half = 0; half < 2; ++half) {
                             if (ks == 0 && n_sig > 0) {
@@ -228,14 +239,24 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
 #pragma unroll
                                 for (int tap = 0; tap < 9; ++tap) {
                                     const uint64_t b_off = (uint64_t)(tap * (S::W_TAP_BYTES >> 4));
-#pragma unroll
-                                    for (int prod = 0; prod < 3; ++prod) {
+                                    if constexpr (S::DUAL) {
 #pragma unroll
                                         for (int m2 = 0; m2 < S::MH; ++m2) {
                                             const uint64_t a_off = a_base + (uint64_t)((tap / 3) * HALO_W + 8 * m2 + (tap % 3));
-                                            // DUAL: x_hi w_hi -> the large accumulator, the two small products -> the one N3 columns further
-                                            const uint32_t acc = acc0 + (uint32_t)(m2 * S::ACC_N + ((S::DUAL && prod != 0) ? N3 : 0));
-                                            umma2_f16(acc, (prod == 2 ? a_lo_desc : a_hi_desc) + a_off, (prod == 1 ? w_lo_desc : w_hi_desc) + b_off, idesc, 1u);
+                                            const uint32_t acc = acc0 + (uint32_t)(m2 * S::ACC_N);
+                                            // x_hi [w_hi | w_lo] -> large accumulator | small accumulator (N = 2 * N3), then x_lo w_hi -> small
+                                            umma2_f16(acc, a_hi_desc + a_off, w_hi_desc + b_off, idesc_merged, 1u);
+                                            umma2_f16(acc + (uint32_t)N3, a_lo_desc + a_off, w_lo_desc + b_off, idesc, 1u);
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int prod = 0; prod < 3; ++prod) {
+#pragma unroll
+                                            for (int m2 = 0; m2 < S::MH; ++m2) {
+                                                const uint64_t a_off = a_base + (uint64_t)((tap / 3) * HALO_W + 8 * m2 + (tap % 3));
+                                                const uint32_t acc = acc0 + (uint32_t)(m2 * S::ACC_N);
+                                                umma2_f16(acc, (prod == 2 ? a_lo_desc : a_hi_desc) + a_off, (prod == 1 ? w_lo_desc : w_hi_desc) + b_off, idesc, 1u);
+                                            }
                                         }
                                     }
                                 }
@@ -297,12 +318,13 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
         if (bad && p.status) atomicOr(p.status, 1);
     } else if (warp >= 4) {
         // ===================== epilogue (own column, own TMEM) =====================
-        // 4 M tiles per column (MH = 2): all eight warps drain half 0, then half 1 (warps 4-7 the first M tile of the half, warps
-        // 8-11 the second).  2 M tiles (MH = 1): a half is ONE M tile, and each group of four warps owns one half for good --
-        // with both groups on the same half, the loads / stores of a drain (residuals!) would have to finish within the 27 MMAs
-        // of the other half before the next drain could start (measured: 239 us instead of 202 us for a 32->32 layer with a
-        // residual); owning a half gives every drain a whole plane's worth of MMAs to hide behind.
-        const int e = warp - 4, q = e & 3, g2 = e >> 2;
+        // Each group of four epilogue warps (warps 4-7, warps 8-11) OWNS one half tile for good and drains its MH M tiles plane after
+        // plane.  A drain is TMEM -> registers, zero, hand the slot back, then affine / activation / residual loads / stores; the
+        // issuer needs the slot back by the time it has issued the OTHER half's MMAs of the next plane.  With both groups working
+        // on the same half (the round-1 layout) the loads / stores of half 0 had to finish before half 1's drain could even
+        // start: measured 239 us instead of 202 us for a 32->32 layer with a residual at 2 M tiles per CTA, and the 16-channel
+        // layers (one stage per plane) ran epilogue-bound at 40 % tensor-pipe activity.
+        const int e = warp - 4, q = e & 3, half = e >> 2;
         const int m = q * 32 + lane;
         const int mh = m >> 3, mw = m & 7;
         double gs[2] = {0.0, 0.0}, gq[2] = {0.0, 0.0};
@@ -310,6 +332,7 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
         const ConvEpilogue& ep = p.ep;
         const bool want_gn = ep.gn_partials != nullptr;
         const float mult = __ldg(ep.scale);                      // uniform: 2^-k of the fp16 weight scaling (pack_weight_ring)
+        const int bar_full = half ? 6 : 3, bar_back = half ? 7 : 5;   // named barriers of this group (128 threads)
         int n_seen = 0;
         int f = f_begin;
         Segment sg;
@@ -319,12 +342,16 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
             const int h = h0 + mh;
             for (int z = sg.z0; z < sg.z1; ++z, ++n_seen) {
                 const int slot = z % 3;
-#pragma unroll 1
-                for (int hh = 0; hh < 2; ++hh) {
-                    // MH == 2: hh = 0, 1 are the two halves, M tile = MH * half + g2.  MH == 1: one iteration, half = M tile = g2.
-                    const int half = (S::MH == 1) ? g2 : hh;
-                    if (S::MH == 1 && hh > 0) break;
-                    const int mt = (S::MH == 1) ? g2 : S::MH * half + g2;
+                if (q == 0) mbar_wait_polls(&acc_full[half], (uint32_t)(n_seen & 1));
+                named_barrier(bar_full, 128);
+                tc_fence_after();
+                auto hand_back = [&]() {
+                    named_barrier(bar_back, 128);                                        // this CTA's slot is drained and zeroed ...
+                    if (q == 0 && lane == 0) mbar_arrive_remote(&acc_empty[half], 0);    // ... one arrival per CTA on the issuer's barrier
+                };
+#pragma unroll
+                for (int m2 = 0; m2 < S::MH; ++m2) {
+                    const int mt = S::MH * half + m2;
                     const int w = w0 + 8 * mt + mw;
                     const bool ok = (h < p.H) && (w < p.W);
                     const size_t pos = ((size_t)z * p.H + h) * p.W + w;
@@ -332,19 +359,9 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
                     // the products that share the accumulator (3; DUAL: only x_hi w_hi)
                     const float comp = kTruncBiasPerMma * (float)((S::DUAL ? 1 : 3) * NKS * taps_inside(z, p.D, 1) * taps_inside(h, p.H, 1) * taps_inside(w, p.W, 1));
                     const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * S::ACC_N + slot * COUT);
-                    // who synchronises: MH == 2 all eight epilogue warps (barriers 3 / 5); MH == 1 the four warps of this group (3 / 5 and 6 / 7)
-                    const int n_sync = (S::MH == 1) ? 128 : EPI_THREADS;
-                    const int bar_full = (S::MH == 1 && g2 == 1) ? 6 : 3, bar_back = (S::MH == 1 && g2 == 1) ? 7 : 5;
-                    const bool leader = (S::MH == 1) ? (q == 0) : (e == 0);
-                    if (leader) mbar_wait_polls(&acc_full[half], (uint32_t)(n_seen & 1));
-                    named_barrier(bar_full, n_sync);
-                    tc_fence_after();
-                    auto hand_back = [&]() {
-                        named_barrier(bar_back, n_sync);                                     // this CTA's slot is drained and zeroed ...
-                        if (leader && lane == 0) mbar_arrive_remote(&acc_empty[half], 0);    // ... one arrival per CTA on the issuer's barrier
-                    };
                     const float mult_v = S::DUAL ? mult : mult * (1.0f + comp);
-                    ring_drain_slot<COUT, S::DUAL, N3, 0, 1>(ep, s_shift, mult_v, comp, t0, ok, pos, vox, want_gn, gs, gq, hand_back);
+                    if (m2 == S::MH - 1) ring_drain_slot<COUT, S::DUAL, N3, 0, 1>(ep, s_shift, mult_v, comp, t0, ok, pos, vox, want_gn, gs, gq, hand_back);
+                    else                 ring_drain_slot<COUT, S::DUAL, N3, 0, 1>(ep, s_shift, mult_v, comp, t0, ok, pos, vox, want_gn, gs, gq, []() {});
                 }
             }
         }

@@ -271,7 +271,7 @@ class PackedConv(object):
     """Folded, packed parameters of one 3x3x3 layer (see packing.pack_conv3d)."""
     __slots__ = ("weight", "scale", "shift", "cin_chunks", "cout_pad", "out_chunks", "act_split", "act_lo", "act_hi",
                  "cin", "cout", "weight_tc", "cout_pad_tc", "weight_f16", "scale_f16", "weight_ring", "weight_ring2", "scale_ring", "_desc",
-                 "precision", "cout_pad_ring2")
+                 "precision", "cout_pad_ring2", "weight_ring2d")
 
     def __init__(self, weight, scale, shift, cin_chunks, cout_pad, out_chunks, act_split, act_lo, act_hi,
                  cin=None, cout=None, weight_tc=None, cout_pad_tc=None):
@@ -279,6 +279,7 @@ class PackedConv(object):
         self._desc = None                                              # per-(arithmetic, mode) descriptor templates (_conv_desc)
         self.precision = None                                          # per-layer arithmetic override (None: the caller's choice)
         self.cout_pad_ring2 = None                                     # columns per ring slot of a narrow layer's CTA-pair packing
+        self.weight_ring2d = None                                      # CTA-pair packing for two accumulators per slot (merged B operand)
         self.weight_tc, self.cout_pad_tc = weight_tc, cout_pad_tc      # tcgen05 packings (packing.attach_tc)
         self.weight_f16, self.scale_f16 = None, None
         self.weight_ring = None                                        # plane-ring packing (packing.pack_weight_ring)
@@ -289,7 +290,8 @@ class PackedConv(object):
         self.cin_chunks, self.cout_pad, self.out_chunks = cin_chunks, cout_pad, out_chunks
         self.act_split, self.act_lo, self.act_hi = act_split, ACT[act_lo], ACT[act_hi]
 
-    TENSORS = ("weight", "scale", "shift", "weight_tc", "weight_f16", "scale_f16", "weight_ring", "weight_ring2", "scale_ring")
+    TENSORS = ("weight", "scale", "shift", "weight_tc", "weight_f16", "scale_f16", "weight_ring", "weight_ring2", "scale_ring",
+               "weight_ring2d")
 
     def to(self, device, memo=None):
         """Moves every buffer to ``device`` in place (one copy per buffer; ``memo`` de-duplicates buffers shared between
@@ -314,7 +316,7 @@ def _precision(pc, precision):
     precision = DEFAULT_PRECISION if precision is None else precision
     if precision not in PRECISION:
         raise RuntimeError("conv3d: unknown precision %r" % (precision,))
-    if precision == "3xf16r2d" and (pc.weight_ring2 is None or (pc.cout_pad_tc == 48 and pc.cout_pad_ring2 is None)):
+    if precision == "3xf16r2d" and pc.weight_ring2d is None:
         precision = "3xf16r2"          # two accumulators per slot do not fit TMEM for this shape
     if precision == "3xf16r2" and pc.weight_ring2 is None:
         precision = "3xf16r"           # same arithmetic and schedule on single CTAs: no CTA-pair specialisation for this shape
@@ -392,7 +394,7 @@ def _desc_template(pc, precision, planar, dilation, device):
     tc = precision != "fp32"
     d.weight = _ptr(pc.weight)
     f16 = precision in ("3xf16",) + RING_PRECISIONS
-    d.weight_tc = _ptr(pc.weight_ring2 if precision in ("3xf16r2", "3xf16r2d") else pc.weight_ring if precision == "3xf16r"
+    d.weight_tc = _ptr(pc.weight_ring2d if precision == "3xf16r2d" else pc.weight_ring2 if precision == "3xf16r2" else pc.weight_ring if precision == "3xf16r"
                        else pc.weight_f16 if precision == "3xf16" else pc.weight_tc)
     ring = precision in RING_PRECISIONS
     d.scale, d.shift = _ptr(pc.scale_ring if ring else pc.scale_f16 if f16 else pc.scale), _ptr(pc.shift)

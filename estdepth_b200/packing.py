@@ -158,7 +158,7 @@ RING2_SHAPES = ((2, 32), (3, 32), (1, 16), (2, 16), (3, 48))
 RING2_COMPACT = {(3, 48): 33}    # (k-steps, cout_pad_tc) -> columns per ring slot when the layer's real width allows fewer
 
 
-def pack_weight_ring2(packed, cout_pad_tc=None, scale=None, cslot=None):
+def pack_weight_ring2(packed, cout_pad_tc=None, scale=None, cslot=None, dual=False):
     """SIMT packing [27][cin_pad][cout_pad] -> CTA-pair ring packing of conv3d_ring2.cu,
     [7 live-tap masks][3 rotations][nks][2 CTAs][9 taps][hi,lo][2 K-groups][3*C/2 rows][8 x fp16] (float32-typed bytes)
     + the power-of-two exponent of ``pack_weight_f16``.
@@ -170,7 +170,12 @@ def pack_weight_ring2(packed, cout_pad_tc=None, scale=None, cslot=None):
 
     ``cslot`` (default C): rows per ring slot.  A layer with fewer real output channels than its padded width packs only
     ``cslot`` rows per slot and pads the TOTAL to a multiple of 16 -- the 33-channel layer dres2 (hybrid_depth_decoder.py:90)
-    gets N = 112 instead of 3 x 48 = 144: a fifth fewer tensor-core cycles, and 4 M tiles instead of 2 fit TMEM."""
+    gets N = 112 instead of 3 x 48 = 144: a fifth fewer tensor-core cycles, and 4 M tiles instead of 2 fit TMEM.
+
+    ``dual`` (two accumulators per ring slot, precision 3xf16r2d): per tap, CTA 0 holds a "merged" block with ALL N rows of w_hi
+    and CTA 1 one with all N rows of w_lo -- the two halves of the B operand [w_hi | w_lo] of ONE MMA with 2N columns (large
+    accumulator | small accumulator) -- followed by a "third" block with that CTA's half of w_hi for the x_lo w_hi product:
+    [7 masks][3 rotations][nks][2 CTAs][9 taps]{[2 K-groups][N rows], [2 K-groups][N/2 rows]}[8 x fp16]."""
     taps, cin_pad, cout_pad = packed.shape
     assert taps == 27
     C = tc_cout_pad(cout_pad) if cout_pad_tc is None else cout_pad_tc
@@ -204,6 +209,15 @@ def pack_weight_ring2(packed, cout_pad_tc=None, scale=None, cslot=None):
         for r in range(3):
             slots = [parts[(r - j + 1) % 3] if (mask >> ((r - j + 1) % 3)) & 1 else zero for j in range(3)]
             full = torch.cat(slots + [pad], dim=4)                            # [ks][tap9][prod][kg][N][e]
+            if dual:
+                hi_rows, lo_rows = full[:, :, 0], full[:, :, 1]                # [ks][tap9][kg][N][e]
+                per_cta = []
+                for cta in range(2):
+                    merged = (hi_rows if cta == 0 else lo_rows).reshape(nks, 9, 2 * n_rows, 8)
+                    third = hi_rows[:, :, :, cta * NH:(cta + 1) * NH].reshape(nks, 9, 2 * NH, 8)
+                    per_cta.append(torch.cat([merged, third], dim=2))          # [ks][tap9][2N + 2NH rows][e]
+                rots.append(torch.stack(per_cta, dim=1))                       # [ks][cta][tap9][rows][e]
+                continue
             halves = full.reshape(nks, 9, 2, 2, 2, NH, 8).permute(0, 4, 1, 2, 3, 5, 6)      # [ks][half][tap9][prod][kg][NH][e]
             rots.append(halves)
         variants.append(torch.stack(rots, dim=0))
@@ -227,8 +241,11 @@ def attach_tc(pc):
             # narrow layer: `cslot` columns per ring slot (conv3d_ring2.cu Shape<3, 33, 4>); the kernel is selected by cout_pad
             pc.cout_pad_ring2 = cslot
             pc.weight_ring2, k_ring2 = pack_weight_ring2(pc.weight[:, :, :cslot].contiguous(), pc.cout_pad_tc, pc.scale, cslot=cslot)
+            pc.weight_ring2d, _ = pack_weight_ring2(pc.weight[:, :, :cslot].contiguous(), pc.cout_pad_tc, pc.scale, cslot=cslot, dual=True)
         else:
             pc.weight_ring2, k_ring2 = pack_weight_ring2(pc.weight, pc.cout_pad_tc, pc.scale)
+            if pc.cout_pad_tc <= 32:                      # two accumulators per slot fit TMEM (and N = 6 * cout_pad <= 256)
+                pc.weight_ring2d, _ = pack_weight_ring2(pc.weight, pc.cout_pad_tc, pc.scale, dual=True)
     if pc.weight.shape[0] == 27 and (nks, pc.cout_pad_tc) in RING_SHAPES:
         pc.weight_ring, k_ring = pack_weight_ring(pc.weight, pc.cout_pad_tc, pc.scale)
         assert pc.weight_ring2 is None or k_ring2 == k_ring
