@@ -287,16 +287,18 @@ class MatchingFeatureNet(nn.Module):
         epilogues; activations stay in vol4 between them, pre-split (vol4s) wherever the reader is another planar layer."""
         from . import ops
         P = self._packed(x.device)
-        x = _folded(x, self.firstconv[0][0], self.firstconv[0][1], relu=True)   # 3->32 stride-2 stem conv: cuDNN
-        N, _, Hh, Wh = x.shape
-        half = lambda: torch.empty(8, N, Hh, Wh, 4, device=x.device, dtype=torch.float32)  # noqa: E731
-        cur = self._conv_tc(P["stem4"], self._conv_tc(P["stem2"], ops.nchw_to_vol4(x), half()), half())
+        # 3->32 stride-2 stem conv + BN + ReLU: the library's direct kernel, NCHW images -> (pre-split) vol4 in one pass
+        wf, bf = _folded.params(self.firstconv[0][0], self.firstconv[0][1])
+        stem = _tag(ops.stem_conv(x.contiguous(), wf, bf, out_split=SPLIT_ACTIVATIONS), SPLIT_ACTIVATIONS)
+        _, N, Hh, Wh, _ = stem.shape
+        dev = x.device
+        half = lambda: torch.empty(8, N, Hh, Wh, 4, device=dev, dtype=torch.float32)  # noqa: E731
+        cur = self._conv_tc(P["stem4"], self._conv_tc(P["stem2"], stem, half()), half())
         tmp = half()
         for i in range(len(self.layer1)):
             self._conv_tc(P[("layer1", i, 1)], cur, tmp)
             cur = self._conv_tc(P[("layer1", i, 2)], tmp, half(), cur)
         H, W = (Hh + 1) // 2, (Wh + 1) // 2
-        dev = x.device
 
         def vol(chunks):
             return torch.empty(chunks, N, H, W, 4, device=dev, dtype=torch.float32)

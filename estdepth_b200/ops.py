@@ -543,6 +543,20 @@ def nchw_to_vol4(x, out=None):
     return out
 
 
+def stem_conv(img_nchw, weight, bias, out=None, out_split=False):
+    """Conv2d(3, 32, 3, stride 2, pad 1) + folded affine + ReLU: NCHW images [N,3,H,W] -> vol4 [8,N,Ho,Wo,4] (optionally pre-split)."""
+    N, C, H, W = img_nchw.shape
+    if C != 3 or tuple(weight.shape) != (32, 3, 3, 3):
+        raise RuntimeError("stem_conv: 3 -> 32 channels, 3x3 filter only")
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty(8, N, Ho, Wo, 4, device=img_nchw.device, dtype=torch.float32) if out is None else out
+    t = _pb()
+    check(_lib.get().estd_stem_conv(_ptr(img_nchw), _ptr(weight), _ptr(bias), _ptr(out), N, H, W, int(bool(out_split)),
+                                    _ptr(status_flag(img_nchw.device), torch.int32) if out_split else None, _stream()), "estd_stem_conv")
+    _pe(t, "stem_conv", 2.0 * 27 * 32 * N * Ho * Wo, 4.0 * N * (3 * H * W + 32 * Ho * Wo))
+    return out
+
+
 def vol4_to_nchw(v, out=None):
     chunks, N, H, W, _ = v.shape
     out = torch.empty(N, chunks * 4, H, W, device=v.device, dtype=torch.float32) if out is None else out

@@ -212,6 +212,13 @@ ESTD_API int estd_ncdhw_to_vol4(const float* ncdhw, float* vol4, int C, int D, i
 /* stack of N feature maps: torch NCHW [N][C][H][W] <-> vol4 [C/4][N][H][W][4] (planes = maps), for the planar
  * tensor-core convolutions of the matching-feature net (networks/psm_submodule.py:14-37,51-54) */
 ESTD_API int estd_nchw_to_vol4(const float* nchw, float* vol4, int N, int C, int H, int W, void* stream);
+
+/* First layer of the matching-feature net: Conv2d(3, 32, 3, stride 2, pad 1) + folded BN + ReLU (networks/psm_submodule.py:42-44)
+ * from the NCHW image stack [N][3][H][W] into vol4 [8][N][Ho][Wo][4], Ho = (H - 1) / 2 + 1.  weight: [32][3][3][3] with the BN
+ * multiplier folded in, bias: [32] folded offset.  out_split: write the result pre-split (vol4s, see estd_conv3d_desc); status:
+ * optional device int OR-ed with 1 when a value leaves the fp16 range (out_split only). */
+ESTD_API int estd_stem_conv(const float* img_nchw, const float* weight, const float* bias, float* out_vol4, int N, int H, int W,
+                   int out_split, int* status, void* stream);
 ESTD_API int estd_vol4_to_nchw(const float* vol4, float* nchw, int N, int C, int H, int W, void* stream);
 /* vol4 [C/4][N][H][W][4] = bilinear resize (align_corners = 0, ATen upsample_bilinear2d arithmetic) of relu?(src + bias[c]),
  * src NCHW [N][C][h][w]; bias may be NULL.  Replaces conv-bias/ReLU + F.upsample + torch.cat of the SPP branches

@@ -275,9 +275,13 @@ def test_cuda_poses_vs_reference_algorithm_on_the_same_gpu_cfg2():
 # ------------------------------------------------------------------------------------------- feature cache
 def test_frame_id_feature_cache_estm_cfg3():
     """ESTM at 480 x 640 with and without ``frame_ids`` (consecutive 3-frame windows share 2 frames: their matching features
-    are computed once, where eval_hybrid_seq.py:169-190 recomputes them).  Same depth maps bit for bit (the in-house kernels are
-    batch invariant, and so is the cuDNN stem with benchmark off); steady-state time per step printed for both and compared."""
+    are computed once, where eval_hybrid_seq.py:169-190 recomputes them).  Same depth maps bit for bit (the kernels are batch
+    invariant); the matching-feature net sees one new frame per steady-state step instead of three.  Steady-state time per step
+    is printed for both (the clean-process measurement is bench.py's extras.cfg3_estm.with_frame_ids: inside a long pytest
+    process the 6 ms steps are host bound and the GPU time saved does not show)."""
     model, _ = _model(50, 64)
+    frames_seen = []
+    hook = model.matchingFeature.register_forward_hook(lambda mod, args, out: frames_seen.append(int(args[0].shape[0])))
     torch.backends.cudnn.benchmark = False
     n_frames = 14
     windows = [synth.synth_inputs(3, 480, 640, seed=0, start=s) for s in range(n_frames - 2)]
@@ -303,7 +307,12 @@ def test_frame_id_feature_cache_estm_cfg3():
         return torch.cat(maps), e0.elapsed_time(e1) / (len(windows) - 2)
 
     run(False)
+    n0 = len(frames_seen)
     run(True)
+    per_step_with_ids = frames_seen[n0:]
+    assert frames_seen[:n0] == [3] * (n_frames - 2)                     # the reference's behaviour: every window recomputes its 3 frames
+    assert per_step_with_ids == [3] + [1] * (n_frames - 3)             # with ids: 3 new frames in the first window, then 1 per step
+    hook.remove()
     times = {False: [], True: []}
     for _ in range(3):
         for with_ids in (False, True):
@@ -317,8 +326,7 @@ def test_frame_id_feature_cache_estm_cfg3():
     diff = float((plain - cached).abs().max())
     print("frame-id feature cache, ESTM steady state at 480x640: %.2f ms/step without ids, %.2f ms/step with ids (%.1f %% less); "
           "max |depth diff| = %.3e" % (ms_plain, ms_cached, 100.0 * (1 - ms_cached / ms_plain), diff))
-    assert diff < 1e-4, diff
-    assert ms_cached < ms_plain
+    assert diff == 0.0, diff
 
 
 # ------------------------------------------------------------------------------------------- driver I/O

@@ -608,3 +608,20 @@ def test_fused_logit_head_equals_head_conv_then_1x1x1(precision):
     assert (logits_b.cpu() - want).abs().max().item() < 2e-5
     assert (logits_b - logits_a).abs().max().item() < 2e-5
     assert (depth_b - depth_a).abs().max().item() < 1e-4 and (prob_b - prob_a).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 96), (3, 37, 53)], ids=["even", "odd"])
+def test_stem_conv_matches_conv2d_bn_relu(shape):
+    """psm_submodule.py:42-44: convbn(3, 32, 3, stride 2, pad 1) + ReLU, straight from NCHW images into vol4 (fp32 and pre-split)."""
+    N, H, W = shape
+    g = torch.Generator().manual_seed(9)
+    img = torch.rand(N, 3, H, W, generator=g) * 2 - 1
+    w = torch.randn(32, 3, 3, 3, generator=g) / 27 ** 0.5
+    b = torch.randn(32, generator=g) / 3
+    want = F.relu(F.conv2d(img, w, b, stride=2, padding=1))
+    got = ops.stem_conv(img.to(DEV), w.to(DEV), b.to(DEV))
+    assert tuple(got.shape) == (8, N, want.shape[2], want.shape[3], 4)
+    assert maxdiff(ops.vol4_to_nchw(got).cpu(), want) < 2e-6
+    split = ops.stem_conv(img.to(DEV), w.to(DEV), b.to(DEV), out_split=True)
+    assert torch.equal(split, ops.to_split(got))
+    ops.check_status(torch.device(DEV))
