@@ -13,6 +13,9 @@ timeout 400 ncu --profile-from-start off --set full --clock-control none --impor
 ncu -i /tmp/conv3d.ncu-rep --page raw --csv > gpurun_out/conv3d_r02.csv 2>/dev/null
 timeout 400 ncu --profile-from-start off --set full --clock-control none -k regex:"est_attend|head_softargmin|gru_blend|gru_reset|warp_cost|premix|gn_finalize" -c 24 -o /tmp/hbm -f python profiles/profile_step.py >> gpurun_out/ncu_r02.log 2>&1
 ncu -i /tmp/hbm.ncu-rep --page raw --csv > gpurun_out/hbm_kernels_r02.csv 2>/dev/null
+# BASELINE configs[4]: 640x960, D=128 -- ncu roofline capture of the fused warp -> cost-volume kernel
+timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"warp_cost" -c 2 -o /tmp/k1cfg5 -f python profiles/profile_step.py cfg5 >> gpurun_out/ncu_r02.log 2>&1
+ncu -i /tmp/k1cfg5.ncu-rep --page raw --csv > gpurun_out/warp_cost_cfg5_r02.csv 2>/dev/null
 timeout 400 ncu --profile-from-start off --section SpeedOfLight --section MemoryWorkloadAnalysis --section WarpStateStats --section LaunchStats --section Occupancy --section ComputeWorkloadAnalysis --clock-control none -k regex:"conv2d_tc" -c 130 -o /tmp/planar -f python profiles/profile_step.py >> gpurun_out/ncu_r02.log 2>&1
 ncu -i /tmp/planar.ncu-rep --page raw --csv > gpurun_out/planar_r02.csv 2>/dev/null
 for m in joint estm estm_ids; do timeout 120 python profiles/host_profile.py $m; done > gpurun_out/host_profile_r02.txt 2>&1
