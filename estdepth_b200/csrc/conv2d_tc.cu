@@ -16,6 +16,10 @@
 //            (profiles/mma_probe.cu: an M=128, K=16 MMA costs max(N/2, 32 + N/4) cycles).
 //   TMEM     2 M tiles x 2C columns per unit, double buffered: the epilogue of unit u (8 warps: TMEM -> hi + lo -> affine ->
 //            activation -> residual -> 16-byte stores) overlaps the MMAs of unit u+1.
+//   Pre-split inputs (vol4s, the normal case between planar layers) need no splitter: the issuer waits on the TMA barrier
+//            itself and the 8 splitter warps become 8 MORE epilogue warps (each warp then owns half of the slice's channels
+//            of its 32 pixels).  ncu (profiles/planar_epilogue_r02.txt): with 8 epilogue warps the 1x1 layers were bound by
+//            the epilogue's instruction issue (440 instructions per 16-channel block and warp, 2 warps per scheduler).
 //   The number of 16-channel k-steps is a run-time argument (64 ... 2048 input channels use the same kernel), and layers
 //   wider than COUT run as cout_pad/COUT slices INSIDE one launch (unit = tile x slice, slices of a tile on adjacent CTAs so
 //   that the input tile is shared through L2): the small, deep maps of the context decoder (15x20 ... 30x40 pixels, 256
@@ -71,6 +75,7 @@ struct Params {
     ConvEpilogue ep;
     int in0_chunks, nks;
     int in0_split, in1_split;                   // the input segments are pre-split (vol4s): the splitter warps pass them through
+    int all_presplit;                           // every input segment is: no splitter pass, the splitter warps join the epilogue
     int D, H, W;                                // D = number of maps in the stack
     int tiles_h, tiles_w, n_units;
 };
@@ -92,15 +97,19 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nks = p.nks;
+    // helpers: the splitter warps work as a second set of epilogue warps (needs two 16-channel blocks per slice)
+    const bool helpers = p.all_presplit && COUT >= 32;
+    const int epi_threads = helpers ? EPI_THREADS + SPLIT_THREADS : EPI_THREADS;
 
     pdl_launch_dependents();                 // the next kernel of the stream may start its prologue as SMs free up
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], SPLIT_THREADS); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_THREADS); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], epi_threads); }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_base_smem, S::TMEM_COLS);
-    if (warp == 3) for (int i = lane; i < p.cout_total; i += 32) { s_scale[i] = p.ep.scale[i]; s_shift[i] = p.ep.shift[i]; }
+    // all threads: a 2048-channel layer read by one warp was 64 dependent round trips before the first TMA could be issued
+    for (int i = tid; i < p.cout_total; i += THREADS) { s_scale[i] = p.ep.scale[i]; s_shift[i] = p.ep.shift[i]; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -149,7 +158,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             const uint32_t acc0 = tmem_base + (uint32_t)(buf * S::COLS_PER_UNIT);
             for (int ks = 0; ks < nks; ++ks, ++it) {
                 const int s = it % STAGES;
-                mbar_wait_polls(&ready[s], (uint32_t)((it / STAGES) & 1));
+                mbar_wait_polls(p.all_presplit ? &full[s] : &ready[s], (uint32_t)((it / STAGES) & 1));
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(smem + (size_t)s * S::STAGE_BYTES);
                 const uint64_t a_hi_desc = make_desc(a_hi, 2 * S::KGROUP_BYTES, HALO_W * 16);
@@ -174,7 +183,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                 __syncwarp();
             }
         }
-    } else if (warp >= FIRST_SPLIT_WARP) {
+    } else if (warp >= FIRST_SPLIT_WARP && !p.all_presplit) {
         // ===================== hi/lo splitter =====================
         const int t = tid - FIRST_SPLIT_WARP * 32;
         float amax = 0.0f;
@@ -208,13 +217,35 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         }
         const bool bad = !(amax <= 65504.0f);
         if (bad && p.status) atomicOr(p.status, 1);
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && (warp < FIRST_SPLIT_WARP || helpers)) {
         // ===================== epilogue =====================
-        const int e = warp - 4, q = e & 3, mt = e >> 2;          // TMEM lane quarter; M tile
+        const int e = warp - 4, q = e & 3, mt = (e >> 2) & 1;    // TMEM lane quarter (= warp % 4); M tile
+        // channels of the slice this warp handles: all of them, or one half when the splitter warps help
+        const int c_lo = helpers ? (e >> 3) * (COUT / 2) : 0, c_hi = helpers ? c_lo + COUT / 2 : COUT;
         const int m = q * 32 + lane;
         const int mh = m >> 3, mw = m & 7;
         const size_t vox = (size_t)p.D * p.H * p.W;
         const ConvEpilogue& ep = p.ep;
+        const int act = ep.act_hi;                               // planar layers have one activation (checked by the launcher)
+        const bool has_res = ep.res0 != nullptr;
+        // residual of one 16-channel block of this thread's pixel in unit k: issued as soon as the previous one is consumed -- for
+        // the next block of the unit, or for the first block of this CTA's NEXT unit -- so that its latency hides behind the split
+        // and the stores of this block and the TMEM loads of the next (issued at the start of each unit it was fully exposed)
+        float4 r0[4];
+        auto issue_res = [&](int k, int c0) {
+            int d, h0, w0, slice;
+            unit_origin(k, d, h0, w0, slice);
+            const int h = h0 + mh, w = w0 + 8 * mt + mw;
+            const bool ok = (h < p.H) && (w < p.W);
+            const size_t pos = ((size_t)d * p.H + h) * p.W + w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ch = ((slice * COUT + c0) >> 2) + j;
+                r0[j] = (ok && ch < ep.out_chunks) ? ldg4(ep.res0 + ((size_t)ch * vox + pos) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        if (has_res && n_mine > 0) issue_res(0, c_lo);
+        float amax = 0.0f;
         for (int k = 0; k < n_mine; ++k) {
             const int buf = k & 1, use = k >> 1;
             int d, h0, w0, slice;
@@ -227,91 +258,74 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             const size_t ovox = ep.out_up2 ? 4 * vox : vox;
             const size_t opos = ep.out_up2 ? ((size_t)d * 2 * p.H + 2 * h) * (2 * p.W) + 2 * w : pos;
             const size_t orow = (size_t)2 * p.W * 4;               // floats per row of the up-sampled map
-            float4 r0[4];
-            auto load_res = [&](int c0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int ch = ((cbase + c0) >> 2) + j;
-                    const bool valid = ok && ch < ep.out_chunks;
-                    r0[j] = (ep.res0 && valid) ? ldg4(ep.res0 + ((size_t)ch * vox + pos) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            };
-            float amax = 0.0f;
-            load_res(0);
             const float mult = s_scale[cbase];                     // uniform within a slice: the per-channel multiplier is folded into the weights
             // truncation-bias compensation (common.cuh): the large-product accumulator received one MMA per k-step for every
             // filter tap inside the map (the small products accumulate apart and need none)
             const float comp = kTruncBiasPerMma * (float)(nks * (S::TAPS == 9 ? taps_inside(h, p.H, S::DIL) * taps_inside(w, p.W, S::DIL) : 1));
             if (e == 0) mbar_wait_polls(&acc_full[buf], (uint32_t)(use & 1));
-            named_barrier(3, EPI_THREADS);
+            named_barrier(3, epi_threads);
             tc_fence_after();
             const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * S::COLS_PER_UNIT + mt * N_ALL);
 #pragma unroll 1
-            for (int c0 = 0; c0 < COUT; c0 += 16) {
+            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+                float a[16], b[16];
+                tmem_ld16(t0 + (uint32_t)c0, a);
+                tmem_ld16(t0 + (uint32_t)(COUT + c0), b);
                 // the 16 offsets of this block in one batch (a shared-memory load queues behind the tensor core's operand fetches)
                 float4 sh[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sh[j] = *reinterpret_cast<const float4*>(s_shift + cbase + c0 + 4 * j);
-                float a[16], b[16];
-                tmem_ld16(t0 + (uint32_t)c0, a);
-                tmem_ld16(t0 + (uint32_t)(COUT + c0), b);
                 tmem_ld_wait();
-                if (ep.res0 && ep.res_split) {                     // vol4s residual: chunks (0,1) = hi / lo of 8 channels, (2,3) of the next 8
-                    float t[16];
-                    join8(r0[0], r0[1], t); join8(r0[2], r0[3], t + 8);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) r0[j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
-                }
-                float o[16];
+                float v[16];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int c = cbase + c0 + 4 * j;
-                    const int ch = c >> 2;
+                    const float s4[4] = {sh[j].x, sh[j].y, sh[j].z, sh[j].w};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) o[4 * j + i] = 0.0f;
-                    if (!ok || ch >= ep.out_chunks) continue;
-                    const int act = (c < ep.act_split) ? ep.act_lo : ep.act_hi;
-                    float v[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] = fmaf(a[4 * j + i], comp, a[4 * j + i]) + b[4 * j + i];
-                    v[0] = fmaf(v[0], mult, sh[j].x); v[1] = fmaf(v[1], mult, sh[j].y);
-                    v[2] = fmaf(v[2], mult, sh[j].z); v[3] = fmaf(v[3], mult, sh[j].w);
-                    if (act == ESTD_ACT_RELU) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.0f);
-                    } else if (act == ESTD_ACT_TANH) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) v[i] = tanhf(v[i]);
-                    } else if (act == ESTD_ACT_SIGMOID) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) v[i] = sigmoidf_acc(v[i]);
-                    }
-                    v[0] += r0[j].x; v[1] += r0[j].y; v[2] += r0[j].z; v[3] += r0[j].w;
-                    if (act == ESTD_ACT_ADD_RELU) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.0f);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) o[4 * j + i] = v[i] * ep.post_scale;
-                    if (ep.out_split) continue;
-                    const float4 o4 = make_float4(o[4 * j + 0], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                    if (ep.out_up2) {                                // nearest x2: the pixel's 2 x 2 block of the [2H][2W] map
-                        float* dst = ep.out0 + ((size_t)ch * ovox + opos) * 4;
-                        st4(dst, o4); st4(dst + 4, o4); st4(dst + orow, o4); st4(dst + orow + 4, o4);
-                        continue;
-                    }
-                    const size_t off = ((size_t)ch * vox + pos) * 4;
-                    float* dst = (ch < ep.out0_chunks) ? ep.out0 + off : ep.out1 + (off - (size_t)ep.out0_chunks * vox * 4);
-                    st4(dst, o4);
+                    for (int i = 0; i < 4; ++i) v[4 * j + i] = fmaf(fmaf(a[4 * j + i], comp, a[4 * j + i]) + b[4 * j + i], mult, s4[i]);
                 }
+                if (act == ESTD_ACT_RELU) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+                } else if (act == ESTD_ACT_TANH) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
+                } else if (act == ESTD_ACT_SIGMOID) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = sigmoidf_acc(v[i]);
+                }
+                if (has_res) {
+                    if (ep.res_split) {                            // vol4s residual: chunks (0,1) = hi / lo of 8 channels, (2,3) of the next 8
+                        float t[8];
+                        join8(r0[0], r0[1], t);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] += t[i];
+                        join8(r0[2], r0[3], t);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[8 + i] += t[i];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { v[4 * j] += r0[j].x; v[4 * j + 1] += r0[j].y; v[4 * j + 2] += r0[j].z; v[4 * j + 3] += r0[j].w; }
+                    }
+                    if (c0 + 16 < c_hi) issue_res(k, c0 + 16);
+                    else if (k + 1 < n_mine) issue_res(k + 1, c_lo);
+                }
+                if (act == ESTD_ACT_ADD_RELU) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+                }
+                if (ep.post_scale != 1.0f) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] *= ep.post_scale;
+                }
+                const int ch0 = (cbase + c0) >> 2;                 // first of the block's 4 output chunks
                 if (ep.out_split) {
                     // vol4s: x_hi of 8 channels -> chunk c/4, x_lo -> the next chunk
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
-                        const int ch = ((cbase + c0) >> 2) + 2 * g;
-                        if (!ok || ch >= ep.out_chunks) continue;
+                        const int ch = ch0 + 2 * g;
                         uint4 hi, lo;
-                        split8(o + 8 * g, hi, lo, amax);
+                        split8(v + 8 * g, hi, lo, amax);
+                        if (!ok || ch >= ep.out_chunks) continue;
                         float* dst = ep.out0 + ((size_t)ch * ovox + opos) * 4;
                         uint4* dh = reinterpret_cast<uint4*>(dst);
                         uint4* dl = reinterpret_cast<uint4*>(dst + ovox * 4);
@@ -323,13 +337,28 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                             dh2[0] = hi; dh2[1] = hi; dl2[0] = lo; dl2[1] = lo;
                         }
                     }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int ch = ch0 + j;
+                        if (!ok || ch >= ep.out_chunks) continue;
+                        const float4 o4 = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        if (ep.out_up2) {                            // nearest x2: the pixel's 2 x 2 block of the [2H][2W] map
+                            float* dst = ep.out0 + ((size_t)ch * ovox + opos) * 4;
+                            st4(dst, o4); st4(dst + 4, o4); st4(dst + orow, o4); st4(dst + orow + 4, o4);
+                            continue;
+                        }
+                        const size_t off = ((size_t)ch * vox + pos) * 4;
+                        float* dst = (ch < ep.out0_chunks) ? ep.out0 + off : ep.out1 + (off - (size_t)ep.out0_chunks * vox * 4);
+                        st4(dst, o4);
+                    }
                 }
-                if (c0 + 16 < COUT) load_res(c0 + 16);
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);
-            if (ep.out_split && !(amax <= 65504.0f) && ep.status) atomicOr(ep.status, 1);
         }
+        // values of pixels outside the map come from zero-filled tiles and channels beyond out_chunks from zero weights: finite
+        if (ep.out_split && !(amax <= 65504.0f) && ep.status) atomicOr(ep.status, 1);
     }
 
     tc_fence_before();
@@ -351,6 +380,7 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
     ESTD_REQUIRE(d->in1_chunks == 0 || (d->in0_chunks % 4) == 0, "estd_conv3d(planar): first input segment must hold a multiple of 4 chunks");
     ESTD_REQUIRE(!d->gn_partials && !d->res1, "estd_conv3d(planar): GroupNorm partial sums / second residual are not implemented for planar convolutions");
     ESTD_REQUIRE(!d->out_up2 || !d->out1, "estd_conv3d(planar): an up-sampled output is one tensor");
+    ESTD_REQUIRE(d->act_lo == d->act_hi, "estd_conv3d(planar): one activation per layer (act_lo == act_hi)");
     CUtensorMap map0, map1;
     int rc = make_vol4_tensor_map(&map0, d->in0, d->in0_chunks, d->D, d->H, d->W, S::HALO_W * 4, S::HALO_H, 1, 4);
     if (rc) return rc;
@@ -364,6 +394,7 @@ static int launch(const estd_conv3d_desc* d, cudaStream_t stream, bool count_onl
     fill_epilogue(&p.ep, d);
     p.in0_chunks = d->in0_chunks;
     p.in0_split = d->in0_split; p.in1_split = d->in1_split;
+    p.all_presplit = d->in0_split && (d->in1_chunks == 0 || d->in1_split);
     p.nks = (cin_chunks + 3) / 4;
     p.D = d->D; p.H = d->H; p.W = d->W;
     p.tiles_h = tiles_h; p.tiles_w = tiles_w; p.n_units = (int)n_units;
