@@ -342,6 +342,27 @@ conv3d_ring2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
             const int h = h0 + mh;
             for (int z = sg.z0; z < sg.z1; ++z, ++n_seen) {
                 const int slot = z % 3;
+                // residuals of the NEXT plane -> L2, one plane period ahead of their use.  The drain cannot hold them in registers
+                // (two accumulators per slot fill the budget) and consumes every load right after issuing it: one exposed latency per
+                // 16-channel block and residual.  32->32 at cfg2 size with 0 / 1 / 2 residuals: 171 / 197 / 269 us before, 171 / 190 /
+                // 247 us with the prefetch (profiles/ring_residual_r02.txt).  Staging the tile in shared memory by TMA instead was
+                // measured and is no better (195 / 245 us): what is left is not latency but the residual's bytes competing with the
+                // tensor core's operand fetches for the shared-memory / L1 data pipe.
+                if (ep.res0 && z + 1 < sg.z1) {
+#pragma unroll
+                    for (int m2 = 0; m2 < S::MH; ++m2) {
+                        const int w = w0 + 8 * (S::MH * half + m2) + mw;
+                        if (h < p.H && w < p.W) {
+                            const size_t posn = ((size_t)(z + 1) * p.H + h) * p.W + w;
+#pragma unroll
+                            for (int ch = 0; ch < (COUT + 3) / 4; ++ch) {
+                                if (ch >= ep.out_chunks) break;
+                                prefetch_l2(ep.res0 + ((size_t)ch * vox + posn) * 4);
+                                if (ep.res1) prefetch_l2(ep.res1 + ((size_t)ch * vox + posn) * 4);
+                            }
+                        }
+                    }
+                }
                 if (q == 0) mbar_wait_polls(&acc_full[half], (uint32_t)(n_seen & 1));
                 named_barrier(bar_full, 128);
                 tc_fence_after();
