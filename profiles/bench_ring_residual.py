@@ -47,3 +47,11 @@ outs = [torch.empty(8, D, H, W, 4, device=dev) for _ in range(3)]
 for name, kw in (("no residual", lambda i: {}), ("one residual", lambda i: dict(res0=r0[i % 3])), ("two residuals", lambda i: dict(res0=r0[i % 3], res1=r1[i % 3]))):
     t = timeit(lambda i: ops.conv3d(pc, xs[i % 3], outs[i % 3], precision="3xf16r2d", **kw(i)))
     print("ring2d 32->32 %-14s %7.1f us" % (name, t))
+
+# the 16-channel layers (logit-head convolutions 16->16, ConvGRU gates 32->16): two M tiles per epilogue group
+for cin in (16, 32):
+    w = torch.randn(16, cin, 3, 3, 3, generator=g) / (cin * 27) ** 0.5
+    pc = packing.attach_tc(ops.PackedConv(packing.pack_weight(w, list(range(cin)), list(range(16))), torch.ones(16), torch.zeros(16), cin // 4, 16, 4, 16, "relu", "relu")).to(dev)
+    xin = [torch.randn(cin // 4, D, H, W, 4, device=dev) for _ in range(3)]
+    t = timeit(lambda i: ops.conv3d(pc, xin[i % 3], outs[i % 3][:4], precision="3xf16r2d"))
+    print("ring2d %2d->16               %7.1f us" % (cin, t))
