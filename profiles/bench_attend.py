@@ -1,10 +1,14 @@
-"""K3 (EST attention gather) isolated at cfg2 size, N = 1..3, for the kernel variants / register budgets:
-    ESTD_ATTEND=twopass | ESTD_ATTEND_OCC=4|5|6|8   python profiles/bench_attend.py"""
+"""K3 (EST attention gather) isolated at cfg2 size, N = 1..3:  python profiles/bench_attend.py [path/to/other/libestdepth_b200.so]
+(the optional argument times another build of the library: A/B of kernel variants on one box)."""
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
+from estdepth_b200 import _lib  # noqa: E402
+
+if len(sys.argv) > 1:
+    _lib.LIB_PATH = os.path.abspath(sys.argv[1])
 from estdepth_b200 import ops, synth  # noqa: E402
 
 dev = "cuda"
@@ -18,7 +22,7 @@ kv = [torch.randn(4, D, H, W, 4, generator=g).to(dev) for _ in range(8)]
 hs = [torch.empty(4, D, H, W, 4, device=dev) for _ in range(2)]
 tabs = ops.volume_warp_tables_torch([poses[2], poses[1], poses[3], poses[0]], 1, K4)[0].contiguous()
 dv = (torch.arange(D, dtype=torch.float32) * (9.9 / (D - 1)) + 0.1).to(dev)
-tag = "twopass" if os.environ.get("ESTD_ATTEND", "").startswith("t") else "onepass occ=%s" % os.environ.get("ESTD_ATTEND_OCC", "6")
+tag = os.path.basename(os.path.dirname(_lib.LIB_PATH))
 for n in (1, 2, 3):
     def run(i):
         ops.est_attend(kv[0], [kv[1 + 2 * j] for j in range(n)], [kv[2 + 2 * j] for j in range(n)], tabs[:n].contiguous(), dv, 0.1, 9.9 / (D - 1), out=hs[i % 2])
