@@ -60,6 +60,8 @@ SIGNATURES = {
     "estd_scalar_to_vol4": (_I, [_P, _P, _I, _I, _I, _P]),
     "estd_nchw_to_vol4": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "estd_stem_conv": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "estd_stem7_conv": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "estd_maxpool3x3s2_vol4": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "estd_upsample_bilinear_vol4": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "estd_vol4_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _P]),
 }

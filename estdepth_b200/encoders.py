@@ -415,6 +415,15 @@ class ContextEncoder(nn.Module):
             return _folded(y, blk.conv3, blk.bn3, relu=True, residual=identity)
         return _folded(y, blk.conv2, blk.bn2, relu=True, residual=identity)
 
+    @staticmethod
+    def _plain_stem(e):
+        """torchvision's stem as the direct kernels implement it: conv 7x7 / 2 / pad 3 without bias, max-pool 3 / 2 / pad 1."""
+        c, p = e.conv1, e.maxpool
+        pair = lambda v: tuple(v) if isinstance(v, (tuple, list)) else (v, v)  # noqa: E731
+        return (tuple(c.weight.shape) == (64, 3, 7, 7) and c.bias is None and c.stride == (2, 2) and c.padding == (3, 3) and
+                c.dilation == (1, 1) and c.groups == 1 and pair(p.kernel_size) == (3, 3) and pair(p.stride) == (2, 2) and
+                pair(p.padding) == (1, 1) and pair(p.dilation) == (1, 1) and not p.ceil_mode)
+
     def _stage_tc(self, stage, x4):
         """One ResNet stage (Bottlenecks: ResNet-50/101/152, BasicBlocks: ResNet-18/34) on the planar tcgen05 kernel;
         activations stay in vol4 from the max-pool to the decoder (no NCHW copies between stages).  The stride-2 3x3 of a
@@ -448,16 +457,28 @@ class ContextEncoder(nn.Module):
             for stage in (e.layer2, e.layer3, e.layer4):
                 maps.append(stage(maps[-1]))
             return maps
-        maps = [_folded(x, e.conv1, e.bn1, relu=True)]
-        x = e.maxpool(maps[-1])
         if self.tensor_cores and x.is_cuda:
-            # maps[1:] are returned in vol4 (5-D); the decoder's tensor-core path consumes them as they are (_as_vol4)
+            # every map is returned in vol4 (5-D); the decoder's tensor-core path consumes them as they are (_as_vol4).
+            # conv1 (7x7 stride 2) + BN + ReLU and the 3x3 stride-2 max-pool are the library's direct kernels: NCHW images ->
+            # pre-split vol4, no cuDNN convolution and no layout pass left in the context branch
             from . import ops
-            x4 = ops.nchw_to_vol4(x.contiguous())
+            if self._plain_stem(e):
+                wf, bf = _folded.params(e.conv1, e.bn1)
+                cached = getattr(self, "_stem7_w", None)
+                if cached is None or cached[0] is not wf:            # tap-major copy of the folded weight, made once
+                    cached = self._stem7_w = (wf, wf.permute(1, 2, 3, 0).contiguous())
+                stem = _tag(ops.stem7_conv(x.contiguous(), cached[1], bf, out_split=SPLIT_ACTIVATIONS), SPLIT_ACTIVATIONS)
+                x4 = _tag(ops.maxpool3x3s2_vol4(stem, in_split=SPLIT_ACTIVATIONS, out_split=SPLIT_ACTIVATIONS), SPLIT_ACTIVATIONS)
+                maps = [stem]
+            else:
+                maps = [_folded(x, e.conv1, e.bn1, relu=True)]
+                x4 = ops.nchw_to_vol4(e.maxpool(maps[-1]).contiguous())
             for stage in (e.layer1, e.layer2, e.layer3, e.layer4):
                 x4 = self._stage_tc(stage, x4)
                 maps.append(x4)
             return maps
+        maps = [_folded(x, e.conv1, e.bn1, relu=True)]
+        x = e.maxpool(maps[-1])
         for stage in (e.layer1, e.layer2, e.layer3, e.layer4):
             for blk in stage:
                 x = self._block(blk, x)
@@ -569,16 +590,17 @@ class ContextDecoder2D(nn.Module):
         """fused_logits: [B*T, D, H/4, W/4] raw logits of stereo_head1 (ReLU applied here, :268)."""
         from . import ops
         P = self._use_tc(semantic_vs, ("upconv_1_0", "upconv_1_1", "upconv_0_0", "upconv_0_1", "dispconv_1", "dispconv_0"))
-        if P is not None and semantic_vs.shape[1] % 16 == 0 and skip_half.shape[1] % 16 == 0:
+        if P is not None and semantic_vs.shape[1] % 16 == 0 and _channels(skip_half) % 16 == 0:
             # whole refinement on the planar tcgen05 kernel: cat -> second input segment, sigmoid * depth_max in the epilogue
             x = _run3x3(P["upconv_1_0"], _as_vol4(semantic_vs), in1=ops.nchw_to_vol4(F.relu(fused_logits)), up2=True)
-            x = _run3x3(P["upconv_1_1"], x, in1=ops.nchw_to_vol4(skip_half.contiguous()))
+            x = _run3x3(P["upconv_1_1"], x, in1=_as_vol4(skip_half))
             d1 = _run3x3(P["dispconv_1"], x, post_scale=self.depth_max, out_split=False)  # [1 chunk, N, H/2, W/2, 4]
             depth_half = _up2(d1[0, ..., 0].unsqueeze(1))
             x = _run3x3(P["upconv_0_1"], _run3x3(P["upconv_0_0"], x, up2=True))
             depth_full = _run3x3(P["dispconv_0"], x, post_scale=self.depth_max, out_split=False)[0, ..., 0].unsqueeze(1).contiguous()
             return depth_half, depth_full
         self._log_cudnn("refinement", semantic_vs)
+        skip_half = _as_nchw(skip_half)
         x = self.upconv_1_0(torch.cat([semantic_vs, F.relu(fused_logits)], dim=1))
         x = self.upconv_1_1(torch.cat([_up2(x), skip_half], 1))
         depth_half = _up2(self.depth_max * torch.sigmoid(self.dispconv_1(x)))

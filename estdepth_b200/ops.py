@@ -557,6 +557,33 @@ def stem_conv(img_nchw, weight, bias, out=None, out_split=False):
     return out
 
 
+def stem7_conv(img_nchw, weight, bias, out=None, out_split=False):
+    """torchvision ResNet conv1: Conv2d(3, 64, 7, stride 2, pad 3) + folded affine + ReLU: NCHW images [N,3,H,W] -> vol4
+    [16,N,Ho,Wo,4] (optionally pre-split).  ``weight`` is TAP-MAJOR: the PyTorch weight [64,3,7,7] permuted to [3,7,7,64]."""
+    N, C, H, W = img_nchw.shape
+    if C != 3 or tuple(weight.shape) != (3, 7, 7, 64):
+        raise RuntimeError("stem7_conv: 3 -> 64 channels, 7x7 filter, weight permuted to [3, 7, 7, 64]")
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty(16, N, Ho, Wo, 4, device=img_nchw.device, dtype=torch.float32) if out is None else out
+    t = _pb()
+    check(_lib.get().estd_stem7_conv(_ptr(img_nchw), _ptr(weight), _ptr(bias), _ptr(out), N, H, W, int(bool(out_split)),
+                                     _ptr(status_flag(img_nchw.device), torch.int32) if out_split else None, _stream()), "estd_stem7_conv")
+    _pe(t, "stem_conv", 2.0 * 147 * 64 * N * Ho * Wo, 4.0 * N * (3 * H * W + 64 * Ho * Wo))
+    return out
+
+
+def maxpool3x3s2_vol4(x4, out=None, in_split=False, out_split=False):
+    """MaxPool2d(3, stride 2, pad 1) over vol4 maps [C/4,N,H,W,4] -> [C/4,N,Ho,Wo,4]; either side may be pre-split (vol4s)."""
+    chunks, N, H, W, _ = x4.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty(chunks, N, Ho, Wo, 4, device=x4.device, dtype=torch.float32) if out is None else out
+    t = _pb()
+    check(_lib.get().estd_maxpool3x3s2_vol4(_ptr(x4), _ptr(out), chunks, N, H, W, int(bool(in_split)), int(bool(out_split)),
+                                            _ptr(status_flag(x4.device), torch.int32) if out_split else None, _stream()), "estd_maxpool3x3s2_vol4")
+    _pe(t, "layout", 0.0, 16.0 * chunks * N * (H * W + Ho * Wo))
+    return out
+
+
 def vol4_to_nchw(v, out=None):
     chunks, N, H, W, _ = v.shape
     out = torch.empty(N, chunks * 4, H, W, device=v.device, dtype=torch.float32) if out is None else out

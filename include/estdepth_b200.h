@@ -219,6 +219,17 @@ ESTD_API int estd_nchw_to_vol4(const float* nchw, float* vol4, int N, int C, int
  * optional device int OR-ed with 1 when a value leaves the fp16 range (out_split only). */
 ESTD_API int estd_stem_conv(const float* img_nchw, const float* weight, const float* bias, float* out_vol4, int N, int H, int W,
                    int out_split, int* status, void* stream);
+/* First layer of the context encoder: torchvision ResNet conv1 = Conv2d(3, 64, 7, stride 2, pad 3) + folded BN + ReLU
+ * (hybrid_models/resnet_encoder.py:40-51: encoder.conv1 / bn1 / relu) from the NCHW image stack [N][3][H][W] into vol4
+ * [16][N][Ho][Wo][4], Ho = (H - 1) / 2 + 1.  weight: TAP-MAJOR [3][7][7][64] (the PyTorch weight permuted (1, 2, 3, 0)) with the
+ * BN multiplier folded in, bias: [64].  out_split / status as for estd_stem_conv. */
+ESTD_API int estd_stem7_conv(const float* img_nchw, const float* weight, const float* bias, float* out_vol4, int N, int H, int W,
+                    int out_split, int* status, void* stream);
+/* MaxPool2d(kernel 3, stride 2, pad 1) (torchvision ResNet `maxpool`, run at resnet_encoder.py:46) over a stack of maps in vol4:
+ * [chunks][N][H][W][4] -> [chunks][N][Ho][Wo][4], Ho = (H - 1) / 2 + 1; chunks even.  in_split / out_split: the tensors are
+ * pre-split (vol4s); status as for estd_stem_conv. */
+ESTD_API int estd_maxpool3x3s2_vol4(const float* in_vol4, float* out_vol4, int chunks, int N, int H, int W, int in_split, int out_split,
+                           int* status, void* stream);
 ESTD_API int estd_vol4_to_nchw(const float* vol4, float* nchw, int N, int C, int H, int W, void* stream);
 /* vol4 [C/4][N][H][W][4] = bilinear resize (align_corners = 0, ATen upsample_bilinear2d arithmetic) of relu?(src + bias[c]),
  * src NCHW [N][C][h][w]; bias may be NULL.  Replaces conv-bias/ReLU + F.upsample + torch.cat of the SPP branches

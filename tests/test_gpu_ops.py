@@ -625,3 +625,43 @@ def test_stem_conv_matches_conv2d_bn_relu(shape):
     split = ops.stem_conv(img.to(DEV), w.to(DEV), b.to(DEV), out_split=True)
     assert torch.equal(split, ops.to_split(got))
     ops.check_status(torch.device(DEV))
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 128), (3, 37, 53), (1, 10, 130)], ids=["even", "odd", "wide"])
+def test_stem7_conv_matches_conv2d_bn_relu(shape):
+    """torchvision ResNet conv1 + bn1 + relu (resnet_encoder.py:40-51): Conv2d(3, 64, 7, stride 2, pad 3) with the BN folded in, straight
+    from NCHW images into vol4 (fp32 and pre-split); tiles of 5 x 64 output pixels, so ragged and multi-tile sizes are covered."""
+    N, H, W = shape
+    g = torch.Generator().manual_seed(10)
+    img = torch.rand(N, 3, H, W, generator=g) * 2 - 1
+    w = torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5
+    b = torch.randn(64, generator=g) / 3
+    want = F.relu(F.conv2d(img.double(), w.double(), b.double(), stride=2, padding=3)).float()
+    wt = w.permute(1, 2, 3, 0).contiguous().to(DEV)                # tap-major [3, 7, 7, 64]
+    got = ops.stem7_conv(img.to(DEV), wt, b.to(DEV))
+    assert tuple(got.shape) == (16, N, want.shape[2], want.shape[3], 4)
+    assert maxdiff(ops.vol4_to_nchw(got).cpu(), want) < 5e-6
+    split = ops.stem7_conv(img.to(DEV), wt, b.to(DEV), out_split=True)
+    assert torch.equal(split, ops.to_split(got))
+    ops.check_status(torch.device(DEV))
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 24), (3, 37, 53)], ids=["even", "odd"])
+def test_maxpool3x3s2_vol4_matches_max_pool2d(shape):
+    """torchvision ResNet maxpool = MaxPool2d(3, stride 2, pad 1) over vol4 maps, fp32 and pre-split on either side (bit-exact: a
+    maximum of stored values; the pre-split form holds 22 significant bits of each)."""
+    N, H, W = shape
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(N, 16, H, W, generator=g)
+    want = F.max_pool2d(x, 3, stride=2, padding=1)
+    x4 = ops.nchw_to_vol4(x.to(DEV))
+    got = ops.maxpool3x3s2_vol4(x4)
+    assert torch.equal(ops.vol4_to_nchw(got).cpu(), want)
+    xs = ops.to_split(x4)
+    want_s = F.max_pool2d(ops.vol4_to_nchw(ops.from_split(xs)).cpu(), 3, stride=2, padding=1)      # the values the split form holds
+    got_s = ops.maxpool3x3s2_vol4(xs, in_split=True)
+    assert torch.equal(ops.vol4_to_nchw(got_s).cpu(), want_s)
+    got_ss = ops.maxpool3x3s2_vol4(xs, in_split=True, out_split=True)
+    assert torch.equal(ops.from_split(got_ss), got_s)
+    assert torch.equal(ops.maxpool3x3s2_vol4(x4, out_split=True), ops.to_split(got))
+    ops.check_status(torch.device(DEV))
