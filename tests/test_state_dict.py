@@ -85,3 +85,21 @@ def test_forward_and_constructor_signatures_are_drop_in():
     # the shim the eval drivers import (eval_hybrid.py:11, eval_hybrid_seq.py:10)
     from hybrid_models.model_hybrid import DepthNetHybrid as Shim
     assert Shim is DepthNetHybrid
+
+
+def test_direct_stem_kernels_are_used_for_torchvision_stems_only():
+    """encoders.ContextEncoder._plain_stem: the library's 7x7/2 convolution and 3x3/2 max-pool kernels implement exactly
+    torchvision's stem (resnet_encoder.py:40-51 runs encoder.conv1 / bn1 / relu / maxpool); anything else keeps the cuDNN path."""
+    from estdepth_b200.encoders import ContextEncoder
+    for layers in (18, 50):
+        enc = ContextEncoder(layers)
+        assert ContextEncoder._plain_stem(enc.encoder)
+    enc = ContextEncoder(18)
+    enc.encoder.maxpool = torch.nn.MaxPool2d(3, stride=2, padding=1, ceil_mode=True)
+    assert not ContextEncoder._plain_stem(enc.encoder)
+    enc = ContextEncoder(18)
+    enc.encoder.conv1 = torch.nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=True)
+    assert not ContextEncoder._plain_stem(enc.encoder)
+    enc = ContextEncoder(18)
+    enc.encoder.conv1 = torch.nn.Conv2d(3, 64, 7, stride=1, padding=3, bias=False)
+    assert not ContextEncoder._plain_stem(enc.encoder)
