@@ -684,10 +684,12 @@ def run_ours(args):
     dom = max(((k, v) for k, v in kernels.items() if "share_ms_per_step" in v), key=lambda kv: kv[1]["share_ms_per_step"])
     conv = kernels.get(conv_name, dom[1])
     mma_per_flop = {"fp32": 0.0}.get(model.precision, 3.0)
-    # dram__bytes_read.sum + dram__bytes_write.sum of one 32->32 launch at cfg2 size from the committed ncu --set full capture
-    # (profiles/kernels_r01_final.txt): CTA-pair kernel 217.5 + 115.2 MB against 314.6 MB algorithmic (157.3 MB read + 157.3 MB
-    # written; the reads carry the 18x34 / 16x32 halo, part of the output is still in L2 when the kernel ends)
-    traffic = {"3xf16r2": 332.6e6, "3xf16r": 375.8e6}.get(model.precision) if args.workload == "cfg2" else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of one plain 32->32 launch at cfg2 size from the committed ncu --set full captures
+    # (two-accumulator CTA-pair kernel, profiles/conv3d_kernels_r02.txt: 195.5 + 122.0 MB, mean of six launches; round 1,
+    # profiles/kernels_r01_final.txt: single-accumulator CTA-pair kernel 217.5 + 115.2 MB, single-CTA ring 375.8 MB) against 314.6 MB
+    # algorithmic (157.3 MB read + 157.3 MB written; the reads carry the 18x18 halo, part of the output is still in L2 when the
+    # kernel ends)
+    traffic = {"3xf16r2d": 317.5e6, "3xf16r2": 332.6e6, "3xf16r": 375.8e6}.get(model.precision) if args.workload == "cfg2" else None
     kname = {"3xf16r": "estd::ring::conv3d_ring_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule, fp16 two-term split)",
              "3xf16r2": "estd::ring2::conv3d_ring2_kernel (3x3x3 implicit GEMM on tcgen05, plane-ring schedule on CTA pairs / "
                         "cta_group::2, fp16 two-term split)",
@@ -697,6 +699,8 @@ def run_ours(args):
     roofline = {"kernel": kname if conv_name in kernels else dom[0], "bound": "tensor",
                 "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
+                "traffic_note": "bytes per plain 32->32 launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, "
+                                "profiles/conv3d_kernels_r02.txt); algorithmic: 314.6e6",
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "share_of_step": conv.get("share_of_step"),
                 "note": "achieved = ALGORITHMIC fp32 conv flops (54*Cin*Cout*Vx) / CUDA-event time, averaged over the step's launches; the "
